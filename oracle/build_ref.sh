@@ -1,0 +1,23 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE.  Builds the reference's own CPU path (project.cu, compiled where it
+# lies under /root/reference, unmodified, via oracle/ref_harness.cu) into oracle/_ref/.
+# One binary per body count because N_BODIES is a compile-time array size in the reference
+# (project.cu:1-3, :38-43).  Outputs go ONLY to oracle/_ref/ (git-ignored, travels with gpurun).
+#
+#   oracle/build_ref.sh 40000 1000000        -> oracle/_ref/ref_harness_N40000, ..._N1000000
+set -euo pipefail
+here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+ref="${BH_REFERENCE_ROOT:-/root/reference}/implementation/project.cu"
+if [ ! -f "$ref" ]; then
+    echo "build_ref: $ref not present (GPU box?) - keeping prebuilt oracle/_ref as is" >&2
+    exit 0
+fi
+mkdir -p "$here/_ref"
+for n in "$@"; do
+    out="$here/_ref/ref_harness_N$n"
+    if [ -x "$out" ] && [ "$out" -nt "$here/ref_harness.cu" ] && [ "$out" -nt "$ref" ]; then continue; fi
+    # -O2 as in SURVEY 8(c); host code only ever executes; static cudart so the binary is self-contained.
+    nvcc -O2 -w -std=c++17 -DN_BODIES="$n" -DREF_SOURCE="\"$ref\"" \
+         -o "$out" "$here/ref_harness.cu"
+    echo "built $out"
+done

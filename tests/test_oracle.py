@@ -1,0 +1,132 @@
+"""CPU suite: pins the oracle (oracle/bh_oracle.c) against golden vectors produced by the
+reference's own CPU functions (tests/golden/make_golden.py), bit for bit."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden_inputs, load_golden
+from gpu_nbody_simulation_b200 import initial_conditions as ic
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+FULL_CASES = ["shipped_2048", "clustered_1000", "tiny_1", "tiny_2_coincident", "tiny_5"]
+
+
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_oracle_bit_exact_full_cases(name):
+    pos, vel, mass, g = golden_inputs(name)
+    p, v = pos.copy(), vel.copy()
+    for s in range(int(g["steps"])):
+        tree = oracle.Tree(p, mass)
+        assert np.array_equal(tree.nodes(), g[f"tree{s}"], equal_nan=True), f"{name}: node table differs at step {s}"
+        f, _ = tree.forces()
+        assert np.array_equal(f, g[f"forces{s}"], equal_nan=True)
+        a, v, p = oracle.update(f, mass, v, p, 1.0)
+        assert np.array_equal(a, g[f"acc{s}"], equal_nan=True)
+        assert np.array_equal(v, g[f"vel_after{s}"], equal_nan=True)
+        assert np.array_equal(p, g[f"pos_after{s}"], equal_nan=True)
+
+
+def test_oracle_shipped_40000_digests(shipped40k):
+    g = shipped40k
+    p, v, mass = g["pos"].copy(), g["vel"].copy(), g["mass"]
+    sub = int(g["sub"])
+    for s in range(int(g["steps"])):
+        tree = oracle.Tree(p, mass)
+        nodes = tree.nodes()
+        assert nodes.shape[0] == int(g[f"nodes{s}"])
+        assert sha(nodes) == str(g[f"tree_sha{s}"])
+        f, cnt = tree.forces(nthreads=oracle.max_threads())
+        assert sha(f) == str(g[f"forces_sha{s}"])
+        assert np.array_equal(f[::sub], g[f"forces_sub{s}"])
+        a, v, p = oracle.update(f, mass, v, p, 1.0)
+        assert sha(p) == str(g[f"pos_sha{s}"]) and sha(v) == str(g[f"vel_sha{s}"])
+        if s == 0:
+            # facts recorded in SURVEY.md 8(c) for the shipped data
+            assert nodes.shape[0] == 95353
+            assert cnt["self_skips"] == 32097
+            assert cnt["interactions"] == 7957239 and cnt["visits"] == 12412432
+            assert abs(nodes[0, 6] - 58554.6) < 0.05
+        if s == 1:
+            assert nodes.shape[0] == 265      # the tree collapses after one step
+
+
+def test_oracle_shipped_depth_histogram(shipped40k):
+    g = shipped40k
+    tree = oracle.Tree(g["pos"], g["mass"])
+    canon = tree.canonical()
+    hist = np.bincount(canon[:, 0].astype(int), minlength=10)
+    assert hist.tolist() == [1, 4, 16, 64, 256, 784, 3136, 11664, 39580, 39848]
+    leaves = canon[canon[:, 9] == 0]
+    assert leaves.shape[0] == 71515
+    assert int((leaves[:, 5] == 0).sum()) == 35604                    # empty leaves
+    assert int((leaves[:, 8] >= 0).sum()) == 16793                    # single occupant, above cap
+    assert int((leaves[:, 8] <= -2).sum()) == 15304                   # single occupant at cap
+    assert int(((leaves[:, 8] == -1) & (leaves[:, 5] > 0)).sum()) == 3814  # multi-body cap leaves
+
+
+def test_oracle_disk_1m_tree_digest(disk1m_golden):
+    """BASELINE config 2 inputs regenerate from the seed; the oracle tree matches the reference's."""
+    g = disk1m_golden
+    pos, vel, mass = ic.uniform_disk(1_000_000, seed=12345)
+    assert sha(np.concatenate([mass, pos.ravel(), vel.ravel()])) == str(g["inputs_sha"])
+    tree = oracle.Tree(pos, mass)
+    nodes = tree.nodes()
+    assert nodes.shape[0] == int(g["nodes0"]) == 193473
+    assert sha(nodes) == str(g["tree_sha0"])
+    sub = int(g["sub"])
+    f, _ = tree.forces(i0=0, stride=sub, nthreads=oracle.max_threads())
+    assert np.array_equal(f[::sub], g["forces_sub0"])
+
+
+def test_oracle_keys_follow_insertion_path(shipped40k):
+    """Bisection keys == the path QuadInsert takes: every single-occupant leaf's cell prefix."""
+    g = shipped40k
+    pos, mass = g["pos"][:5000], g["mass"][:5000]
+    tree = oracle.Tree(pos, mass)
+    b = oracle.root_bounds(pos)
+    keys = oracle.body_keys(pos, b, 10)
+    nodes = tree.nodes()
+    # walk from the root along each body's key; must end in a leaf that holds the body
+    for i in range(0, 5000, 7):
+        ni, depth = 0, 1
+        while nodes[ni, 0] != -1:
+            q = (int(keys[i]) >> (2 * (9 - depth))) & 3
+            ni = int(nodes[ni, q])
+            depth += 1
+        occ = int(nodes[ni, 11])
+        assert occ == i or occ == -i - 2 or (occ == -1 and depth == 10)
+
+
+def test_oracle_dump_format(tmp_path, shipped40k):
+    g = shipped40k
+    tree = oracle.Tree(g["pos"][:300], g["mass"][:300])
+    path = os.path.join(tmp_path, "quadtree_init_cpu.txt")
+    tree.dump(path)
+    lines = open(path).read().splitlines()
+    assert len(lines) == tree.size
+    import re
+    pat = re.compile(r"occupantIndex=(-?\d+)\s+occupantPos=\(([-0-9.e+]+),([-0-9.e+]+)\)")  # plot_quadtree.py:7-9
+    assert lines[0].split()[0] == "0"
+    n_occ = 0
+    for ln in lines:
+        tok = ln.split()
+        assert len(tok) >= 6
+        if "occupantIndex" in ln:
+            assert pat.search(ln)
+            n_occ += 1
+    assert n_occ > 300
+
+
+def test_direct_sum_small():
+    pos = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 2.0]])
+    mass = np.array([1.0, 2.0, 3.0])
+    f = oracle.direct_forces(pos, mass, G=1.0)
+    assert np.allclose(f[0], [2.0, 3.0 / 4.0])
+    assert np.allclose(f.sum(axis=0), 0.0, atol=1e-15)
