@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the Barnes-Hut hot path (BASELINE.json: body·steps/s, theta = 0.5, 2-D).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1] — 1 000 000 bodies, uniform disk R = 0.1, seed
+12345, the reference's constants (G, dt = 1, theta = 0.5, depth cap 10).  A *step* is one pass of
+the whole hot path: bounds -> cell keys -> radix sort -> tree + COM -> traversal -> integrate.
+Because the reference's own physics flings bodies away after ONE step and the tree collapses to
+a few hundred nodes, every step starts from the initial distribution (the
+restore of positions / velocities is inside the timed region) — i.e. every timed step does the
+full-size, non-degenerate work of the reference's step 0.  At N > 1 GPUs the body count grows with
+N (weak scaling, 1M bodies per GPU, Morton-sharded, NCCL all-gather of positions every step).
+
+`value`  : device-resident throughput, inputs in HBM, CUDA events on the library's stream.
+`e2e`    : same step through the C-ABI with HOST buffers: pinned H2D of positions, velocities and
+           masses + step + D2H of positions every step, wall clock around the synchronous calls.
+`roofline`: traversal kernel, 20 flop per accepted interaction against the FP32
+           FMA peak measured by a register-resident FMA loop on the same device.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BODIES_PER_GPU = 1_000_000
+SEED = 12345
+FLOP_PER_INTERACTION = 20.0
+METRIC = "body_steps_per_s"
+UNIT = "body·steps/s"
+
+
+def make_workload(n):
+    from gpu_nbody_simulation_b200 import initial_conditions as ic
+    return ic.uniform_disk(n, seed=SEED)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(n_bodies, steps, warmup, budget_s=150.0):
+    """Times the reference's OWN CPU path (oracle/_ref, unmodified project.cu functions, 1 thread —
+    the reference has no threading) or, if it was not built, the oracle port.  Every step restarts
+    from the initial distribution, like the GPU arm.  Returns (value, info)."""
+    import oracle
+    est_per_step = {1_000_000: 10.5, 262_144: 2.6, 65_536: 0.6}
+    total = steps + warmup
+    choice = None
+    for n in (1_000_000, 262_144, 65_536):
+        if n <= n_bodies and oracle.ref_available(n) and est_per_step[n] * total <= budget_s:
+            choice = n
+            break
+    pos, vel, mass = make_workload(1_000_000)
+    if choice is not None:
+        p, v, m = pos[:choice], vel[:choice], mass[:choice]
+        _, tim = oracle.run_ref(p, v, m, steps=total, dump="", keep_dump=False, reset_each_step=True)
+        timed = tim[warmup:]
+        secs = sum(t["build_us"] + t["force_us"] + t["update_us"] for t in timed) * 1e-6
+        value = choice * len(timed) / secs
+        info = {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": (f"{len(timed)} full steps (buildTree + computeForces + update*) of the reference's own CPU "
+                           f"functions on the first {choice} bodies of the 1M uniform disk, restarted from the initial "
+                           f"distribution every step; build {sum(t['build_us'] for t in timed) / len(timed) / 1e3:.0f} ms, "
+                           f"force {sum(t['force_us'] for t in timed) / len(timed) / 1e3:.0f} ms per step"),
+                "ms_per_step": secs / len(timed) * 1e3}
+        return value, info
+    # oracle port: full tree build, forces on a strided subset, single thread
+    stride = 64
+    t0 = time.perf_counter()
+    tree = oracle.Tree(pos, mass)
+    t1 = time.perf_counter()
+    tree.forces(stride=stride, nthreads=1)
+    t2 = time.perf_counter()
+    secs = (t1 - t0) + (t2 - t1) * stride
+    value = 1_000_000 / secs
+    return value, {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"oracle port: full 1M tree build + forces for every {stride}th body, extrapolated",
+                   "ms_per_step": secs * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, info = cpu_reference_run(1_000_000, args.steps, args.warmup)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "uniform disk N=1M, theta=0.5, reference constants, every step from the initial "
+                                   "distribution (CPU reference path, see cpu_baseline.sample)"},
+            "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import gpu_nbody_simulation_b200 as bh
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n = BODIES_PER_GPU * world
+    pos, vel, mass = make_workload(n)
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sim = bh.Simulation(n, device=local, rank=rank, n_ranks=world)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(bh.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        sim.attach_nccl(bytes(idt.cpu().numpy().tobytes()))
+    sim.set_bodies(pos, vel, mass)
+    sim.snapshot()
+
+    # ---- device-resident timing -------------------------------------------------------------------
+    # L2 is flushed (512 MB written) before every timed step; each step is timed on its own with
+    # CUDA events on the library's stream and the K durations are summed.
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush_l2(i):
+        flush_buf.fill_(i & 0xFF)
+        torch.cuda.synchronize()
+
+    def timed_steps(k):
+        tot = 0.0
+        for i in range(k):
+            flush_l2(i)
+            sim.step_from_snapshot(1)
+            tot += sim.last_step_ms()
+        return tot
+
+    sim.step_from_snapshot(W)
+    sim.synchronize()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    sim.reset_timers()
+    ms = timed_steps(K)
+    barrier()
+    ms = max_over_ranks(ms)
+    launches = sim.timers()["kernel_launches"]
+    # back-to-back variant (no flush, one call, events around all K steps): how a real run behaves
+    sim.step_from_snapshot(K)
+    barrier()
+    ms_b2b = max_over_ranks(sim.last_step_ms())
+    clocks = sampler.stop()
+    value = n * K / (ms * 1e-3)
+
+    # ---- per-phase events + interaction count (second pass, direct launches, same work) -----------
+    simc = bh.Simulation(n, device=local, rank=rank, n_ranks=1, counters=True) if world == 1 else None
+    phases, inter_per_step, roofline = None, None, None
+    if rank == 0 and simc is not None:
+        simc.set_bodies(pos, vel, mass)
+        simc.snapshot()
+        simc.step_from_snapshot(1)
+        simc.synchronize()
+        cnt = simc.counters()
+        inter_per_step = cnt["interactions"]
+        simc.close()
+        sim.set_profiling(True)
+        sim.step_from_snapshot(2)
+        sim.reset_timers()
+        timed_steps(K)
+        sim.synchronize()
+        t = sim.timers()
+        sim.set_profiling(False)
+        phases = {k: t[k] / max(t["steps"], 1) for k in ("bounds_keys_us", "sort_us", "build_us", "traverse_us",
+                                                         "exchange_us", "total_us")}
+        peak_tf, mhz = bh.measure_fp32_peak(local)
+        trav_s = phases["traverse_us"] * 1e-6
+        achieved = inter_per_step * FLOP_PER_INTERACTION / trav_s / 1e12
+        roofline = {"bound": "fp32", "kernel": "traverse_kernel<fp32,integrate>", "achieved": achieved,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                    "peak_source": f"measured here: FFMA loop, {peak_tf:.1f} TFLOP/s (implies {mhz:.0f} MHz at 128 FMA/clk/SM); "
+                                   "FP32 peak is not in MEASURED_PEAKS.json (SURVEY 8d)",
+                    "interactions_per_step": inter_per_step, "flop_per_interaction": FLOP_PER_INTERACTION,
+                    "kernel_us": phases["traverse_us"],
+                    "kernel_timing": "cudaEvents around the kernel on the library's stream, averaged over a second pass "
+                                     "of the same K steps with direct launches (the timed pass replays a CUDA graph)",
+                    "interactions_per_s": inter_per_step / trav_s}
+        # whole-step HBM view: mandatory body traffic (72 B/body FP64 state) vs measured copy peak
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            src = "MEASURED_PEAKS.json"
+        except Exception:
+            hbm_peak, src = 6650.0, "fallback"
+        roofline["hbm_view"] = {"bytes_per_body_step": 72, "achieved_gbs": 72.0 * n / (ms / K * 1e-3) / 1e9,
+                                "peak_gbs": hbm_peak, "peak_source": src,
+                                "note": "the step is FP32-issue bound, not HBM bound (SURVEY 8d)"}
+
+    # ---- end to end through the C-ABI with host buffers --------------------------------------------
+    hp = torch.from_numpy(pos).pin_memory()
+    hv = torch.from_numpy(vel).pin_memory()
+    hm = torch.from_numpy(mass).pin_memory()
+    hout = torch.empty((n, 2), dtype=torch.float64).pin_memory()
+    for _ in range(max(1, min(W, 3))):
+        sim.set_bodies(hp, hv, hm); sim.step(1); sim.positions(hout)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        sim.set_bodies(hp, hv, hm)      # H2D of this step's inputs (pinned)
+        sim.step(1)
+        sim.positions(hout)             # D2H of this step's result (synchronizes)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": n * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(40 * n), "d2h_bytes_per_step": int(16 * n),
+           "ms_per_step": e2e_s / K * 1e3}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        _, cpu_baseline = cpu_reference_run(1_000_000, 1, 0, budget_s=30.0)
+        cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (double-float displacement; FP64 state, tree and integrator)", "data": "synthetic",
+                "config": {"workload": f"uniform disk N={n} ({BODIES_PER_GPU} per GPU), R=0.1, seed {SEED}, theta=0.5, "
+                                       "G=6.67e-11, dt=1, depth cap 10; every step restarts from the initial distribution "
+                                       "(device-to-device restore inside the timed region)",
+                           "l2": "flushed before every timed step (512 MB written); steps timed one by one with CUDA "
+                                 "events and summed; value_back_to_back is the same K steps in one call without flush",
+                           "parallelism": f"morton-shard x{world}" if world > 1 else "single GPU"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "phases_us": phases,
+                "value_back_to_back": n * K / (ms_b2b * 1e-3)}
+        print(json.dumps(line), flush=True)
+    sim.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

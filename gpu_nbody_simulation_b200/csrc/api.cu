@@ -1,0 +1,734 @@
+// C-ABI of libbh.so: context life cycle, the per-step kernel sequence (optionally replayed as a
+// CUDA graph), multi-GPU position exchange over NCCL, getters in original body order.
+// See include/bh.h for the contract and the reference lines each entry point replaces.
+#include <dlfcn.h>
+#include <nccl.h>   // types only; the library is dlopen'ed so that libbh.so has no hard NCCL dependency
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "bh_internal.h"
+#include "host_io.h"
+
+namespace bh {
+
+thread_local uint64_t g_launches = 0;
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+// ---- NCCL through dlopen ---------------------------------------------------------------------
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.handle ? &api : nullptr;
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_NOLOAD); if (h) break; }   // torch's copy if loaded
+    if (!h) for (const char* nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) { set_error("libnccl not loadable: %s", dlerror()); return nullptr; }
+#define BH_SYM(field, name)                                                        \
+    api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name));            \
+    if (!api.field) { set_error("libnccl lacks %s", name); return nullptr; }
+    BH_SYM(GetUniqueId, "ncclGetUniqueId");
+    BH_SYM(CommInitRank, "ncclCommInitRank");
+    BH_SYM(CommDestroy, "ncclCommDestroy");
+    BH_SYM(Broadcast, "ncclBroadcast");
+    BH_SYM(GroupStart, "ncclGroupStart");
+    BH_SYM(GroupEnd, "ncclGroupEnd");
+    BH_SYM(GetErrorString, "ncclGetErrorString");
+#undef BH_SYM
+    api.handle = h;
+    return &api;
+}
+
+#define BH_NCCL_OK(api, expr)                                                                   \
+    do {                                                                                        \
+        ncclResult_t r__ = (expr);                                                              \
+        if (r__ != ncclSuccess) {                                                               \
+            set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, (api)->GetErrorString(r__)); \
+            return BH_ERR_NCCL;                                                                 \
+        }                                                                                       \
+    } while (0)
+
+// small helper kernels ---------------------------------------------------------------------------
+__global__ void gather2_kernel(const double2* __restrict__ in, const uint32_t* __restrict__ perm, int64_t n,
+                               double2* __restrict__ out) {   // out[j] = in[perm[j]]
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[j] = in[perm[j]];
+}
+__global__ void gather1_kernel(const double* __restrict__ in, const uint32_t* __restrict__ perm, int64_t n,
+                               double* __restrict__ out) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[j] = in[perm[j]];
+}
+__global__ void scatter2_kernel(const double2* __restrict__ in, const uint32_t* __restrict__ perm, int64_t n,
+                                double2* __restrict__ out) {  // out[perm[j]] = in[j]
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[perm[j]] = in[j];
+}
+
+}  // namespace bh
+
+using namespace bh;
+
+struct bh_ctx {
+    bh_params p;
+    Dims d;
+    SortPlan sp;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    double2 *pos = nullptr, *vel = nullptr, *acc = nullptr, *force = nullptr, *snap_pos = nullptr,
+            *snap_vel = nullptr, *tmp2 = nullptr;
+    double* mass = nullptr;
+    double* tmp1 = nullptr;
+    uint32_t* keys[2] = {nullptr, nullptr};
+    uint32_t* idx[2] = {nullptr, nullptr};
+    int sorted = 0;               // which of keys[]/idx[] holds the sorted result
+    StepConsts* consts = nullptr;
+    TreeArrays tree{};
+    Scratch s{};
+    float4* packed = nullptr;     // direct-sum kernel input
+    // multi-GPU
+    int64_t own_lo = 0, own_hi = 0;
+    uint32_t* own_list = nullptr;
+    uint32_t* own_count = nullptr;
+    uint32_t* perm = nullptr;     // internal index -> original index (n_ranks > 1)
+    bool renumbered = false;
+    ncclComm_t comm = nullptr;
+    // graphs
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};   // [0] plain step, [1] step from snapshot
+    uint64_t graph_kernels[2] = {0, 0};
+    // timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t pev[8] = {};
+    bool profiling = false;
+    bh_timers timers{};
+    uint64_t launches_base = 0;
+    bool bodies_set = false, tree_valid = false, have_snapshot = false, timed = false;
+    int bounds_grid = 1;
+};
+
+namespace {
+
+int compute_dims(const bh_params& p, Dims& d, SortPlan& sp) {
+    d.n = p.n_bodies;
+    d.max_depth = p.max_depth;
+    d.finest = p.max_depth - 1;
+    uint64_t off = 0;
+    for (int l = 0; l <= kMaxLevels; ++l) {
+        d.level_off[l] = off;
+        if (l <= d.finest) off += 1ull << (2 * l);
+    }
+    d.ncells_finest = 1ull << (2 * d.finest);
+    d.npyramid = off;
+    sp.key_bits = 2 * d.finest;
+    int bits = sp.key_bits < 1 ? 1 : sp.key_bits;
+    sp.passes = (bits + 8) / 9;
+    sp.bits_per_pass = (bits + sp.passes - 1) / sp.passes;
+    sp.nbins_log2 = sp.bits_per_pass <= 8 ? 8 : 9;
+    sp.ntiles = (int)((p.n_bodies + kSortTile - 1) / kSortTile);
+    if (sp.ntiles < 1) sp.ntiles = 1;
+    return BH_OK;
+}
+
+template <typename T>
+int dev_alloc(T** ptr, size_t count) {
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)ptr, count * sizeof(T));
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? BH_ERR_NOMEM : BH_ERR_CUDA;
+    }
+    return BH_OK;
+}
+
+#define BH_TRY(expr) do { int rc__ = (expr); if (rc__ != BH_OK) return rc__; } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int check_launch() {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("kernel launch: %s", cudaGetErrorString(e)); return BH_ERR_CUDA; }
+    return BH_OK;
+}
+
+// All-gather of one owned slice per rank (ragged sizes allowed): grouped broadcasts.
+int exchange_slices(bh_ctx* c, void* base, size_t elem_bytes) {
+    if (c->p.n_ranks <= 1) return BH_OK;
+    NcclApi* api = nccl_api();
+    if (!api || !c->comm) { set_error("multi-rank context without an attached NCCL communicator"); return BH_ERR_NCCL; }
+    BH_NCCL_OK(api, api->GroupStart());
+    for (int r = 0; r < c->p.n_ranks; ++r) {
+        int64_t lo, hi;
+        bh_shard_range(c->p.n_bodies, c->p.n_ranks, r, &lo, &hi);
+        char* ptr = (char*)base + (size_t)lo * elem_bytes;
+        BH_NCCL_OK(api, api->Broadcast(ptr, ptr, (size_t)(hi - lo) * elem_bytes, ncclUint8, r, c->comm, c->stream));
+    }
+    BH_NCCL_OK(api, api->GroupEnd());
+    return BH_OK;
+}
+
+void zero_scratch(bh_ctx* c) {
+    cudaMemsetAsync(c->s.zero_base, 0, c->s.zero_bytes, c->stream);
+    cudaMemsetAsync(c->tree.count + c->d.level_off[c->d.finest], 0, c->d.ncells_finest * sizeof(uint32_t), c->stream);
+    if (c->own_count) cudaMemsetAsync(c->own_count, 0, sizeof(uint32_t), c->stream);
+}
+
+void prof_mark(bh_ctx* c, int i) { if (c->profiling) cudaEventRecord(c->pev[i], c->stream); }
+
+// bounds -> keys -> sort -> tree, on the context's stream
+int enqueue_build(bh_ctx* c) {
+    zero_scratch(c);
+    prof_mark(c, 0);
+    launch_bounds(c->pos, c->d.n, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream);
+    launch_keys(c->pos, c->d.n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream);
+    prof_mark(c, 1);
+    launch_sort(c->keys, c->idx, c->d.n, c->sp, c->s, &c->sorted, c->stream);
+    prof_mark(c, 2);
+    launch_tree(c->keys[c->sorted], c->idx[c->sorted], c->pos, c->mass, c->d.n, c->p, c->d, c->tree, c->s, c->consts,
+                c->stream);
+    if (c->p.n_ranks > 1)
+        launch_own_list(c->idx[c->sorted], c->d.n, c->own_lo, c->own_hi, c->own_list, c->own_count, c->stream);
+    prof_mark(c, 3);
+    return check_launch();
+}
+
+int enqueue_forces(bh_ctx* c, bool integrate) {
+    const bool multi = c->p.n_ranks > 1;
+    launch_traverse(c->keys[c->sorted], c->idx[c->sorted], c->pos, c->vel, c->acc, c->force, c->mass, c->d.n,
+                    c->own_lo, c->own_hi, multi ? c->own_list : nullptr, c->own_count,
+                    multi ? (c->own_hi - c->own_lo) : c->d.n, c->p, c->d, c->tree, c->consts, c->s.counters, integrate,
+                    c->stream);
+    prof_mark(c, 4);
+    return check_launch();
+}
+
+int enqueue_step(bh_ctx* c, bool from_snapshot) {
+    if (from_snapshot) {
+        cudaMemcpyAsync(c->pos, c->snap_pos, sizeof(double2) * c->d.n, cudaMemcpyDeviceToDevice, c->stream);
+        cudaMemcpyAsync(c->vel, c->snap_vel, sizeof(double2) * c->d.n, cudaMemcpyDeviceToDevice, c->stream);
+    }
+    BH_TRY(enqueue_build(c));
+    BH_TRY(enqueue_forces(c, true));
+    if (c->p.n_ranks > 1) BH_TRY(exchange_slices(c, c->pos, sizeof(double2)));
+    prof_mark(c, 5);
+    return BH_OK;
+}
+
+void accumulate_profile(bh_ctx* c) {
+    if (!c->profiling) return;
+    cudaEventSynchronize(c->pev[5]);
+    float ms[5];
+    for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&ms[i], c->pev[i], c->pev[i + 1]);
+    c->timers.bounds_keys_us += ms[0] * 1e3;
+    c->timers.sort_us += ms[1] * 1e3;
+    c->timers.build_us += ms[2] * 1e3;
+    c->timers.traverse_us += ms[3] * 1e3;   // traversal with the fused integrator
+    c->timers.exchange_us += ms[4] * 1e3;
+    c->timers.total_us += (ms[0] + ms[1] + ms[2] + ms[3] + ms[4]) * 1e3;
+    c->timers.steps += 1;
+}
+
+int run_steps(bh_ctx* c, int nsteps, bool from_snapshot) {
+    if (!c->bodies_set) { set_error("bh_step before bh_set_bodies"); return BH_ERR_INVALID; }
+    if (from_snapshot && !c->have_snapshot) { set_error("no snapshot taken"); return BH_ERR_INVALID; }
+    if (nsteps < 0) { set_error("nsteps < 0"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    const bool use_graph = !(c->p.flags & BH_FLAG_NO_GRAPH) && !c->profiling && c->p.n_ranks == 1;
+    const int gi = from_snapshot ? 1 : 0;
+    BH_CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+    if (use_graph && nsteps > 0) {
+        if (!c->graph[gi]) {
+            cudaGraph_t graph = nullptr;
+            uint64_t before = g_launches;
+            BH_CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = enqueue_step(c, from_snapshot);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+            if (rc != BH_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) { set_error("stream capture: %s", cudaGetErrorString(e)); return BH_ERR_CUDA; }
+            c->graph_kernels[gi] = g_launches - before;
+            g_launches = before;   // capture launched nothing
+            BH_CUDA_OK(cudaGraphInstantiate(&c->graph[gi], graph, 0));
+            cudaGraphDestroy(graph);
+        }
+        for (int s = 0; s < nsteps; ++s) {
+            BH_CUDA_OK(cudaGraphLaunch(c->graph[gi], c->stream));
+            g_launches += c->graph_kernels[gi];
+        }
+    } else {
+        for (int s = 0; s < nsteps; ++s) {
+            BH_TRY(enqueue_step(c, from_snapshot));
+            accumulate_profile(c);
+        }
+    }
+    BH_CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true;
+    if (nsteps > 0) c->tree_valid = true;
+    return BH_OK;
+}
+
+int copy_out2(bh_ctx* c, const double2* dev, double* host, bool gather_ranks) {
+    if (!host) { set_error("null output buffer"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    if (gather_ranks && c->p.n_ranks > 1) BH_TRY(exchange_slices(c, (void*)dev, sizeof(double2)));
+    const double2* src = dev;
+    if (c->renumbered) {
+        scatter2_kernel<<<(unsigned)((c->d.n + 255) / 256), 256, 0, c->stream>>>(dev, c->perm, c->d.n, c->tmp2);
+        ++g_launches;
+        src = c->tmp2;
+    }
+    BH_CUDA_OK(cudaMemcpyAsync(host, src, sizeof(double2) * c->d.n, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return BH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bh_last_error(void) { return g_err; }
+int bh_abi_version(void) { return BH_ABI_VERSION; }
+
+void bh_default_params(bh_params* p) {
+    memset(p, 0, sizeof *p);
+    p->n_bodies = 40000;
+    p->G = 6.67e-11; p->dt = 1.0; p->theta = 5e-1; p->dist_eps = 1e-15; p->mass_eps = 1e-15;
+    p->pad_frac = 0.1; p->pad_fallback = 1e-6; p->max_depth = 10; p->device = -1; p->flags = 0;
+    p->exact_leaf_max = 64; p->rank = 0; p->n_ranks = 1;
+}
+
+int bh_shard_range(int64_t n, int32_t n_ranks, int32_t rank, int64_t* lo, int64_t* hi) {
+    if (n < 0 || n_ranks < 1 || rank < 0 || rank >= n_ranks || !lo || !hi) {
+        set_error("bh_shard_range: bad arguments");
+        return BH_ERR_INVALID;
+    }
+    *lo = (int64_t)(((__int128)n * rank) / n_ranks);
+    *hi = (int64_t)(((__int128)n * (rank + 1)) / n_ranks);
+    return BH_OK;
+}
+
+int bh_create(const bh_params* p, bh_ctx** out) {
+    if (!p || !out) { set_error("bh_create: null argument"); return BH_ERR_INVALID; }
+    if (p->n_bodies < 1 || p->n_bodies >= (1ll << 30)) { set_error("n_bodies must be in [1, 2^30)"); return BH_ERR_INVALID; }
+    if (p->max_depth < 1 || p->max_depth > kMaxDepthDense) {
+        set_error("max_depth must be in [1, %d] (dense pyramid)", kMaxDepthDense);
+        return BH_ERR_INVALID;
+    }
+    if (p->n_ranks < 1 || p->rank < 0 || p->rank >= p->n_ranks) { set_error("bad rank / n_ranks"); return BH_ERR_INVALID; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+        return BH_ERR_CUDA;
+    }
+    bh_ctx* c = new bh_ctx();
+    c->p = *p;
+    if (p->device >= 0) c->device = p->device; else BH_CUDA_OK(cudaGetDevice(&c->device));
+    if (c->device >= ndev) { set_error("device %d of %d", c->device, ndev); delete c; return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    compute_dims(c->p, c->d, c->sp);
+    const int64_t n = p->n_bodies;
+    int rc = BH_OK;
+    auto fail = [&](int code) { bh_destroy(c); return code; };
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        set_error("cudaStreamCreate: %s", cudaGetErrorString(e));
+        return fail(BH_ERR_CUDA);
+    }
+#define BH_ALLOC(ptr, count) if ((rc = dev_alloc(&(ptr), (size_t)(count))) != BH_OK) return fail(rc)
+    BH_ALLOC(c->pos, n); BH_ALLOC(c->vel, n); BH_ALLOC(c->acc, n); BH_ALLOC(c->force, n); BH_ALLOC(c->mass, n);
+    BH_ALLOC(c->keys[0], n); BH_ALLOC(c->keys[1], n); BH_ALLOC(c->idx[0], n); BH_ALLOC(c->idx[1], n);
+    BH_ALLOC(c->consts, 1);
+    const uint64_t np = c->d.npyramid;
+    BH_ALLOC(c->tree.mass, np); BH_ALLOC(c->tree.comx, np); BH_ALLOC(c->tree.comy, np);
+    BH_ALLOC(c->tree.count, np); BH_ALLOC(c->tree.first, np); BH_ALLOC(c->tree.rec, np);
+    // zeroed scratch block
+    const int nbins = 1 << c->sp.nbins_log2;
+    size_t words = (size_t)kMaxSortPasses * kMaxBins + 16 /*tickets, heavy, bbox ticket*/ + 16 /*8 x u64 counters*/ +
+                   (size_t)c->sp.passes * c->sp.ntiles * nbins;
+    uint32_t* zb = nullptr;
+    BH_ALLOC(zb, words);
+    c->s.zero_base = (uint8_t*)zb;
+    c->s.zero_bytes = words * sizeof(uint32_t);
+    c->s.digit_hist = zb;
+    c->s.tickets = zb + (size_t)kMaxSortPasses * kMaxBins;
+    c->s.heavy_count = c->s.tickets + 8;
+    c->s.bbox_ticket = c->s.tickets + 9;
+    c->s.counters = (unsigned long long*)(c->s.tickets + 16);
+    c->s.tile_state = c->s.tickets + 32;
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, c->device)) != cudaSuccess) { set_error("%s", cudaGetErrorString(e)); return fail(BH_ERR_CUDA); }
+    int64_t bg = (n + 256 * 8 - 1) / (256 * 8);
+    c->bounds_grid = (int)std::max<int64_t>(1, std::min<int64_t>(bg, prop.multiProcessorCount * 4));
+    BH_ALLOC(c->s.bbox_partial, (size_t)c->bounds_grid * 4);
+    BH_ALLOC(c->s.heavy_list, c->d.ncells_finest);
+    if (p->n_ranks > 1) {
+        BH_ALLOC(c->own_list, n); BH_ALLOC(c->own_count, 1); BH_ALLOC(c->perm, n); BH_ALLOC(c->tmp2, n); BH_ALLOC(c->tmp1, n);
+    }
+#undef BH_ALLOC
+    bh_shard_range(n, p->n_ranks, p->rank, &c->own_lo, &c->own_hi);
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    for (auto& ev : c->pev) cudaEventCreate(&ev);
+    cudaMemsetAsync(c->acc, 0, sizeof(double2) * n, c->stream);
+    cudaMemsetAsync(c->force, 0, sizeof(double2) * n, c->stream);
+    cudaMemsetAsync(c->tree.count, 0, sizeof(uint32_t) * np, c->stream);
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { set_error("%s", cudaGetErrorString(e)); return fail(BH_ERR_CUDA); }
+    c->launches_base = g_launches;
+    *out = c;
+    return BH_OK;
+}
+
+int bh_destroy(bh_ctx* c) {
+    if (!c) return BH_OK;
+    DeviceGuard g(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto& gr : c->graph) if (gr) cudaGraphExecDestroy(gr);
+    if (c->comm) { NcclApi* api = nccl_api(); if (api) api->CommDestroy(c->comm); }
+    void* ptrs[] = {c->pos, c->vel, c->acc, c->force, c->snap_pos, c->snap_vel, c->tmp2, c->mass, c->tmp1, c->keys[0],
+                    c->keys[1], c->idx[0], c->idx[1], c->consts, c->tree.mass, c->tree.comx, c->tree.comy,
+                    c->tree.count, c->tree.first, c->tree.rec, c->s.zero_base, c->s.bbox_partial, c->s.heavy_list,
+                    c->packed, c->own_list, c->own_count, c->perm};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    for (auto& ev : c->pev) if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return BH_OK;
+}
+
+int bh_nccl_unique_id(void* id128) {
+    NcclApi* api = nccl_api();
+    if (!api) return BH_ERR_NCCL;
+    ncclUniqueId id;
+    BH_NCCL_OK(api, api->GetUniqueId(&id));
+    memcpy(id128, &id, sizeof id);
+    return BH_OK;
+}
+
+int bh_attach_nccl(bh_ctx* c, const void* id128) {
+    if (!c || !id128) { set_error("null argument"); return BH_ERR_INVALID; }
+    NcclApi* api = nccl_api();
+    if (!api) return BH_ERR_NCCL;
+    DeviceGuard g(c->device);
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    BH_NCCL_OK(api, api->CommInitRank(&c->comm, c->p.n_ranks, id, c->p.rank));
+    return BH_OK;
+}
+
+int bh_set_bodies(bh_ctx* c, const double* pos, const double* vel, const double* mass) {
+    if (!c || !pos || !vel || !mass) { set_error("null argument"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    const int64_t n = c->d.n;
+    if (c->p.n_ranks == 1) {
+        BH_CUDA_OK(cudaMemcpyAsync(c->pos, pos, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
+        BH_CUDA_OK(cudaMemcpyAsync(c->vel, vel, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
+        BH_CUDA_OK(cudaMemcpyAsync(c->mass, mass, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        // Morton renumbering: internal index j = j-th body of the initial cell-key order, so that a
+        // rank's contiguous index slice is a contiguous Morton range of the initial distribution.
+        BH_CUDA_OK(cudaMemcpyAsync(c->pos, pos, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
+        zero_scratch(c);
+        launch_bounds(c->pos, n, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream);
+        launch_keys(c->pos, n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream);
+        launch_sort(c->keys, c->idx, n, c->sp, c->s, &c->sorted, c->stream);
+        BH_CUDA_OK(cudaMemcpyAsync(c->perm, c->idx[c->sorted], sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, c->stream));
+        const unsigned blocks = (unsigned)((n + 255) / 256);
+        BH_CUDA_OK(cudaMemcpyAsync(c->tmp2, pos, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
+        gather2_kernel<<<blocks, 256, 0, c->stream>>>(c->tmp2, c->perm, n, c->pos);
+        BH_CUDA_OK(cudaMemcpyAsync(c->tmp2, vel, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
+        gather2_kernel<<<blocks, 256, 0, c->stream>>>(c->tmp2, c->perm, n, c->vel);
+        BH_CUDA_OK(cudaMemcpyAsync(c->tmp1, mass, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        gather1_kernel<<<blocks, 256, 0, c->stream>>>(c->tmp1, c->perm, n, c->mass);
+        g_launches += 3;
+        c->renumbered = true;
+    }
+    BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    BH_TRY(check_launch());
+    c->bodies_set = true;
+    c->tree_valid = false;
+    return BH_OK;
+}
+
+static int set_vec(bh_ctx* c, double2* dst, const double* src) {
+    if (!c || !src) { set_error("null argument"); return BH_ERR_INVALID; }
+    if (!c->bodies_set) { set_error("bh_set_bodies first"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    const int64_t n = c->d.n;
+    if (!c->renumbered) {
+        BH_CUDA_OK(cudaMemcpyAsync(dst, src, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        BH_CUDA_OK(cudaMemcpyAsync(c->tmp2, src, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
+        gather2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->tmp2, c->perm, n, dst);
+        ++g_launches;
+    }
+    BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->tree_valid = false;
+    return BH_OK;
+}
+int bh_set_positions(bh_ctx* c, const double* pos) { return set_vec(c, c ? c->pos : nullptr, pos); }
+int bh_set_velocities(bh_ctx* c, const double* vel) { return set_vec(c, c ? c->vel : nullptr, vel); }
+
+int bh_snapshot(bh_ctx* c) {
+    if (!c || !c->bodies_set) { set_error("bh_snapshot: no bodies"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    const int64_t n = c->d.n;
+    if (!c->snap_pos) { BH_TRY(dev_alloc(&c->snap_pos, (size_t)n)); BH_TRY(dev_alloc(&c->snap_vel, (size_t)n)); }
+    BH_CUDA_OK(cudaMemcpyAsync(c->snap_pos, c->pos, sizeof(double2) * n, cudaMemcpyDeviceToDevice, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(c->snap_vel, c->vel, sizeof(double2) * n, cudaMemcpyDeviceToDevice, c->stream));
+    BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->have_snapshot = true;
+    return BH_OK;
+}
+
+int bh_restore(bh_ctx* c) {
+    if (!c || !c->have_snapshot) { set_error("bh_restore: no snapshot"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    const int64_t n = c->d.n;
+    BH_CUDA_OK(cudaMemcpyAsync(c->pos, c->snap_pos, sizeof(double2) * n, cudaMemcpyDeviceToDevice, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(c->vel, c->snap_vel, sizeof(double2) * n, cudaMemcpyDeviceToDevice, c->stream));
+    c->tree_valid = false;
+    return BH_OK;
+}
+
+int bh_step(bh_ctx* c, int32_t nsteps) {
+    if (!c) { set_error("null context"); return BH_ERR_INVALID; }
+    return run_steps(c, nsteps, false);
+}
+int bh_step_from_snapshot(bh_ctx* c, int32_t nsteps) {
+    if (!c) { set_error("null context"); return BH_ERR_INVALID; }
+    return run_steps(c, nsteps, true);
+}
+
+int bh_build_tree(bh_ctx* c) {
+    if (!c || !c->bodies_set) { set_error("bh_build_tree: no bodies"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    BH_TRY(enqueue_build(c));
+    c->tree_valid = true;
+    return BH_OK;
+}
+
+int bh_compute_forces(bh_ctx* c) {
+    if (!c || !c->tree_valid) { set_error("bh_compute_forces: build the tree first"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    cudaMemsetAsync(c->s.counters, 0, 4 * sizeof(unsigned long long), c->stream);
+    return enqueue_forces(c, false);
+}
+
+int bh_integrate(bh_ctx* c) {
+    if (!c || !c->bodies_set) { set_error("bh_integrate: no bodies"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    launch_integrate(c->pos, c->vel, c->acc, c->force, c->mass, c->own_lo, c->own_hi, c->p.dt, c->stream);
+    BH_TRY(check_launch());
+    if (c->p.n_ranks > 1) BH_TRY(exchange_slices(c, c->pos, sizeof(double2)));
+    c->tree_valid = false;
+    return BH_OK;
+}
+
+int bh_synchronize(bh_ctx* c) {
+    if (!c) { set_error("null context"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return BH_OK;
+}
+
+int bh_get_positions(bh_ctx* c, double* out) { if (!c) return BH_ERR_INVALID; return copy_out2(c, c->pos, out, false); }
+int bh_get_velocities(bh_ctx* c, double* out) { if (!c) return BH_ERR_INVALID; return copy_out2(c, c->vel, out, true); }
+int bh_get_accelerations(bh_ctx* c, double* out) { if (!c) return BH_ERR_INVALID; return copy_out2(c, c->acc, out, true); }
+int bh_get_forces(bh_ctx* c, double* out) { if (!c) return BH_ERR_INVALID; return copy_out2(c, c->force, out, true); }
+
+int bh_get_bounds(bh_ctx* c, double out4[4]) {
+    if (!c || !c->tree_valid) { set_error("bh_get_bounds: no tree built"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    StepConsts h;
+    BH_CUDA_OK(cudaMemcpyAsync(&h, c->consts, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    out4[0] = h.xmin; out4[1] = h.xmax; out4[2] = h.ymin; out4[3] = h.ymax;
+    return BH_OK;
+}
+
+static int fetch_sorted(bh_ctx* c, std::vector<uint32_t>& keys, std::vector<uint32_t>& idx) {
+    const int64_t n = c->d.n;
+    keys.resize(n); idx.resize(n);
+    BH_CUDA_OK(cudaMemcpyAsync(keys.data(), c->keys[c->sorted], 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(idx.data(), c->idx[c->sorted], 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return BH_OK;
+}
+
+static int fetch_perm(bh_ctx* c, std::vector<uint32_t>& perm) {
+    perm.clear();
+    if (!c->renumbered) return BH_OK;
+    perm.resize(c->d.n);
+    BH_CUDA_OK(cudaMemcpy(perm.data(), c->perm, 4 * c->d.n, cudaMemcpyDeviceToHost));
+    return BH_OK;
+}
+
+int bh_get_body_keys(bh_ctx* c, uint32_t* out) {
+    if (!c || !out || !c->tree_valid) { set_error("bh_get_body_keys: no tree built"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    std::vector<uint32_t> keys, idx, perm;
+    BH_TRY(fetch_sorted(c, keys, idx));
+    BH_TRY(fetch_perm(c, perm));
+    for (int64_t j = 0; j < c->d.n; ++j) {
+        uint32_t b = idx[j];
+        out[perm.empty() ? b : perm[b]] = keys[j];
+    }
+    return BH_OK;
+}
+
+int bh_get_sorted_order(bh_ctx* c, uint32_t* out) {
+    if (!c || !out || !c->tree_valid) { set_error("bh_get_sorted_order: no tree built"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    std::vector<uint32_t> keys, idx, perm;
+    BH_TRY(fetch_sorted(c, keys, idx));
+    BH_TRY(fetch_perm(c, perm));
+    for (int64_t j = 0; j < c->d.n; ++j) out[j] = perm.empty() ? idx[j] : perm[idx[j]];
+    return BH_OK;
+}
+
+int bh_get_tree_size(bh_ctx* c, int64_t* n_nodes) {
+    if (!c || !n_nodes || !c->tree_valid) { set_error("bh_get_tree_size: no tree built"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    unsigned long long v = 0;
+    BH_CUDA_OK(cudaMemcpyAsync(&v, c->s.counters + 4, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    *n_nodes = (int64_t)v;
+    return BH_OK;
+}
+
+static int fetch_host_tree(bh_ctx* c, HostTree& ht) {
+    const uint64_t np = c->d.npyramid;
+    const int64_t n = c->d.n;
+    ht.finest = c->d.finest;
+    for (int l = 0; l <= kMaxLevels; ++l) ht.level_off[l] = c->d.level_off[l];
+    ht.mass.resize(np); ht.comx.resize(np); ht.comy.resize(np); ht.count.resize(np); ht.first.resize(np);
+    ht.sidx.resize(n); ht.pos.resize(2 * n);
+    BH_CUDA_OK(cudaMemcpyAsync(ht.mass.data(), c->tree.mass, 8 * np, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(ht.comx.data(), c->tree.comx, 8 * np, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(ht.comy.data(), c->tree.comy, 8 * np, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(ht.count.data(), c->tree.count, 4 * np, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(ht.first.data(), c->tree.first, 4 * np, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(ht.sidx.data(), c->idx[c->sorted], 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(ht.pos.data(), c->pos, 16 * n, cudaMemcpyDeviceToHost, c->stream));
+    StepConsts h;
+    BH_CUDA_OK(cudaMemcpyAsync(&h, c->consts, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    ht.bounds[0] = h.xmin; ht.bounds[1] = h.xmax; ht.bounds[2] = h.ymin; ht.bounds[3] = h.ymax;
+    BH_TRY(fetch_perm(c, ht.perm));
+    return BH_OK;
+}
+
+int bh_get_tree(bh_ctx* c, double* out_rows, int64_t cap_rows, int64_t* n_rows) {
+    if (!c || !n_rows || !c->tree_valid) { set_error("bh_get_tree: no tree built"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    HostTree ht;
+    BH_TRY(fetch_host_tree(c, ht));
+    *n_rows = canonical_rows(ht, out_rows, cap_rows);
+    return BH_OK;
+}
+
+int bh_dump_quadtree(bh_ctx* c, const char* path) {
+    if (!c || !path || !c->tree_valid) { set_error("bh_dump_quadtree: no tree built"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    HostTree ht;
+    BH_TRY(fetch_host_tree(c, ht));
+    return dump_quadtree_txt(ht, path);
+}
+
+int bh_get_counters(bh_ctx* c, bh_counters* out) {
+    if (!c || !out) { set_error("null argument"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    unsigned long long v[8];
+    uint32_t heavy = 0;
+    BH_CUDA_OK(cudaMemcpyAsync(v, c->s.counters, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(&heavy, c->s.heavy_count, 4, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    memset(out, 0, sizeof *out);
+    out->interactions = v[0]; out->visits = v[1]; out->opens = v[2]; out->warp_steps = v[3]; out->nodes = v[4];
+    out->heavy_cells = heavy;
+    return BH_OK;
+}
+
+int bh_set_profiling(bh_ctx* c, int32_t on) {
+    if (!c) { set_error("null context"); return BH_ERR_INVALID; }
+    c->profiling = on != 0;
+    return BH_OK;
+}
+
+int bh_get_timers(bh_ctx* c, bh_timers* out) {
+    if (!c || !out) { set_error("null argument"); return BH_ERR_INVALID; }
+    *out = c->timers;
+    out->kernel_launches = g_launches - c->launches_base;
+    return BH_OK;
+}
+
+int bh_reset_timers(bh_ctx* c) {
+    if (!c) { set_error("null context"); return BH_ERR_INVALID; }
+    memset(&c->timers, 0, sizeof c->timers);
+    c->launches_base = g_launches;
+    return BH_OK;
+}
+
+int bh_last_step_ms(bh_ctx* c, float* ms) {
+    if (!c || !ms || !c->timed) { set_error("bh_last_step_ms: no timed step"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    BH_CUDA_OK(cudaEventSynchronize(c->ev1));
+    BH_CUDA_OK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return BH_OK;
+}
+
+int bh_direct_forces(bh_ctx* c, double* out, float* device_ms) {
+    if (!c || !c->bodies_set) { set_error("bh_direct_forces: no bodies"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    if (!c->packed) BH_TRY(dev_alloc(&c->packed, (size_t)c->d.n));
+    BH_CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+    launch_direct(c->pos, c->mass, c->d.n, c->p.G, c->packed, c->force, c->stream);
+    BH_CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+    BH_TRY(check_launch());
+    BH_CUDA_OK(cudaEventSynchronize(c->ev1));
+    c->timed = true;
+    if (device_ms) BH_CUDA_OK(cudaEventElapsedTime(device_ms, c->ev0, c->ev1));
+    if (out) return copy_out2(c, c->force, out, false);
+    return BH_OK;
+}
+
+int bh_load_text(const char* mf, const char* pf, const char* vf, int64_t n, double* mass, double* pos, double* vel) {
+    return load_text(mf, pf, vf, n, mass, pos, vel);
+}
+
+int bh_append_positions_txt(const char* path, const double* pos, int64_t n, double time, int truncate) {
+    return append_positions_txt(path, pos, n, time, truncate);
+}
+
+int bh_measure_fp32_peak(int32_t device, double* tflops, double* mhz) {
+    if (!tflops) { set_error("null argument"); return BH_ERR_INVALID; }
+    return measure_fp32_peak(device, tflops, mhz);
+}
+
+}  // extern "C"

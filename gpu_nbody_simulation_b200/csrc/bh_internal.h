@@ -1,0 +1,118 @@
+// Internal declarations shared by the CUDA translation units of libbh.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/bh.h"
+
+namespace bh {
+
+constexpr int kMaxLevels = 16;       // levels 0..max_depth-1 (max_depth <= 13 in the dense pyramid)
+constexpr int kMaxDepthDense = 13;   // 4^12 finest cells * 32 B = 512 MiB of records
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per tile
+constexpr int kMaxSortPasses = 4;
+constexpr int kMaxBins = 512;
+
+// node flags (packed FP32 traversal record and FP64 verification path share them)
+constexpr uint32_t kNodeNonZero = 1u;  // mass > mass_eps         (project.cu:617 / :731)
+constexpr uint32_t kNodeLeaf = 2u;     // all four children == -1 (project.cu:623-626)
+constexpr uint32_t kNodeSingle = 4u;   // exactly one body inside (PARTICLE_INDEX == idx or -idx-2)
+
+// 32-byte traversal record; the four children of a cell are one 128-byte line.
+struct __align__(32) NodeRec {
+    float chx, chy;   // COM, high float of the double-float pair
+    float clx, cly;   // COM, low float   (com = ch + cl to ~2^-48)
+    float gm;         // (float)(G * mass)
+    uint32_t flags;   // kNode*
+    uint32_t count;   // bodies in the cell (saturating at 2^32-1 is impossible: N < 2^32)
+    uint32_t first;   // sorted position of the cell's first body
+};
+
+// Written by the bounds kernel on the device every step; read by every later kernel.
+struct StepConsts {
+    double xmin, xmax, ymin, ymax;     // padded root box (project.cu:553-572)
+    double size[kMaxLevels];           // max(width, height) of a level-l cell (project.cu:637-639)
+    float thr2[kMaxLevels];            // FP32 mode: accept iff d^2 > thr2[l]  (== size/(d+eps) < theta)
+    double thr[kMaxLevels];            // FP64 mode helper (unused by the reference-order test)
+};
+
+struct TreeArrays {
+    // dense pyramid: level l occupies [level_off[l], level_off[l] + 4^l), Morton order inside
+    double* mass;
+    double* comx;
+    double* comy;
+    uint32_t* count;   // bodies per cell
+    uint32_t* first;   // sorted position of first body
+    NodeRec* rec;
+};
+
+struct Scratch {
+    // zeroed by ONE memset at the start of every step:
+    uint8_t* zero_base;
+    size_t zero_bytes;
+    uint32_t* digit_hist;     // [kMaxSortPasses][kMaxBins]
+    uint32_t* tile_state;     // [passes][ntiles][nbins]
+    uint32_t* tickets;        // [kMaxSortPasses] + misc counters
+    uint32_t* heavy_count;    // 1
+    unsigned long long* counters;  // [8] interactions, visits, opens, warp_steps, nodes, heavy
+    uint32_t* bbox_ticket;    // 1
+    uint32_t* finest_count;   // alias of tree.count at the finest level (inside the zeroed block)
+    // not zeroed:
+    double* bbox_partial;     // [grid][4]
+    uint32_t* heavy_list;     // finest cell ids
+};
+
+struct SortPlan {
+    int key_bits, passes, bits_per_pass, nbins_log2;  // nbins_log2 in {8, 9}
+    int ntiles;
+};
+
+struct Dims {
+    int64_t n;
+    int max_depth;     // D
+    int finest;        // F = D-1
+    uint64_t level_off[kMaxLevels + 1];
+    uint64_t ncells_finest;
+    uint64_t npyramid;
+};
+
+// ---- kernel launchers (each in its own .cu) ------------------------------------------------
+void launch_bounds(const double2* pos, int64_t n, const bh_params& p, const Dims& d, Scratch& s,
+                   StepConsts* consts, int grid, cudaStream_t st);
+void launch_keys(const double2* pos, int64_t n, const Dims& d, const SortPlan& sp, const StepConsts* consts,
+                 uint32_t* keys, uint32_t* idx, uint32_t* digit_hist, cudaStream_t st);
+void launch_sort(uint32_t* keys[2], uint32_t* vals[2], int64_t n, const SortPlan& sp, Scratch& s,
+                 int* result_buf, cudaStream_t st);
+void launch_tree(const uint32_t* skeys, const uint32_t* sidx, const double2* pos, const double* mass,
+                 int64_t n, const bh_params& p, const Dims& d, TreeArrays& t, Scratch& s,
+                 const StepConsts* consts, cudaStream_t st);
+void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, double2* pos, double2* vel, double2* acc,
+                     double2* force, const double* mass, int64_t n, int64_t own_lo, int64_t own_hi,
+                     const uint32_t* own_list, const uint32_t* own_count_dev, int64_t own_n,
+                     const bh_params& p, const Dims& d, const TreeArrays& t, const StepConsts* consts,
+                     unsigned long long* counters, bool integrate, cudaStream_t st);
+void launch_integrate(double2* pos, double2* vel, double2* acc, const double2* force, const double* mass,
+                      int64_t lo, int64_t hi, double dt, cudaStream_t st);
+void launch_own_list(const uint32_t* sidx, int64_t n, int64_t lo, int64_t hi, uint32_t* own_list,
+                     uint32_t* own_count, cudaStream_t st);
+void launch_direct(const double2* pos, const double* mass, int64_t n, double G, float4* packed,
+                   double2* force, cudaStream_t st);
+int measure_fp32_peak(int device, double* tflops, double* mhz);
+
+int traverse_launch_count();
+extern thread_local uint64_t g_launches;  // kernels launched by this library on this thread
+
+void set_error(const char* fmt, ...);
+#define BH_CUDA_OK(expr)                                                                          \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            ::bh::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+            return BH_ERR_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+}  // namespace bh

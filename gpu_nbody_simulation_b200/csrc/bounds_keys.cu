@@ -1,0 +1,164 @@
+// Kernel 1: FP64 bounding box + per-level constants, and per-body cell keys.
+//
+// Replaces ComputeRootBounds (project.cu:536-573) and the root-to-cap descent that QuadInsert /
+// DetermineChild perform per body (project.cu:348-356, :358-453).  Both are bit-exact by
+// construction: min/max are order independent, the padding uses the reference's operation
+// order with contraction disabled (__dmul_rn / __dadd_rn), and the key is produced by the same
+// FP64 bisection `mid = (min + max) / 2` with the same four-way comparison the reference uses.
+#include "bh_internal.h"
+
+namespace bh {
+
+namespace {
+
+constexpr int kBoundsThreads = 256;
+
+// std::min(a, b) == (b < a) ? b : a ; std::max(a, b) == (a < b) ? b : a   (project.cu:547-550)
+__device__ __forceinline__ double ref_min(double cur, double x) { return (x < cur) ? x : cur; }
+__device__ __forceinline__ double ref_max(double cur, double x) { return (cur < x) ? x : cur; }
+
+__global__ void __launch_bounds__(kBoundsThreads)
+bounds_kernel(const double2* __restrict__ pos, int64_t n, double* __restrict__ partial,
+              uint32_t* __restrict__ ticket, StepConsts* __restrict__ consts, double pad_frac,
+              double pad_fallback, double theta, double dist_eps, int finest) {
+    double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double2 p = pos[i];
+        xmin = ref_min(xmin, p.x); xmax = ref_max(xmax, p.x);
+        ymin = ref_min(ymin, p.y); ymax = ref_max(ymax, p.y);
+    }
+    __shared__ double s[4][kBoundsThreads / 32];
+    __shared__ bool last;
+    auto block_reduce = [&]() {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            xmin = ref_min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+            xmax = ref_max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+            ymin = ref_min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+            ymax = ref_max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        }
+        int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if (l == 0) { s[0][w] = xmin; s[1][w] = xmax; s[2][w] = ymin; s[3][w] = ymax; }
+        __syncthreads();
+        if (w == 0) {
+            constexpr int NW = kBoundsThreads / 32;
+            xmin = l < NW ? s[0][l] : INFINITY; xmax = l < NW ? s[1][l] : -INFINITY;
+            ymin = l < NW ? s[2][l] : INFINITY; ymax = l < NW ? s[3][l] : -INFINITY;
+#pragma unroll
+            for (int o = NW / 2; o > 0; o >>= 1) {
+                xmin = ref_min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+                xmax = ref_max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+                ymin = ref_min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+                ymax = ref_max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+            }
+        }
+        __syncthreads();
+    };
+    block_reduce();
+    if (threadIdx.x == 0) {
+        double* o = partial + 4 * (size_t)blockIdx.x;
+        o[0] = xmin; o[1] = xmax; o[2] = ymin; o[3] = ymax;
+        __threadfence();
+        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    xmin = INFINITY; xmax = -INFINITY; ymin = INFINITY; ymax = -INFINITY;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+        const volatile double* o = partial + 4 * (size_t)b;
+        xmin = ref_min(xmin, o[0]); xmax = ref_max(xmax, o[1]);
+        ymin = ref_min(ymin, o[2]); ymax = ref_max(ymax, o[3]);
+    }
+    block_reduce();
+    if (threadIdx.x == 0) {
+        *ticket = 0;
+        // project.cu:553-570, same operation order, no FMA contraction
+        double dx = __dsub_rn(xmax, xmin), dy = __dsub_rn(ymax, ymin);
+        double max_dim = (dx < dy) ? dy : dx;                 // std::max(dx, dy)
+        double pad = __dmul_rn(pad_frac, max_dim);
+        if (max_dim == 0.0) pad = pad_fallback;
+        xmin = __dsub_rn(xmin, pad); xmax = __dadd_rn(xmax, pad);
+        ymin = __dsub_rn(ymin, pad); ymax = __dadd_rn(ymax, pad);
+        consts->xmin = xmin; consts->xmax = xmax; consts->ymin = ymin; consts->ymax = ymax;
+        // cell extent per level, following the low-side bisection chain (project.cu:417-428)
+        double xl = xmin, xh = xmax, yl = ymin, yh = ymax;
+        for (int l = 0; l < kMaxLevels; ++l) {
+            double w = __dsub_rn(xh, xl), h = __dsub_rn(yh, yl);
+            double size = (w > h) ? w : h;                    // project.cu:637-639
+            consts->size[l] = size;
+            // size / (d + eps) < theta  <=>  d > size/theta - eps
+            double thr = (theta > 0.0) ? (size / theta - dist_eps) : INFINITY;
+            consts->thr[l] = thr;
+            float t2;
+            if (!(theta > 0.0)) t2 = INFINITY;
+            else if (thr < 0.0) t2 = -1.0f;
+            else t2 = (float)(thr * thr);
+            consts->thr2[l] = t2;
+            if (l < finest) {
+                xh = __dmul_rn(__dadd_rn(xl, xh), 0.5);
+                yh = __dmul_rn(__dadd_rn(yl, yh), 0.5);
+            }
+        }
+    }
+}
+
+// One thread per body.  Also accumulates the radix-sort digit histograms of all passes.
+__global__ void __launch_bounds__(256)
+keys_kernel(const double2* __restrict__ pos, int64_t n, int finest, const StepConsts* __restrict__ consts,
+            uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ digit_hist,
+            int passes, int bits_per_pass) {
+    __shared__ uint32_t hist[kMaxSortPasses * kMaxBins];
+    for (int i = threadIdx.x; i < passes * kMaxBins; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const double bx0 = consts->xmin, bx1 = consts->xmax, by0 = consts->ymin, by1 = consts->ymax;
+    const uint32_t dmask = (1u << bits_per_pass) - 1u;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double2 p = pos[i];
+        double xl = bx0, xh = bx1, yl = by0, yh = by1;
+        uint32_t key = 0;
+        for (int l = 0; l < finest; ++l) {
+            double mx = __dmul_rn(__dadd_rn(xl, xh), 0.5);   // (min + max) / 2, exact halving
+            double my = __dmul_rn(__dadd_rn(yl, yh), 0.5);
+            // project.cu:352-355 — the four explicit tests (NaN coordinates fall through to 3)
+            uint32_t q;
+            if (p.x < mx && p.y < my) q = 0;
+            else if (p.x >= mx && p.y < my) q = 1;
+            else if (p.x < mx && p.y >= my) q = 2;
+            else q = 3;
+            if (q & 1u) xl = mx; else xh = mx;               // child bounds project.cu:421-429
+            if (q & 2u) yl = my; else yh = my;
+            key = (key << 2) | q;
+        }
+        keys[i] = key;
+        idx[i] = (uint32_t)i;
+        for (int ps = 0; ps < passes; ++ps)
+            atomicAdd(&hist[ps * kMaxBins + ((key >> (ps * bits_per_pass)) & dmask)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * kMaxBins; i += blockDim.x) {
+        uint32_t v = hist[i];
+        if (v) atomicAdd(&digit_hist[i], v);
+    }
+}
+
+}  // namespace
+
+void launch_bounds(const double2* pos, int64_t n, const bh_params& p, const Dims& d, Scratch& s,
+                   StepConsts* consts, int grid, cudaStream_t st) {
+    bounds_kernel<<<grid, kBoundsThreads, 0, st>>>(pos, n, s.bbox_partial, s.bbox_ticket, consts, p.pad_frac,
+                                                   p.pad_fallback, p.theta, p.dist_eps, d.finest);
+    ++g_launches;
+}
+
+void launch_keys(const double2* pos, int64_t n, const Dims& d, const SortPlan& sp, const StepConsts* consts,
+                 uint32_t* keys, uint32_t* idx, uint32_t* digit_hist, cudaStream_t st) {
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    keys_kernel<<<(int)blocks, 256, 0, st>>>(pos, n, d.finest, consts, keys, idx, digit_hist, sp.passes,
+                                             sp.bits_per_pass);
+    ++g_launches;
+}
+
+}  // namespace bh

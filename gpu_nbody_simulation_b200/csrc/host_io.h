@@ -1,0 +1,27 @@
+// Host-side helpers of libbh.so: the reference's text formats and the canonical node table.
+#pragma once
+#include <stdint.h>
+
+#include <vector>
+
+namespace bh {
+
+struct HostTree {
+    int finest = 0;
+    uint64_t level_off[17] = {};
+    double bounds[4] = {};
+    std::vector<double> mass, comx, comy;
+    std::vector<uint32_t> count, first;
+    std::vector<uint32_t> sidx;   // body (internal index) per sorted position
+    std::vector<uint32_t> perm;   // internal -> original index (empty = identity)
+    std::vector<double> pos;      // internal order, xy interleaved
+};
+
+// DFS pre-order, children 0->3; row = {depth, xmin, xmax, ymin, ymax, mass, comx, comy, occupant, internal}.
+// Writes at most cap_rows rows; returns the total number of nodes.
+int64_t canonical_rows(const HostTree& t, double* out_rows, int64_t cap_rows);
+int dump_quadtree_txt(const HostTree& t, const char* path);
+int load_text(const char* mf, const char* pf, const char* vf, int64_t n, double* mass, double* pos, double* vel);
+int append_positions_txt(const char* path, const double* pos, int64_t n, double time, int truncate);
+
+}  // namespace bh

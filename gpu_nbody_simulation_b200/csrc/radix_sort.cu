@@ -1,0 +1,177 @@
+// Kernel 2: onesweep LSD radix sort of (cell key, body index) pairs.
+//
+// No reference counterpart: the reference inserts bodies one at a time on the host
+// (project.cu:586-588).  Sorting by cell key makes (a) every finest cell's bodies one contiguous,
+// index-ordered run (stable sort => the reference's insertion order inside a cell is kept, which
+// is what makes the cap-level running average of project.cu:367-373 reproducible bit for bit) and
+// (b) consecutive bodies spatially coherent for the warp-level traversal.
+//
+// One kernel per digit pass ("onesweep"): every tile of 4096 keys ranks its keys locally, publishes
+// its per-digit counts and obtains the counts of all earlier tiles by decoupled look-back over a
+// per-pass status array, so each key is read once and written once per pass.  The per-pass global
+// digit histograms are produced by the key-generation kernel (bounds_keys.cu), so there is no
+// separate histogram read of the keys.  Tile ids come from an atomic ticket, which guarantees that
+// every tile a block waits on is already resident (forward progress without co-scheduling
+// assumptions).  Stable: ranks follow (warp, item, lane) order == global index order.
+#include "bh_internal.h"
+
+namespace bh {
+
+namespace {
+
+constexpr uint32_t kFlagAgg = 1u << 30;   // tile published its own digit count
+constexpr uint32_t kFlagIncl = 2u << 30;  // tile published the inclusive prefix over tiles 0..t
+constexpr uint32_t kValMask = (1u << 30) - 1u;
+
+template <int NBINS_LOG2>
+__global__ void __launch_bounds__(kSortThreads)
+onesweep_pass(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+              uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
+              int bits, const uint32_t* __restrict__ digit_hist, uint32_t* tile_state, uint32_t* ticket) {
+    constexpr int NBINS = 1 << NBINS_LOG2;
+    constexpr int NWARPS = kSortThreads / 32;
+    constexpr int PER_T = NBINS / kSortThreads;  // digits owned per thread (1 or 2)
+    __shared__ uint32_t s_warp[NWARPS][NBINS];   // per-warp digit counts -> per-warp offsets
+    __shared__ uint32_t s_base[NBINS];           // global position of this tile's first key of digit d
+    __shared__ uint32_t s_scan[NWARPS];
+    __shared__ uint32_t s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < NWARPS * NBINS; i += kSortThreads) (&s_warp[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t dmask = (1u << bits) - 1u;
+    const int64_t base = (int64_t)tile * kSortTile + (int64_t)warp * (32 * kSortItems) + lane;
+
+    uint32_t key[kSortItems];
+    uint32_t rank[kSortItems];
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        int64_t g = base + (int64_t)k * 32;
+        key[k] = (g < n) ? keys_in[g] : 0xffffffffu;
+    }
+    // warp-level stable ranking, item by item
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        int64_t g = base + (int64_t)k * 32;
+        bool valid = g < n;
+        uint32_t d = (key[k] >> shift) & dmask;
+        uint32_t dext = valid ? d : (0x10000u | (uint32_t)lane);  // invalid lanes match nobody
+        uint32_t peers = __match_any_sync(0xffffffffu, dext);
+        uint32_t lt = peers & ((1u << lane) - 1u);
+        uint32_t running = valid ? s_warp[warp][d] : 0u;
+        rank[k] = running + __popc(lt);
+        __syncwarp();
+        if (valid && lt == 0) s_warp[warp][d] = running + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // per digit: exclusive scan over warps, tile total, look-back over earlier tiles
+    uint32_t tile_count[PER_T], excl_prev[PER_T];
+#pragma unroll
+    for (int j = 0; j < PER_T; ++j) {
+        int d = tid + j * kSortThreads;
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) {
+            uint32_t c = s_warp[w][d];
+            s_warp[w][d] = run;
+            run += c;
+        }
+        tile_count[j] = run;
+        volatile uint32_t* st = tile_state + (size_t)tile * NBINS + d;
+        if (tile == 0) *st = kFlagIncl | run;
+        else *st = kFlagAgg | run;
+    }
+#pragma unroll
+    for (int j = 0; j < PER_T; ++j) {
+        int d = tid + j * kSortThreads;
+        uint32_t excl = 0;
+        if (tile > 0) {
+            int64_t t = (int64_t)tile - 1;
+            while (true) {
+                volatile uint32_t* st = tile_state + (size_t)t * NBINS + d;
+                uint32_t v = *st;
+                if (v == 0) continue;  // not published yet; the tile is resident (ticket order)
+                excl += v & kValMask;
+                if ((v >> 30) == 2u) break;
+                --t;
+            }
+            volatile uint32_t* mine = tile_state + (size_t)tile * NBINS + d;
+            *mine = kFlagIncl | (excl + tile_count[j]);
+        }
+        excl_prev[j] = excl;
+    }
+    // exclusive scan of the global digit histogram (block-wide, NBINS values)
+    {
+        uint32_t h[PER_T], local = 0;
+#pragma unroll
+        for (int j = 0; j < PER_T; ++j) {
+            // thread owns digits tid*PER_T + j here (contiguous) for the scan
+            h[j] = digit_hist[tid * PER_T + j];
+            local += h[j];
+        }
+        uint32_t inc = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_scan[warp] = inc;
+        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) woff += (w < warp) ? s_scan[w] : 0u;
+        uint32_t ex = woff + inc - local;
+#pragma unroll
+        for (int j = 0; j < PER_T; ++j) {
+            s_base[tid * PER_T + j] = ex;   // global exclusive start of digit
+            ex += h[j];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < PER_T; ++j) {
+        int d = tid + j * kSortThreads;
+        s_base[d] += excl_prev[j];
+    }
+    __syncthreads();
+
+    // scatter keys and values
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        int64_t g = base + (int64_t)k * 32;
+        if (g < n) {
+            uint32_t d = (key[k] >> shift) & dmask;
+            uint32_t dst = s_base[d] + s_warp[warp][d] + rank[k];
+            keys_out[dst] = key[k];
+            vals_out[dst] = vals_in[g];
+        }
+    }
+}
+
+}  // namespace
+
+void launch_sort(uint32_t* keys[2], uint32_t* vals[2], int64_t n, const SortPlan& sp, Scratch& s,
+                 int* result_buf, cudaStream_t st) {
+    int cur = 0;
+    const int nbins = 1 << sp.nbins_log2;
+    for (int pass = 0; pass < sp.passes; ++pass) {
+        uint32_t* state = s.tile_state + (size_t)pass * sp.ntiles * nbins;
+        const uint32_t* hist = s.digit_hist + (size_t)pass * kMaxBins;
+        int shift = pass * sp.bits_per_pass;
+        if (sp.nbins_log2 == 9)
+            onesweep_pass<9><<<sp.ntiles, kSortThreads, 0, st>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
+                                                                 shift, sp.bits_per_pass, hist, state, s.tickets + pass);
+        else
+            onesweep_pass<8><<<sp.ntiles, kSortThreads, 0, st>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
+                                                                 shift, sp.bits_per_pass, hist, state, s.tickets + pass);
+        ++g_launches;
+        cur ^= 1;
+    }
+    *result_buf = cur;
+}
+
+}  // namespace bh

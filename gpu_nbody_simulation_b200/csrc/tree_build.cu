@@ -1,0 +1,338 @@
+// Kernel 3: quadtree build + upward mass / centre-of-mass pass.
+//
+// Replaces buildTree = InitializeRoot + N x QuadInsert + ComputeMass (project.cu:343-346,
+// :358-453, :473-502, :575-591), which the reference runs sequentially on the host every step.
+//
+// Representation.  With the depth cap (QUADTREE_MAX_DEPTH, root = depth 1) every node of the
+// reference's PR quadtree is a cell of the regular pyramid: level l (0 = root .. F = cap-1) is the
+// 2^l x 2^l grid produced by l FP64 bisections of the padded root box, and a cell's Morton code is
+// the concatenation of DetermineChild results (x = low bit).  The reference tree is exactly the
+// subset { cell : every proper ancestor holds >= 2 bodies }: a node is internal iff it holds >= 2
+// bodies and lies above the cap level, and a split always materialises all four children
+// (project.cu:410-434).  So the tree is stored as the dense pyramid (4^(F+1)-1)/3 cells (349 525 at
+// the default cap, 11 MB of 32-byte records: resident in B200's 126 MB L2) with NO child pointers;
+// existence is implied by the parent's body count.  Topology is therefore a pure function of the
+// sorted cell keys (Karras-style: a finest cell's run is delimited where adjacent sorted keys
+// differ; ancestors' runs are unions of their children's).
+//
+// Arithmetic.  Mass / COM follow the reference operation by operation, without FMA contraction
+// (the reference builds the tree in x86-64 host code):
+//   * cap-level cell: running weighted average in ascending body index (project.cu:367-373);
+//   * single body above the cap: the body's own mass and position (project.cu:400-403);
+//   * internal cell: children 0..3, sums started from 0.0, then one division (project.cu:480-495).
+// Hence the node table is bit-identical to the reference's, except finest cells holding more than
+// `exact_leaf_max` bodies, whose (inherently sequential) running average is replaced by a
+// fixed-shape parallel sum (relative difference ~1e-16; deterministic, identical on every rank).
+#include "bh_internal.h"
+
+namespace bh {
+
+namespace {
+
+struct Cell {
+    double m, cx, cy;
+    uint32_t cnt, first;
+};
+
+// Combine four children (in order 0..3) into their parent.  `single body` parents take the body
+// itself; internal parents follow ComputeMass.
+__device__ __forceinline__ Cell combine4(const Cell c[4], const uint32_t* __restrict__ sidx,
+                                         const double2* __restrict__ pos, const double* __restrict__ mass) {
+    Cell p;
+    p.cnt = c[0].cnt + c[1].cnt + c[2].cnt + c[3].cnt;
+    p.first = c[0].cnt ? c[0].first : c[1].cnt ? c[1].first : c[2].cnt ? c[2].first : c[3].first;
+    if (p.cnt == 0) {
+        p.m = 0.0; p.cx = 0.0; p.cy = 0.0; p.first = 0;
+    } else if (p.cnt == 1) {                       // leaf above the cap: project.cu:400-403
+        uint32_t b = sidx[p.first];
+        double2 x = pos[b];
+        p.m = mass[b]; p.cx = x.x; p.cy = x.y;
+    } else {                                       // project.cu:480-499
+        double tm = 0.0, sx = 0.0, sy = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            tm = __dadd_rn(tm, c[q].m);
+            sx = __dadd_rn(sx, __dmul_rn(c[q].m, c[q].cx));
+            sy = __dadd_rn(sy, __dmul_rn(c[q].m, c[q].cy));
+        }
+        if (tm > 0.0) { sx = __ddiv_rn(sx, tm); sy = __ddiv_rn(sy, tm); }
+        p.m = tm; p.cx = sx; p.cy = sy;
+    }
+    return p;
+}
+
+__device__ __forceinline__ void store_cell(const TreeArrays& t, uint64_t at, const Cell& c, int level, int finest,
+                                           double G, double mass_eps) {
+    t.mass[at] = c.m; t.comx[at] = c.cx; t.comy[at] = c.cy;
+    t.count[at] = c.cnt; t.first[at] = c.first;
+    NodeRec r;
+    r.chx = (float)c.cx; r.chy = (float)c.cy;
+    r.clx = (float)(c.cx - (double)r.chx); r.cly = (float)(c.cy - (double)r.chy);
+    r.gm = (float)(G * c.m);
+    r.flags = (c.m > mass_eps ? kNodeNonZero : 0u) | ((c.cnt <= 1u || level == finest) ? kNodeLeaf : 0u) |
+              (c.cnt == 1u ? kNodeSingle : 0u);
+    r.count = c.cnt; r.first = c.first;
+    t.rec[at] = r;
+}
+
+// ---- finest-cell runs from the sorted keys ------------------------------------------------------
+// The thread at the LAST body of a run finds the run's start by binary search and records
+// (first, count); runs longer than exact_leaf_max are queued for the parallel summation kernel.
+__global__ void __launch_bounds__(256)
+cell_runs_kernel(const uint32_t* __restrict__ skeys, int64_t n, uint32_t* __restrict__ cnt_f,
+                 uint32_t* __restrict__ first_f, uint32_t exact_leaf_max, uint32_t* __restrict__ heavy_list,
+                 uint32_t* __restrict__ heavy_count) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t k = skeys[j];
+    if (j + 1 < n && skeys[j + 1] == k) return;
+    int64_t lo = 0, hi = j;   // first position with key >= k
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (skeys[mid] < k) lo = mid + 1; else hi = mid;
+    }
+    uint32_t c = (uint32_t)(j + 1 - lo);
+    cnt_f[k] = c;
+    first_f[k] = (uint32_t)lo;
+    if (c > exact_leaf_max) heavy_list[atomicAdd(heavy_count, 1u)] = k;
+}
+
+// ---- parallel (non-sequential) summation for very full finest cells -------------------------------
+// One block per queued cell; fixed reduction shape => deterministic and identical on all ranks.
+__global__ void __launch_bounds__(256)
+heavy_cells_kernel(const uint32_t* __restrict__ heavy_list, const uint32_t* __restrict__ heavy_count,
+                   const uint32_t* __restrict__ cnt_f, const uint32_t* __restrict__ first_f,
+                   const uint32_t* __restrict__ sidx, const double2* __restrict__ pos,
+                   const double* __restrict__ mass, double* __restrict__ m_f, double* __restrict__ cx_f,
+                   double* __restrict__ cy_f) {
+    __shared__ double sm[3][256];
+    const uint32_t nheavy = *heavy_count;
+    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+        uint32_t cell = heavy_list[h];
+        uint32_t c = cnt_f[cell], f = first_f[cell];
+        double m = 0.0, sx = 0.0, sy = 0.0;
+        for (uint32_t i = threadIdx.x; i < c; i += 256) {
+            uint32_t b = sidx[f + i];
+            double mb = mass[b];
+            double2 x = pos[b];
+            m += mb; sx += mb * x.x; sy += mb * x.y;
+        }
+        sm[0][threadIdx.x] = m; sm[1][threadIdx.x] = sx; sm[2][threadIdx.x] = sy;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) {
+                sm[0][threadIdx.x] += sm[0][threadIdx.x + o];
+                sm[1][threadIdx.x] += sm[1][threadIdx.x + o];
+                sm[2][threadIdx.x] += sm[2][threadIdx.x + o];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            double tm = sm[0][0];
+            m_f[cell] = tm;
+            cx_f[cell] = tm > 0.0 ? sm[1][0] / tm : 0.0;
+            cy_f[cell] = tm > 0.0 ? sm[2][0] / tm : 0.0;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- bottom kernel: finest cells + up to five levels above -----------------------------------------
+// Block b owns finest cells [1024 b, 1024 b + 1024) = one subtree rooted five levels up.  Thread t
+// computes four sibling finest cells and their parent in registers; the next two levels are
+// combined inside a warp with shuffles, the remaining ones through shared memory.
+constexpr int kBottomThreads = 256;
+
+__device__ __forceinline__ Cell shfl_cell(const Cell& c, int src_lane) {
+    Cell r;
+    r.m = __shfl_sync(0xffffffffu, c.m, src_lane);
+    r.cx = __shfl_sync(0xffffffffu, c.cx, src_lane);
+    r.cy = __shfl_sync(0xffffffffu, c.cy, src_lane);
+    r.cnt = __shfl_sync(0xffffffffu, c.cnt, src_lane);
+    r.first = __shfl_sync(0xffffffffu, c.first, src_lane);
+    return r;
+}
+
+__global__ void __launch_bounds__(kBottomThreads)
+tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, const double2* __restrict__ pos,
+                   const double* __restrict__ mass, double G, double mass_eps, uint32_t exact_leaf_max,
+                   unsigned long long* __restrict__ counters) {
+    const int F = d.finest;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint64_t offF = d.level_off[F];
+    __shared__ Cell s_cells[kBottomThreads / 16];   // level F-3 results (16 per block)
+    __shared__ Cell s_cells4[4];                    // level F-4 results (4 per block)
+    __shared__ uint32_t s_internal[kBottomThreads / 32];
+    uint32_t n_internal = 0;
+
+    // ---- level F: four sibling cells per thread
+    Cell leaf[4];
+    const uint64_t parent_code = (uint64_t)blockIdx.x * kBottomThreads + tid;   // code at level F-1
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint64_t code = (F == 0) ? parent_code : parent_code * 4 + q;
+        Cell c; c.m = 0.0; c.cx = 0.0; c.cy = 0.0; c.cnt = 0; c.first = 0;
+        bool exists = code < d.ncells_finest && (F > 0 || q == 0);
+        if (exists) {
+            c.cnt = t.count[offF + code];
+            if (c.cnt) {
+                c.first = t.first[offF + code];
+                if (c.cnt <= exact_leaf_max) {
+                    // project.cu:367-373: running weighted average in ascending body index
+                    double em = 0.0, ex = 0.0, ey = 0.0;
+                    for (uint32_t i = 0; i < c.cnt; ++i) {
+                        uint32_t b = sidx[c.first + i];
+                        double mb = mass[b];
+                        double2 x = pos[b];
+                        double tot = __dadd_rn(em, mb);
+                        ex = __ddiv_rn(__dadd_rn(__dmul_rn(em, ex), __dmul_rn(mb, x.x)), tot);
+                        ey = __ddiv_rn(__dadd_rn(__dmul_rn(em, ey), __dmul_rn(mb, x.y)), tot);
+                        em = tot;                  // node[TOTAL_MASS] += mass
+                    }
+                    c.m = em; c.cx = ex; c.cy = ey;
+                } else {                           // summed by heavy_cells_kernel
+                    c.m = t.mass[offF + code]; c.cx = t.comx[offF + code]; c.cy = t.comy[offF + code];
+                }
+            }
+            store_cell(t, offF + code, c, F, F, G, mass_eps);
+        }
+        leaf[q] = c;
+    }
+    if (F == 0) {
+        if (blockIdx.x == 0 && tid == 0) atomicAdd(&counters[4], 1ull);   // the root alone
+        return;
+    }
+    // ---- level F-1 (registers)
+    Cell cur = combine4(leaf, sidx, pos, mass);
+    int level = F - 1;
+    uint64_t code = parent_code;
+    uint64_t ncells = d.ncells_finest >> 2;
+    if (code < ncells) {
+        store_cell(t, d.level_off[level] + code, cur, level, F, G, mass_eps);
+        n_internal += (cur.cnt >= 2u);
+    }
+    // ---- levels F-2, F-3: shuffles inside the warp (groups of 4, then 16 lanes)
+#pragma unroll
+    for (int stride = 1; stride <= 4; stride <<= 2) {
+        if (level == 0) break;
+        Cell ch[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ch[q] = shfl_cell(cur, (lane & ~(4 * stride - 1)) + q * stride);
+        --level; code >>= 2; ncells >>= 2;
+        bool owner = (lane & (4 * stride - 1)) == 0;
+        Cell up = combine4(ch, sidx, pos, mass);
+        if (owner && code < ncells) {
+            store_cell(t, d.level_off[level] + code, up, level, F, G, mass_eps);
+            n_internal += (up.cnt >= 2u);
+        }
+        cur = up;
+    }
+    // ---- levels F-4, F-5: shared memory (16 cells of level F-3 per block)
+    if (level > 0) {   // block-uniform
+        if ((lane & 15) == 0) s_cells[tid >> 4] = cur;
+        __syncthreads();
+        const int l4 = level - 1;
+        if (tid < 4) {
+            Cell ch[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ch[q] = s_cells[tid * 4 + q];
+            Cell up = combine4(ch, sidx, pos, mass);
+            uint64_t c4 = (uint64_t)blockIdx.x * 4 + tid;
+            if (c4 < (ncells >> 2)) {
+                store_cell(t, d.level_off[l4] + c4, up, l4, F, G, mass_eps);
+                n_internal += (up.cnt >= 2u);
+            }
+            s_cells4[tid] = up;
+        }
+        __syncthreads();
+        // level F-5: one cell per block
+        if (l4 > 0 && tid == 0) {
+            Cell top = combine4(s_cells4, sidx, pos, mass);
+            int l5 = l4 - 1;
+            uint64_t c5code = blockIdx.x;
+            if (c5code < (ncells >> 4)) {
+                store_cell(t, d.level_off[l5] + c5code, top, l5, F, G, mass_eps);
+                n_internal += (top.cnt >= 2u);
+            }
+        }
+    }
+    // ---- count internal cells (reference node count = 1 + 4 * internal)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_internal += __shfl_xor_sync(0xffffffffu, n_internal, o);
+    if (lane == 0) s_internal[tid >> 5] = n_internal;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < kBottomThreads / 32; ++w) tot += s_internal[w];
+        if (tot) atomicAdd(&counters[5], (unsigned long long)tot);
+    }
+}
+
+// ---- top kernel: remaining levels (F-6 .. 0), one block, level by level through global memory ----
+__global__ void __launch_bounds__(1024)
+tree_top_kernel(TreeArrays t, Dims d, int top_level, const uint32_t* __restrict__ sidx,
+                const double2* __restrict__ pos, const double* __restrict__ mass, double G, double mass_eps,
+                unsigned long long* __restrict__ counters) {
+    const int F = d.finest;
+    __shared__ uint32_t s_int;
+    if (threadIdx.x == 0) s_int = 0;
+    __syncthreads();
+    uint32_t n_internal = 0;
+    for (int level = top_level; level >= 0; --level) {
+        uint64_t ncells = 1ull << (2 * level);
+        uint64_t off = d.level_off[level], offc = d.level_off[level + 1];
+        for (uint64_t c = threadIdx.x; c < ncells; c += blockDim.x) {
+            Cell ch[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint64_t a = offc + 4 * c + q;
+                ch[q].m = t.mass[a]; ch[q].cx = t.comx[a]; ch[q].cy = t.comy[a];
+                ch[q].cnt = t.count[a]; ch[q].first = t.first[a];
+            }
+            Cell up = combine4(ch, sidx, pos, mass);
+            store_cell(t, off + c, up, level, F, G, mass_eps);
+            n_internal += (up.cnt >= 2u);
+        }
+        __syncthreads();   // level `level` complete and visible to the block
+    }
+    if (n_internal) atomicAdd(&s_int, n_internal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // counters[5] holds internal cells counted by the bottom kernel
+        unsigned long long internal = counters[5] + s_int;
+        counters[4] = 1ull + 4ull * internal;   // quadtree.size() of the reference
+    }
+}
+
+}  // namespace
+
+void launch_tree(const uint32_t* skeys, const uint32_t* sidx, const double2* pos, const double* mass,
+                 int64_t n, const bh_params& p, const Dims& d, TreeArrays& t, Scratch& s,
+                 const StepConsts* consts, cudaStream_t st) {
+    (void)consts;
+    const int F = d.finest;
+    uint32_t* cnt_f = t.count + d.level_off[F];
+    uint32_t* first_f = t.first + d.level_off[F];
+    uint32_t exact_max = (uint32_t)(p.exact_leaf_max < 0 ? 0 : p.exact_leaf_max);
+    cell_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(skeys, n, cnt_f, first_f, exact_max, s.heavy_list,
+                                                                  s.heavy_count);
+    ++g_launches;
+    heavy_cells_kernel<<<148 * 4, 256, 0, st>>>(s.heavy_list, s.heavy_count, cnt_f, first_f, sidx, pos, mass,
+                                                t.mass + d.level_off[F], t.comx + d.level_off[F],
+                                                t.comy + d.level_off[F]);
+    ++g_launches;
+    uint64_t parents = F == 0 ? 1 : (d.ncells_finest >> 2);
+    unsigned blocks = (unsigned)((parents + kBottomThreads - 1) / kBottomThreads);
+    tree_bottom_kernel<<<blocks, kBottomThreads, 0, st>>>(t, d, sidx, pos, mass, p.G, p.mass_eps, exact_max,
+                                                          s.counters);
+    ++g_launches;
+    int top_level = F - 6;   // bottom kernel covered F .. F-5
+    if (F >= 1) {
+        if (top_level < 0) top_level = -1;
+        // when the bottom kernel already reached the root (F <= 5) only the node count remains
+        tree_top_kernel<<<1, 1024, 0, st>>>(t, d, top_level, sidx, pos, mass, p.G, p.mass_eps, s.counters);
+        ++g_launches;
+    }
+}
+
+}  // namespace bh

@@ -1,0 +1,167 @@
+/* bh.h — C-ABI of the B200-native 2-D Barnes-Hut engine (libbh.so).
+ *
+ * The reference (DavidSevic/gpu-nbody-simulation, implementation/project.cu) has no library
+ * or FFI seam: its simulation path is inlined in one executable.  This header is the seam cut
+ * through `runSimulationGpu` (project.cu:918-1024); every entry point names the reference
+ * code it replaces.  Plain C types only (no torch, no C++ types); all buffers named `host`
+ * are caller-owned host memory in the reference's own layouts (AoS double[N][2] for vectors,
+ * double[N] for masses, project.cu:38-43), in ORIGINAL body order.
+ *
+ * Threading: one host thread per context.  Every call returns BH_OK (0) or a negative error
+ * code; bh_last_error() returns the message of the last failure on the calling thread.  The
+ * reference reads no CUDA return code at all; here every CUDA / NCCL call is checked.
+ * There is no CPU fallback: without a CUDA device bh_create fails with BH_ERR_CUDA.
+ */
+#ifndef BH_H_
+#define BH_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BH_ABI_VERSION 1
+
+enum {
+    BH_OK = 0,
+    BH_ERR_INVALID = -1,  /* bad argument / bad state */
+    BH_ERR_CUDA = -2,     /* CUDA runtime error (message holds cudaGetErrorString) */
+    BH_ERR_NCCL = -3,     /* NCCL error or libnccl not loadable */
+    BH_ERR_IO = -4,       /* file could not be opened / too few lines (project.cu:118-144) */
+    BH_ERR_NOMEM = -5
+};
+
+/* bh_params.flags */
+enum {
+    BH_FLAG_FP64_TRAVERSAL = 1u << 0, /* evaluate forces in FP64 with the reference's expression
+                                         order (verification mode); default: FP32 arithmetic on a
+                                         double-float displacement */
+    BH_FLAG_COUNTERS = 1u << 1,       /* keep per-step interaction / visit counters (cheap) */
+    BH_FLAG_NO_GRAPH = 1u << 2        /* launch kernels directly instead of replaying a CUDA graph */
+};
+
+/* Runtime copy of the reference's compile-time macros and source-level constants.
+ * bh_default_params() fills in the reference's values. */
+typedef struct bh_params {
+    int64_t n_bodies;     /* -DN_BODIES            project.cu:1-3    (40000) */
+    double G;             /* const double G        project.cu:27     (6.67e-11) */
+    double dt;            /* DELTA_T               project.cu:29     (1.0) */
+    double theta;         /* THETA                 project.cu:60     (0.5) */
+    double dist_eps;      /* "+ 1e-15" on distance project.cu:634, :748 */
+    double mass_eps;      /* "<= 1e-15" node skip  project.cu:617, :731 */
+    double pad_frac;      /* padFraction           project.cu:558    (0.1) */
+    double pad_fallback;  /* pad if extent == 0    project.cu:564    (1e-6) */
+    int32_t max_depth;    /* QUADTREE_MAX_DEPTH    project.cu:61     (10, root = depth 1); 1..13 */
+    int32_t device;       /* CUDA device ordinal; -1 = current device */
+    uint32_t flags;       /* BH_FLAG_* */
+    int32_t exact_leaf_max; /* finest cells with <= this many bodies accumulate mass/COM with the
+                               reference's sequential running average (project.cu:367-373, bit-exact);
+                               fuller cells use a fixed-shape parallel sum.  default 64 */
+    /* multi-GPU: bodies are sharded by contiguous index range after an initial Morton
+     * renumbering; each step all-gathers positions over NCCL (no reference counterpart). */
+    int32_t rank;         /* 0 .. n_ranks-1 */
+    int32_t n_ranks;      /* 1 = single GPU */
+    int32_t reserved[4];
+} bh_params;
+
+typedef struct bh_ctx bh_ctx; /* opaque; owns device memory, stream, CUDA graph, NCCL comm */
+
+/* Per-step work counters with the reference's per-body semantics (project.cu:608-670). */
+typedef struct bh_counters {
+    uint64_t interactions; /* executions of the force block project.cu:651-658 / :765-772 */
+    uint64_t visits;       /* node pops as the reference would count them (per body) */
+    uint64_t opens;        /* per-body opened nodes */
+    uint64_t warp_steps;   /* warp-level traversal steps actually executed (parent expansions) */
+    uint64_t nodes;        /* nodes of the reference-equivalent tree (quadtree.size()) */
+    uint64_t heavy_cells;  /* finest cells summed with the parallel path (see exact_leaf_max) */
+    uint64_t reserved[2];
+} bh_counters;
+
+/* Accumulated device time per phase in microseconds (cudaEvent, only while profiling is on). */
+typedef struct bh_timers {
+    double bounds_keys_us, sort_us, build_us, traverse_us, integrate_us, exchange_us, total_us;
+    uint64_t steps;        /* steps accumulated */
+    uint64_t kernel_launches; /* kernels of this library launched since bh_reset_timers */
+} bh_timers;
+
+const char* bh_last_error(void);
+int bh_abi_version(void);
+void bh_default_params(bh_params* p);
+
+/* ---- life cycle (replaces the cudaMalloc/cudaFree block project.cu:932-940, :1014-1019) ---- */
+int bh_create(const bh_params* p, bh_ctx** out);
+int bh_destroy(bh_ctx* ctx);
+/* multi-GPU: rank 0 calls bh_nccl_unique_id, the host application ships the 128 bytes to every
+ * rank (e.g. torch.distributed broadcast), every rank calls bh_attach_nccl before bh_step. */
+int bh_nccl_unique_id(void* id128);
+int bh_attach_nccl(bh_ctx* ctx, const void* id128);
+/* index range [lo, hi) of bodies owned by `rank` (pure integer logic, usable without a GPU) */
+int bh_shard_range(int64_t n_bodies, int32_t n_ranks, int32_t rank, int64_t* lo, int64_t* hi);
+
+/* ---- body state (replaces the H2D copies project.cu:943-945) ---- */
+int bh_set_bodies(bh_ctx* ctx, const double* pos_xy_host, const double* vel_xy_host, const double* mass_host);
+int bh_set_positions(bh_ctx* ctx, const double* pos_xy_host);   /* teacher forcing */
+int bh_set_velocities(bh_ctx* ctx, const double* vel_xy_host);
+/* device-resident snapshot / restore of (pos, vel): lets a benchmark restart every step from the
+ * initial distribution without touching the host (the reference physics collapses the tree after
+ * one step). */
+int bh_snapshot(bh_ctx* ctx);
+int bh_restore(bh_ctx* ctx);
+
+/* ---- the hot path ---- */
+/* nsteps iterations of the loop body project.cu:955-1011: bounds -> keys -> sort -> tree -> COM ->
+ * traversal -> a=F/m, v+=a dt, x+=v dt.  Asynchronous on the context's stream. */
+int bh_step(bh_ctx* ctx, int32_t nsteps);
+/* same, but every step first restores the snapshot (device-to-device) */
+int bh_step_from_snapshot(bh_ctx* ctx, int32_t nsteps);
+/* phase-split entry points for teacher-forced parity */
+int bh_build_tree(bh_ctx* ctx);       /* replaces buildTree        project.cu:575-591 (+H2D :968) */
+int bh_compute_forces(bh_ctx* ctx);   /* replaces computeForcesGpu project.cu:679-793; needs a built tree */
+int bh_integrate(bh_ctx* ctx);        /* replaces updateAccVelPos  project.cu:819-836 */
+int bh_synchronize(bh_ctx* ctx);      /* cudaDeviceSynchronize project.cu:989, :1003 */
+
+/* ---- results, ORIGINAL body order (replaces the D2H copy project.cu:1010) ---- */
+int bh_get_positions(bh_ctx* ctx, double* out_xy_host);
+int bh_get_velocities(bh_ctx* ctx, double* out_xy_host);
+int bh_get_accelerations(bh_ctx* ctx, double* out_xy_host);
+int bh_get_forces(bh_ctx* ctx, double* out_xy_host);
+int bh_get_bounds(bh_ctx* ctx, double out4[4]);                /* xmin xmax ymin ymax, project.cu:536-573 */
+int bh_get_body_keys(bh_ctx* ctx, uint32_t* out_keys_host);    /* cell path of DetermineChild, project.cu:348-356 */
+int bh_get_sorted_order(bh_ctx* ctx, uint32_t* out_idx_host);  /* body index at every sorted position */
+
+/* Canonical node table of the reference-equivalent tree: DFS pre-order, children 0->3 (the order
+ * of TraverseTreeToFile, project.cu:504-534).  Row = 10 doubles { depth (root 0), xmin, xmax,
+ * ymin, ymax, mass, comx, comy, PARTICLE_INDEX as the reference stores it (idx | -idx-2 | -1),
+ * is_internal }.  bh_get_tree_size returns the row count (== quadtree.size()). */
+int bh_get_tree_size(bh_ctx* ctx, int64_t* n_nodes);
+int bh_get_tree(bh_ctx* ctx, double* out_rows_host, int64_t cap_rows, int64_t* n_rows);
+/* quadtree_{init,final}_gpu.txt writer, format of project.cu:509-526 (reads plot_quadtree.py) */
+int bh_dump_quadtree(bh_ctx* ctx, const char* path);
+
+int bh_get_counters(bh_ctx* ctx, bh_counters* out);
+int bh_set_profiling(bh_ctx* ctx, int32_t on);   /* per-phase cudaEvent timers (forces NO_GRAPH path) */
+int bh_get_timers(bh_ctx* ctx, bh_timers* out);
+int bh_reset_timers(bh_ctx* ctx);
+/* device time in ms between the start and the end of the last bh_step / bh_step_from_snapshot
+ * call, measured with cudaEvents on the context's stream (synchronizes). */
+int bh_last_step_ms(bh_ctx* ctx, float* ms);
+
+/* ---- direct all-pairs kernel (BASELINE config 5; formula of main_approach_1.cpp:53-75) ---- */
+int bh_direct_forces(bh_ctx* ctx, double* out_xy_host /* may be NULL */, float* device_ms);
+
+/* ---- text formats of the reference ---- */
+/* loadSimulationDataFromText project.cu:103-161: first n lines of each file */
+int bh_load_text(const char* masses_file, const char* positions_file, const char* velocities_file,
+                 int64_t n, double* mass_out, double* pos_out, double* vel_out);
+/* savePositions project.cu:855-863: appends "time i x y \n" (std::to_string, 6 decimals) */
+int bh_append_positions_txt(const char* path, const double* pos_xy_host, int64_t n, double time, int truncate);
+
+/* ---- measurement helpers ---- */
+/* FP32 FMA peak of the device measured with a register-resident FMA loop, in TFLOP/s */
+int bh_measure_fp32_peak(int32_t device, double* tflops, double* sm_clock_mhz_est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BH_H_ */

@@ -1,0 +1,99 @@
+"""CPU suite: the C-ABI library loads, exports every symbol include/bh.h declares, its host-only
+entry points behave like the reference's, and it fails loudly without a CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gpu_nbody_simulation_b200 as bh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "bh.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bh_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = bh.lib()
+    names = header_symbols()
+    assert len(names) >= 35
+    for name in names:
+        assert hasattr(L, name), f"libbh.so lacks {name}"
+    assert sorted(bh.ABI_SYMBOLS) == names, "python binding and header disagree"
+    assert L.bh_abi_version() == 1
+
+
+def test_params_struct_matches_header_defaults():
+    p = bh.default_params()
+    assert (p.n_bodies, p.G, p.dt, p.theta) == (40000, 6.67e-11, 1.0, 0.5)      # project.cu:1-3, :27, :29, :60
+    assert (p.dist_eps, p.mass_eps, p.pad_frac, p.pad_fallback) == (1e-15, 1e-15, 0.1, 1e-6)
+    assert (p.max_depth, p.n_ranks, p.rank) == (10, 1, 0)                        # project.cu:61
+    assert C.sizeof(bh.Params) == 8 * 8 + 4 * 6 + 16
+
+
+def test_no_cuda_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(bh.BhError) as e:
+        bh.Simulation(1000)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 40000, 1_000_003, 16_777_216):
+        for r in (1, 2, 3, 8):
+            prev = 0
+            for k in range(r):
+                lo, hi = bh.shard_range(n, r, k)
+                assert lo == prev and hi >= lo
+                assert abs((hi - lo) - n / r) < 1.0
+                prev = hi
+            assert prev == n
+    with pytest.raises(bh.BhError):
+        bh.shard_range(10, 2, 2)
+
+
+def test_load_text_reads_reference_format(tmp_path):
+    pos, vel, mass = bh.initial_conditions.uniform_square(300, seed=3)
+    bh.initial_conditions.write_init_files(str(tmp_path), pos, vel, mass)
+    p, v, m = bh.load_text(str(tmp_path), 257)           # first N lines only (project.cu:121, :137)
+    assert np.array_equal(p, pos[:257]) and np.array_equal(v, vel[:257]) and np.array_equal(m, mass[:257])
+    with pytest.raises(bh.BhError) as e:                  # too few lines -> error (project.cu:122-124)
+        bh.load_text(str(tmp_path), 301)
+    assert "Not enough" in str(e.value)
+    with pytest.raises(bh.BhError) as e:
+        bh.load_text(str(tmp_path / "missing"), 1)
+    assert "Failed to open file" in str(e.value)
+
+
+def test_positions_txt_format(tmp_path):
+    path = str(tmp_path / "positions.txt")
+    pos = np.array([[0.0558754321, -0.0739181], [1.5, 2.0]])
+    dp = C.POINTER(C.c_double)
+    assert bh.lib().bh_append_positions_txt(path.encode(), pos.ctypes.data_as(dp), 2, 0.0, 1) == 0
+    assert bh.lib().bh_append_positions_txt(path.encode(), pos.ctypes.data_as(dp), 2, 1.0, 0) == 0
+    lines = open(path).read().split("\n")
+    # std::to_string formatting, trailing space (project.cu:857-861); plot_2d.py reads 4 floats per line
+    assert lines[0] == "0.000000 0 0.055875 -0.073918 "
+    assert lines[3] == "1.000000 1 1.500000 2.000000 "
+    data = np.loadtxt(path)
+    assert data.shape == (4, 4)
+
+
+def test_initial_condition_generators_are_seeded():
+    a = bh.initial_conditions.uniform_disk(5000, seed=12345)
+    b = bh.initial_conditions.uniform_disk(5000, seed=12345)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    pos, vel, mass = a
+    assert np.all(np.hypot(pos[:, 0], pos[:, 1]) <= 0.1 + 1e-6)
+    assert mass.min() >= 0.1 - 1e-6 and mass.max() <= 0.5 + 1e-6 and np.abs(vel).max() <= 1e-4 + 1e-9
+    p2, _, _ = bh.initial_conditions.plummer_2d(5000, seed=1)
+    assert np.all(np.hypot(p2[:, 0], p2[:, 1]) <= 0.1 + 1e-6)
+    # %.6g round trip: values survive the reference's text writers unchanged
+    assert np.array_equal(np.char.mod("%.6g", pos.ravel()).astype(float), pos.ravel())
