@@ -35,8 +35,13 @@ struct __align__(32) NodeRec {
 struct StepConsts {
     double xmin, xmax, ymin, ymax;     // padded root box (project.cu:553-572)
     double size[kMaxLevels];           // max(width, height) of a level-l cell (project.cu:637-639)
-    float thr2[kMaxLevels];            // FP32 mode: accept iff d^2 > thr2[l]  (== size/(d+eps) < theta)
-    double thr[kMaxLevels];            // FP64 mode helper (unused by the reference-order test)
+    float thr2[kMaxLevels];            // FP32 mode: accept iff (S d)^2 > thr2[l]  (== size/(d+eps) < theta)
+    double thr[kMaxLevels];            // size/theta - eps, unscaled (diagnostic)
+    // FP32 traversal works on coordinates multiplied by the power of two S = `scale`, chosen so that the
+    // root box spans ~2^20: keeps d^2 (d + eps) inside the FP32 exponent range from the box diagonal
+    // down to separations of ~1e-19 of it.  Exact (power of two); it cancels in the accumulated force.
+    double scale;
+    float feps;                        // (float)(dist_eps * scale)
 };
 
 struct TreeArrays {

@@ -81,6 +81,14 @@ bounds_kernel(const double2* __restrict__ pos, int64_t n, double* __restrict__ p
         xmin = __dsub_rn(xmin, pad); xmax = __dadd_rn(xmax, pad);
         ymin = __dsub_rn(ymin, pad); ymax = __dadd_rn(ymax, pad);
         consts->xmin = xmin; consts->xmax = xmax; consts->ymin = ymin; consts->ymax = ymax;
+        // power-of-two normalisation of the FP32 traversal coordinates: box extent -> [2^20, 2^21)
+        double ext = fmax(__dsub_rn(xmax, xmin), __dsub_rn(ymax, ymin));
+        int e2 = (ext > 0.0 && ext < INFINITY) ? ilogb(ext) : 20;
+        int se = 20 - e2;
+        se = se > 120 ? 120 : (se < -120 ? -120 : se);
+        const double scale = scalbn(1.0, se);
+        consts->scale = scale;
+        consts->feps = (float)(dist_eps * scale);
         // cell extent per level, following the low-side bisection chain (project.cu:417-428)
         double xl = xmin, xh = xmax, yl = ymin, yh = ymax;
         for (int l = 0; l < kMaxLevels; ++l) {
@@ -93,7 +101,7 @@ bounds_kernel(const double2* __restrict__ pos, int64_t n, double* __restrict__ p
             float t2;
             if (!(theta > 0.0)) t2 = INFINITY;
             else if (thr < 0.0) t2 = -1.0f;
-            else t2 = (float)(thr * thr);
+            else t2 = (float)((thr * scale) * (thr * scale));
             consts->thr2[l] = t2;
             if (l < finest) {
                 xh = __dmul_rn(__dadd_rn(xl, xh), 0.5);

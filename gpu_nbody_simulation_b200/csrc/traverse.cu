@@ -22,8 +22,11 @@
 // Arithmetic.  FP32 mode (default): the displacement COM - x is formed from double-float pairs
 // (hi + lo), exact to ~2^-48 of the coordinate, everything after it is FP32 (forces are
 // dominated by self-inclusive cap-leaf interactions at distances ~1e-8 of coordinates ~0.1).
-// size/(d+eps) < theta is evaluated as d2 > (size/theta - eps)^2 with the per-level constant
-// precomputed in FP64.  FP64 mode (BH_FLAG_FP64_TRAVERSAL): the reference's expressions verbatim.
+// Coordinates are pre-multiplied by a power of two (StepConsts::scale) so that d2 (d + eps) stays
+// inside the FP32 exponent range; the factor cancels in the force.  size/(d+eps) < theta is
+// evaluated as d2 > (size/theta - eps)^2 with the per-level constant precomputed in FP64.
+// Limit of this mode: separations below ~2^-48 of the coordinate (exactly coincident bodies whose
+// COM differs from them by one FP64 ulp) cannot be resolved; use the FP64 mode for those.  FP64 mode (BH_FLAG_FP64_TRAVERSAL): the reference's expressions verbatim.
 #include "bh_internal.h"
 
 namespace bh {
@@ -55,6 +58,17 @@ struct TravArgs {
     uint32_t level_off[kMaxLevels];
 };
 
+__device__ __forceinline__ float approx_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float approx_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <bool FP64, bool INTEGRATE, bool COUNT>
 __global__ void __launch_bounds__(kTravThreads)
 traverse_kernel(const __grid_constant__ TravArgs a) {
@@ -74,10 +88,12 @@ traverse_kernel(const __grid_constant__ TravArgs a) {
         px = p.x; py = p.y;
         mi = a.mass[body];
     }
-    // double-float split of the body position (FP32 mode)
-    const float xh = (float)px, yh = (float)py;
-    const float xl = (float)(px - (double)xh), yl = (float)(py - (double)yh);
-    const float feps = (float)a.dist_eps;
+    // double-float split of the (power-of-two scaled) body position (FP32 mode)
+    const double scale = a.consts->scale;
+    const double spx = px * scale, spy = py * scale;
+    const float xh = (float)spx, yh = (float)spy;
+    const float xl = (float)(spx - (double)xh), yl = (float)(spy - (double)yh);
+    const float feps = a.consts->feps;
 
     float ax = 0.f, ay = 0.f;        // FP32 mode: sum of G M d / (d2 (d+eps)), times m_i at the end
     double sx = 0.0, sy = 0.0;       // FP64 mode: the reference's `sum`
@@ -105,10 +121,9 @@ traverse_kernel(const __grid_constant__ TravArgs a) {
             const float dy = (r.chy - yh) + (r.cly - yl);
             const float d2 = fmaf(dx, dx, dy * dy);
             accept = leaf || (d2 > thr2);
-            const float inv = rsqrtf(d2);
-            const float t = inv * inv;                // 1 / d2
-            const float u = fmaf(-feps, t, inv);      // 1 / (d + eps) to first order in eps / d
-            float f = r.gm * t * u;
+            // G M / (d2 (d + eps)), project.cu:765-769; d2 == 0 -> inf, times dx == 0 -> NaN like the reference
+            const float w = d2 * (approx_sqrt(d2) + feps);
+            float f = r.gm * approx_rcp(w);
             f = (active && nz && accept && !self) ? f : 0.f;
             ax = fmaf(f, dx, ax);
             ay = fmaf(f, dy, ay);

@@ -61,13 +61,15 @@ __device__ __forceinline__ Cell combine4(const Cell c[4], const uint32_t* __rest
     return p;
 }
 
+// G here is G * scale^2 and `scale` the power-of-two coordinate normalisation (StepConsts::scale).
 __device__ __forceinline__ void store_cell(const TreeArrays& t, uint64_t at, const Cell& c, int level, int finest,
-                                           double G, double mass_eps) {
+                                           double G, double mass_eps, double scale) {
     t.mass[at] = c.m; t.comx[at] = c.cx; t.comy[at] = c.cy;
     t.count[at] = c.cnt; t.first[at] = c.first;
     NodeRec r;
-    r.chx = (float)c.cx; r.chy = (float)c.cy;
-    r.clx = (float)(c.cx - (double)r.chx); r.cly = (float)(c.cy - (double)r.chy);
+    const double sx = c.cx * scale, sy = c.cy * scale;
+    r.chx = (float)sx; r.chy = (float)sy;
+    r.clx = (float)(sx - (double)r.chx); r.cly = (float)(sy - (double)r.chy);
     r.gm = (float)(G * c.m);
     r.flags = (c.m > mass_eps ? kNodeNonZero : 0u) | ((c.cnt <= 1u || level == finest) ? kNodeLeaf : 0u) |
               (c.cnt == 1u ? kNodeSingle : 0u);
@@ -155,9 +157,11 @@ __device__ __forceinline__ Cell shfl_cell(const Cell& c, int src_lane) {
 
 __global__ void __launch_bounds__(kBottomThreads)
 tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, const double2* __restrict__ pos,
-                   const double* __restrict__ mass, double G, double mass_eps, uint32_t exact_leaf_max,
-                   unsigned long long* __restrict__ counters) {
+                   const double* __restrict__ mass, double G0, double mass_eps, uint32_t exact_leaf_max,
+                   unsigned long long* __restrict__ counters, const StepConsts* __restrict__ consts) {
     const int F = d.finest;
+    const double scale = consts->scale;
+    const double G = G0 * scale * scale;
     const int tid = threadIdx.x, lane = tid & 31;
     const uint64_t offF = d.level_off[F];
     __shared__ Cell s_cells[kBottomThreads / 16];   // level F-3 results (16 per block)
@@ -194,7 +198,7 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
                     c.m = t.mass[offF + code]; c.cx = t.comx[offF + code]; c.cy = t.comy[offF + code];
                 }
             }
-            store_cell(t, offF + code, c, F, F, G, mass_eps);
+            store_cell(t, offF + code, c, F, F, G, mass_eps, scale);
         }
         leaf[q] = c;
     }
@@ -208,7 +212,7 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
     uint64_t code = parent_code;
     uint64_t ncells = d.ncells_finest >> 2;
     if (code < ncells) {
-        store_cell(t, d.level_off[level] + code, cur, level, F, G, mass_eps);
+        store_cell(t, d.level_off[level] + code, cur, level, F, G, mass_eps, scale);
         n_internal += (cur.cnt >= 2u);
     }
     // ---- levels F-2, F-3: shuffles inside the warp (groups of 4, then 16 lanes)
@@ -222,7 +226,7 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
         bool owner = (lane & (4 * stride - 1)) == 0;
         Cell up = combine4(ch, sidx, pos, mass);
         if (owner && code < ncells) {
-            store_cell(t, d.level_off[level] + code, up, level, F, G, mass_eps);
+            store_cell(t, d.level_off[level] + code, up, level, F, G, mass_eps, scale);
             n_internal += (up.cnt >= 2u);
         }
         cur = up;
@@ -239,7 +243,7 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
             Cell up = combine4(ch, sidx, pos, mass);
             uint64_t c4 = (uint64_t)blockIdx.x * 4 + tid;
             if (c4 < (ncells >> 2)) {
-                store_cell(t, d.level_off[l4] + c4, up, l4, F, G, mass_eps);
+                store_cell(t, d.level_off[l4] + c4, up, l4, F, G, mass_eps, scale);
                 n_internal += (up.cnt >= 2u);
             }
             s_cells4[tid] = up;
@@ -251,7 +255,7 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
             int l5 = l4 - 1;
             uint64_t c5code = blockIdx.x;
             if (c5code < (ncells >> 4)) {
-                store_cell(t, d.level_off[l5] + c5code, top, l5, F, G, mass_eps);
+                store_cell(t, d.level_off[l5] + c5code, top, l5, F, G, mass_eps, scale);
                 n_internal += (top.cnt >= 2u);
             }
         }
@@ -271,9 +275,11 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
 // ---- top kernel: remaining levels (F-6 .. 0), one block, level by level through global memory ----
 __global__ void __launch_bounds__(1024)
 tree_top_kernel(TreeArrays t, Dims d, int top_level, const uint32_t* __restrict__ sidx,
-                const double2* __restrict__ pos, const double* __restrict__ mass, double G, double mass_eps,
-                unsigned long long* __restrict__ counters) {
+                const double2* __restrict__ pos, const double* __restrict__ mass, double G0, double mass_eps,
+                unsigned long long* __restrict__ counters, const StepConsts* __restrict__ consts) {
     const int F = d.finest;
+    const double scale = consts->scale;
+    const double G = G0 * scale * scale;
     __shared__ uint32_t s_int;
     if (threadIdx.x == 0) s_int = 0;
     __syncthreads();
@@ -290,7 +296,7 @@ tree_top_kernel(TreeArrays t, Dims d, int top_level, const uint32_t* __restrict_
                 ch[q].cnt = t.count[a]; ch[q].first = t.first[a];
             }
             Cell up = combine4(ch, sidx, pos, mass);
-            store_cell(t, off + c, up, level, F, G, mass_eps);
+            store_cell(t, off + c, up, level, F, G, mass_eps, scale);
             n_internal += (up.cnt >= 2u);
         }
         __syncthreads();   // level `level` complete and visible to the block
@@ -309,7 +315,6 @@ tree_top_kernel(TreeArrays t, Dims d, int top_level, const uint32_t* __restrict_
 void launch_tree(const uint32_t* skeys, const uint32_t* sidx, const double2* pos, const double* mass,
                  int64_t n, const bh_params& p, const Dims& d, TreeArrays& t, Scratch& s,
                  const StepConsts* consts, cudaStream_t st) {
-    (void)consts;
     const int F = d.finest;
     uint32_t* cnt_f = t.count + d.level_off[F];
     uint32_t* first_f = t.first + d.level_off[F];
@@ -324,13 +329,13 @@ void launch_tree(const uint32_t* skeys, const uint32_t* sidx, const double2* pos
     uint64_t parents = F == 0 ? 1 : (d.ncells_finest >> 2);
     unsigned blocks = (unsigned)((parents + kBottomThreads - 1) / kBottomThreads);
     tree_bottom_kernel<<<blocks, kBottomThreads, 0, st>>>(t, d, sidx, pos, mass, p.G, p.mass_eps, exact_max,
-                                                          s.counters);
+                                                          s.counters, consts);
     ++g_launches;
     int top_level = F - 6;   // bottom kernel covered F .. F-5
     if (F >= 1) {
         if (top_level < 0) top_level = -1;
         // when the bottom kernel already reached the root (F <= 5) only the node count remains
-        tree_top_kernel<<<1, 1024, 0, st>>>(t, d, top_level, sidx, pos, mass, p.G, p.mass_eps, s.counters);
+        tree_top_kernel<<<1, 1024, 0, st>>>(t, d, top_level, sidx, pos, mass, p.G, p.mass_eps, s.counters, consts);
         ++g_launches;
     }
 }

@@ -1,0 +1,32 @@
+"""Small driver for ncu / compute-sanitizer: a few whole steps of the hot path, direct launches.
+
+    python tools/profile_step.py [--n 1000000] [--steps 3] [--dist disk|plummer|square] [--fp64] [--counters]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gpu_nbody_simulation_b200 as bh  # noqa: E402
+from gpu_nbody_simulation_b200 import initial_conditions as ic  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=1_000_000)
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--dist", default="disk")
+ap.add_argument("--fp64", action="store_true")
+ap.add_argument("--counters", action="store_true")
+ap.add_argument("--max-depth", type=int, default=10)
+a = ap.parse_args()
+gen = {"disk": ic.uniform_disk, "plummer": ic.plummer_2d, "square": ic.uniform_square}[a.dist]
+pos, vel, mass = gen(a.n, seed=12345, round6=False)
+with bh.Simulation(a.n, graph=False, fp64=a.fp64, counters=a.counters, max_depth=a.max_depth) as sim:
+    sim.set_bodies(pos, vel, mass)
+    sim.snapshot()
+    sim.set_profiling(True)
+    sim.step_from_snapshot(a.steps)
+    sim.synchronize()
+    t = sim.timers()
+    print({k: round(v / max(t["steps"], 1), 1) if k.endswith("_us") else v for k, v in t.items()})
+    if a.counters:
+        print(sim.counters())
