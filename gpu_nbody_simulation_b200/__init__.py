@@ -202,7 +202,9 @@ class Simulation:
             flags |= BH_FLAG_COUNTERS
         if not graph:
             flags |= BH_FLAG_NO_GRAPH
+        bpl = int(over.pop("bodies_per_lane", 0))
         self.params = default_params(n_bodies=n_bodies, flags=flags, **over)
+        self.params.reserved[0] = bpl      # traversal tuning knob (include/bh.h)
         self.n = int(n_bodies)
         self._h = C.c_void_p()
         _check(lib().bh_create(C.byref(self.params), C.byref(self._h)))

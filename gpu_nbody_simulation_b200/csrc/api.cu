@@ -107,6 +107,7 @@ struct bh_ctx {
     int sorted = 0;               // which of keys[]/idx[] holds the sorted result
     StepConsts* consts = nullptr;
     TreeArrays tree{};
+    NodeRec* rec_alloc = nullptr;
     Scratch s{};
     float4* packed = nullptr;     // direct-sum kernel input
     // multi-GPU
@@ -196,6 +197,7 @@ int exchange_slices(bh_ctx* c, void* base, size_t elem_bytes) {
 void zero_scratch(bh_ctx* c) {
     cudaMemsetAsync(c->s.zero_base, 0, c->s.zero_bytes, c->stream);
     cudaMemsetAsync(c->tree.count + c->d.level_off[c->d.finest], 0, c->d.ncells_finest * sizeof(uint32_t), c->stream);
+    cudaMemsetAsync(c->tree.self_node, 0xff, c->d.n * sizeof(uint32_t), c->stream);
     if (c->own_count) cudaMemsetAsync(c->own_count, 0, sizeof(uint32_t), c->stream);
 }
 
@@ -365,7 +367,10 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     BH_ALLOC(c->consts, 1);
     const uint64_t np = c->d.npyramid;
     BH_ALLOC(c->tree.mass, np); BH_ALLOC(c->tree.comx, np); BH_ALLOC(c->tree.comy, np);
-    BH_ALLOC(c->tree.count, np); BH_ALLOC(c->tree.first, np); BH_ALLOC(c->tree.rec, np);
+    BH_ALLOC(c->tree.count, np); BH_ALLOC(c->tree.first, np); BH_ALLOC(c->tree.flags, np);
+    BH_ALLOC(c->rec_alloc, np + 4);
+    c->tree.rec = c->rec_alloc + 3;   // 96-byte lead-in: sibling groups (4p+1 .. 4p+4) start on 128-byte lines
+    BH_ALLOC(c->tree.self_node, n);
     // zeroed scratch block
     const int nbins = 1 << c->sp.nbins_log2;
     size_t words = (size_t)kMaxSortPasses * kMaxBins + 16 /*tickets, heavy, bbox ticket*/ + 16 /*8 x u64 counters*/ +
@@ -410,7 +415,7 @@ int bh_destroy(bh_ctx* c) {
     if (c->comm) { NcclApi* api = nccl_api(); if (api) api->CommDestroy(c->comm); }
     void* ptrs[] = {c->pos, c->vel, c->acc, c->force, c->snap_pos, c->snap_vel, c->tmp2, c->mass, c->tmp1, c->keys[0],
                     c->keys[1], c->idx[0], c->idx[1], c->consts, c->tree.mass, c->tree.comx, c->tree.comy,
-                    c->tree.count, c->tree.first, c->tree.rec, c->s.zero_base, c->s.bbox_partial, c->s.heavy_list,
+                    c->tree.count, c->tree.first, c->tree.flags, c->rec_alloc, c->tree.self_node, c->s.zero_base, c->s.bbox_partial, c->s.heavy_list,
                     c->packed, c->own_list, c->own_count, c->perm};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);

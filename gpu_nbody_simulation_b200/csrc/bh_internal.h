@@ -15,6 +15,7 @@ constexpr int kSortItems = 16;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per tile
 constexpr int kMaxSortPasses = 4;
 constexpr int kMaxBins = 512;
+constexpr int kDefaultBodiesPerLane = 1;   // traversal: bodies per lane (bh_params.reserved[0] overrides: 1 or 2)
 
 // node flags (packed FP32 traversal record and FP64 verification path share them)
 constexpr uint32_t kNodeNonZero = 1u;  // mass > mass_eps         (project.cu:617 / :731)
@@ -22,12 +23,15 @@ constexpr uint32_t kNodeLeaf = 2u;     // all four children == -1 (project.cu:62
 constexpr uint32_t kNodeSingle = 4u;   // exactly one body inside (PARTICLE_INDEX == idx or -idx-2)
 
 // 32-byte traversal record; the four children of a cell are one 128-byte line.
+// Pyramid cells are indexed heap-style: root 0, children of cell p are 4p+1 .. 4p+4 (this equals
+// level_off[l] + Morton code).  `rec` is allocated with a 96-byte lead-in so that every sibling
+// group starts on a 128-byte line.
 struct __align__(32) NodeRec {
-    float chx, chy;   // COM, high float of the double-float pair
-    float clx, cly;   // COM, low float   (com = ch + cl to ~2^-48)
-    float gm;         // (float)(G * mass)
-    uint32_t flags;   // kNode*
-    uint32_t count;   // bodies in the cell (saturating at 2^32-1 is impossible: N < 2^32)
+    float chx, chy;   // scaled COM, high float of the double-float pair
+    float clx, cly;   // scaled COM, low float   (com = ch + cl to ~2^-48)
+    float gm;         // (float)(G * mass * scale^2); 0 for nodes the reference skips (mass <= mass_eps)
+    float thr;        // lane accepts iff !(d2 <= thr): level threshold, or -1 for leaves / skipped nodes
+    uint32_t count;   // bodies in the cell
     uint32_t first;   // sorted position of the cell's first body
 };
 
@@ -51,7 +55,9 @@ struct TreeArrays {
     double* comy;
     uint32_t* count;   // bodies per cell
     uint32_t* first;   // sorted position of first body
+    uint32_t* flags;   // kNode* (verification / counting paths)
     NodeRec* rec;
+    uint32_t* self_node;  // per body: pyramid index of the leaf holding only that body, else 0xffffffff
 };
 
 struct Scratch {

@@ -3,30 +3,35 @@
 // Replaces computeForcesGpu (project.cu:679-793; CPU twin computeForces :593-675) and
 // updateAccVelPos (project.cu:819-836).
 //
-// One warp owns 32 consecutive bodies of the Morton-sorted order (lane = body) and walks the
-// dense pyramid depth first with ONE warp-shared stack in shared memory.  A stack entry is
-// (parent cell, mask of the lanes that opened it).  Popping a parent evaluates its four children
-// (one 128-byte line of NodeRec, warp-uniform 128-bit loads) for all participating lanes; every
-// lane applies the reference's test on its own:
+// One warp owns 32*BPL consecutive bodies of the Morton-sorted order (each lane BPL of them) and
+// walks the dense pyramid depth first with ONE warp-shared stack in shared memory.  A stack entry
+// is (cell p, mask of the bodies that opened it).  Popping p evaluates its four children
+// 4p+1 .. 4p+4 (one 128-byte line of NodeRec, warp-uniform vector loads) for all participating
+// bodies; every body applies the reference's test on its own:
 //
 //     skip   if mass <= mass_eps                                        project.cu:731
 //     accept if leaf || size / (sqrt(d2) + eps) < theta                 project.cu:757
 //     self   if leaf && sole occupant == this body -> no force          project.cu:760
-//     open   otherwise -> the lane's bit goes into the child's mask     project.cu:776-785
+//     open   otherwise -> the body's bit goes into the child's mask     project.cu:776-785
 //
 // __ballot_sync over "open" is the child's mask; a child nobody opens is never pushed.  Because a
-// lane takes part in a parent's children only if its bit is in the parent's mask, each body sees
+// body takes part in a cell's children only if its bit is in the cell's mask, each body sees
 // exactly the node set the reference's per-body DFS visits (per-lane acceptance semantics, SURVEY
 // H2) while the warp fetches every node once.  Only the floating-point summation order differs.
 //
-// Arithmetic.  FP32 mode (default): the displacement COM - x is formed from double-float pairs
-// (hi + lo), exact to ~2^-48 of the coordinate, everything after it is FP32 (forces are
-// dominated by self-inclusive cap-leaf interactions at distances ~1e-8 of coordinates ~0.1).
-// Coordinates are pre-multiplied by a power of two (StepConsts::scale) so that d2 (d + eps) stays
-// inside the FP32 exponent range; the factor cancels in the force.  size/(d+eps) < theta is
-// evaluated as d2 > (size/theta - eps)^2 with the per-level constant precomputed in FP64.
+// FP32 mode (default).  The tree build folds the node tests into the record: `thr` is the level's
+// (size/theta - eps)^2 for internal nodes and -1 for leaves and skipped nodes, so "accept" is the
+// single compare !(d2 <= thr); skipped nodes carry gm = 0 and a far-away COM; the self test is one
+// integer compare against the body's own leaf index (self_node, written by the build).  The
+// displacement COM - x is formed from double-float pairs (hi + lo), exact to ~2^-48 of the
+// coordinate (forces are dominated by self-inclusive cap-leaf interactions at distances
+// ~1e-8 of coordinates ~0.1), with packed FP32x2 instructions (FADD2 / FFMA2, sm_100); everything
+// after it is FP32.  Coordinates are pre-multiplied by a power of two (StepConsts::scale) so that
+// d2 (d + eps) stays inside the FP32 exponent range; the factor cancels in the force.
 // Limit of this mode: separations below ~2^-48 of the coordinate (exactly coincident bodies whose
-// COM differs from them by one FP64 ulp) cannot be resolved; use the FP64 mode for those.  FP64 mode (BH_FLAG_FP64_TRAVERSAL): the reference's expressions verbatim.
+// COM differs from them by one FP64 ulp) cannot be resolved; use the FP64 mode for those.
+//
+// FP64 mode (BH_FLAG_FP64_TRAVERSAL): the reference's expressions verbatim on the FP64 tree arrays.
 #include "bh_internal.h"
 
 namespace bh {
@@ -38,15 +43,16 @@ constexpr int kTravWarps = kTravThreads / 32;
 constexpr int kStackCap = 3 * kMaxDepthDense + 8;
 
 struct TravArgs {
-    const uint32_t* skeys;      // sorted cell keys
     const uint32_t* sidx;       // body index per sorted position
     const uint32_t* own_list;   // optional: sorted positions owned by this rank (multi-GPU)
+    const uint32_t* self_node;  // per body: its own single-occupant leaf (pyramid index) or 0xffffffff
     double2* pos;
     double2* vel;
     double2* acc;
     double2* force;
     const double* mass;
     const NodeRec* rec;
+    const uint32_t* flags;
     const double* t_mass;
     const double* t_comx;
     const double* t_comy;
@@ -54,8 +60,6 @@ struct TravArgs {
     unsigned long long* counters;
     int64_t n_slots;            // bodies this launch evaluates
     double G, dt, theta, dist_eps;
-    int finest;
-    uint32_t level_off[kMaxLevels];
 };
 
 __device__ __forceinline__ float approx_sqrt(float x) {
@@ -68,77 +72,211 @@ __device__ __forceinline__ float approx_rcp(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ void sts_entry(uint32_t addr, uint32_t a, uint32_t b, uint32_t c) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %3};" ::"r"(addr), "r"(a), "r"(b), "r"(c) : "memory");
+}
+__device__ __forceinline__ uint4 lds_entry(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 
-template <bool FP64, bool INTEGRATE, bool COUNT>
+// epilogue shared by all variants: force, and optionally a = F/m, v += a dt, x += v dt
+template <bool INTEGRATE>
+__device__ __forceinline__ void finish_body(const TravArgs& a, uint32_t body, double px, double py, double mi,
+                                            double fx, double fy) {
+    a.force[body] = make_double2(fx, fy);
+    if constexpr (INTEGRATE) {
+        const double accx = __ddiv_rn(fx, mi), accy = __ddiv_rn(fy, mi);      // project.cu:827-828
+        double2 v = a.vel[body];
+        v.x = __dadd_rn(v.x, __dmul_rn(accx, a.dt));                          // project.cu:830-831
+        v.y = __dadd_rn(v.y, __dmul_rn(accy, a.dt));
+        const double nx = __dadd_rn(px, __dmul_rn(v.x, a.dt));               // project.cu:833-834
+        const double ny = __dadd_rn(py, __dmul_rn(v.y, a.dt));
+        a.acc[body] = make_double2(accx, accy);
+        a.vel[body] = v;
+        a.pos[body] = make_double2(nx, ny);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP32 traversal, BPL bodies per lane
+// ------------------------------------------------------------------------------------------------
+template <int BPL, bool INTEGRATE, bool COUNT>
 __global__ void __launch_bounds__(kTravThreads)
-traverse_kernel(const __grid_constant__ TravArgs a) {
+traverse_f32_kernel(const __grid_constant__ TravArgs a) {
+    __shared__ uint4 s_stack[kTravWarps][kStackCap];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warp_slot0 = ((int64_t)blockIdx.x * kTravWarps + warp) * (32 * BPL);
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&s_stack[warp][0]);
+
+    uint32_t body[BPL], selfn[BPL];
+    bool live[BPL];
+    double px[BPL], py[BPL], mi[BPL];
+    float2 nh[BPL], nl[BPL];     // minus the scaled body position, hi and lo floats
+    float2 acc2[BPL];            // sum of G M d / (d2 (d + eps)); times m_i at the end
+    const double scale = a.consts->scale;
+    const float feps = a.consts->feps;
+#pragma unroll
+    for (int b = 0; b < BPL; ++b) {
+        const int64_t slot = warp_slot0 + b * 32 + lane;
+        live[b] = slot < a.n_slots;
+        body[b] = 0; selfn[b] = 0xffffffffu; px[b] = py[b] = 0.0; mi[b] = 0.0;
+        if (live[b]) {
+            uint32_t sp = a.own_list ? a.own_list[slot] : (uint32_t)slot;
+            body[b] = a.sidx[sp];
+            selfn[b] = a.self_node[body[b]];
+            double2 p = a.pos[body[b]];
+            px[b] = p.x; py[b] = p.y;
+            mi[b] = a.mass[body[b]];
+        }
+        const double sx = px[b] * scale, sy = py[b] * scale;
+        const float xh = (float)sx, yh = (float)sy;
+        nh[b] = make_float2(-xh, -yh);
+        nl[b] = make_float2(-(float)(sx - (double)xh), -(float)(sy - (double)yh));
+        acc2[b] = make_float2(0.f, 0.f);
+    }
+    uint32_t c_int = 0, c_vis = 0, c_open = 0, c_steps = 0;
+
+    // Evaluate node `idx` for body slot b of this lane.  Returns true if the body opens it.
+    auto eval = [&](const float4 A, const float2 B, uint32_t idx, int b, bool active) -> bool {
+        const float2 dh = __fadd2_rn(make_float2(A.x, A.y), nh[b]);
+        const float2 dl = __fadd2_rn(make_float2(A.z, A.w), nl[b]);
+        const float2 d = __fadd2_rn(dh, dl);
+        const float d2 = fmaf(d.x, d.x, d.y * d.y);
+        const bool accept = !(d2 <= B.y);                                   // leaf || size/(d+eps) < theta
+        // G M / (d2 (d + eps)), project.cu:765-769; d2 == 0 -> inf, times dx == 0 -> NaN like the reference
+        const float w = d2 * (approx_sqrt(d2) + feps);
+        float f = B.x * approx_rcp(w);
+        const bool use = active && accept && (selfn[b] != idx);
+        f = use ? f : 0.f;
+        acc2[b] = __ffma2_rn(make_float2(f, f), d, acc2[b]);
+        if constexpr (COUNT) {
+            const uint32_t fl = a.flags[idx];
+            c_vis += active;
+            c_int += (use && (fl & kNodeNonZero));
+            c_open += (active && !accept);
+        }
+        return active && !accept;
+    };
+
+    int top = 0;
+    {   // the root (project.cu:711-715 pushes node 0)
+        const float4 A = __ldg(reinterpret_cast<const float4*>(a.rec));
+        const float2 B = __ldg(reinterpret_cast<const float2*>(a.rec) + 2);
+        uint32_t m[BPL];
+        uint32_t any = 0;
+#pragma unroll
+        for (int b = 0; b < BPL; ++b) {
+            bool open = eval(A, B, 0u, b, live[b]);
+            m[b] = __ballot_sync(0xffffffffu, open);
+            any |= m[b];
+        }
+        if (any) {
+            if (lane == 0) sts_entry(sbase, 0u, m[0], m[BPL - 1]);
+            top = 1;
+        }
+        __syncwarp();
+    }
+    while (top > 0) {
+        --top;
+        const uint4 e = lds_entry(sbase + (uint32_t)top * 16u);
+        __syncwarp();
+        const uint32_t base = 4u * e.x + 1u;
+        const NodeRec* __restrict__ rp = a.rec + base;
+        bool active[BPL];
+        active[0] = (e.y >> lane) & 1u;
+        if constexpr (BPL > 1) active[BPL - 1] = (e.z >> lane) & 1u;
+        if constexpr (COUNT) c_steps += (lane == 0);
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) {
+            const float4 A = __ldg(reinterpret_cast<const float4*>(rp + q));        // chx chy clx cly
+            const float2 B = __ldg(reinterpret_cast<const float2*>(rp + q) + 2);    // gm thr
+            uint32_t m[BPL];
+            uint32_t any = 0;
+#pragma unroll
+            for (int b = 0; b < BPL; ++b) {
+                bool open = eval(A, B, base + q, b, active[b]);
+                m[b] = __ballot_sync(0xffffffffu, open);
+                any |= m[b];
+            }
+            if (any) {
+                if (lane == 0) sts_entry(sbase + (uint32_t)top * 16u, base + q, m[0], m[BPL - 1]);
+                ++top;
+            }
+        }
+        __syncwarp();
+    }
+
+#pragma unroll
+    for (int b = 0; b < BPL; ++b)
+        if (live[b])
+            finish_body<INTEGRATE>(a, body[b], px[b], py[b], mi[b], mi[b] * (double)acc2[b].x, mi[b] * (double)acc2[b].y);
+    if constexpr (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c_int += __shfl_xor_sync(0xffffffffu, c_int, o);
+            c_vis += __shfl_xor_sync(0xffffffffu, c_vis, o);
+            c_open += __shfl_xor_sync(0xffffffffu, c_open, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&a.counters[0], (unsigned long long)c_int);
+            atomicAdd(&a.counters[1], (unsigned long long)c_vis);
+            atomicAdd(&a.counters[2], (unsigned long long)c_open);
+            atomicAdd(&a.counters[3], (unsigned long long)c_steps);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 verification traversal: the reference's expressions, one body per lane
+// ------------------------------------------------------------------------------------------------
+template <bool INTEGRATE, bool COUNT>
+__global__ void __launch_bounds__(kTravThreads)
+traverse_f64_kernel(const __grid_constant__ TravArgs a) {
     __shared__ uint2 s_stack[kTravWarps][kStackCap];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t slot = ((int64_t)blockIdx.x * kTravWarps + warp) * 32 + lane;
     const bool live = slot < a.n_slots;
-    const int F = a.finest;
-
-    uint32_t body = 0, key = 0;
+    uint32_t body = 0, selfn = 0xffffffffu;
     double px = 0.0, py = 0.0, mi = 0.0;
     if (live) {
         uint32_t sp = a.own_list ? a.own_list[slot] : (uint32_t)slot;
         body = a.sidx[sp];
-        key = a.skeys[sp];
+        selfn = a.self_node[body];
         double2 p = a.pos[body];
         px = p.x; py = p.y;
         mi = a.mass[body];
     }
-    // double-float split of the (power-of-two scaled) body position (FP32 mode)
-    const double scale = a.consts->scale;
-    const double spx = px * scale, spy = py * scale;
-    const float xh = (float)spx, yh = (float)spy;
-    const float xl = (float)(spx - (double)xh), yl = (float)(spy - (double)yh);
-    const float feps = a.consts->feps;
-
-    float ax = 0.f, ay = 0.f;        // FP32 mode: sum of G M d / (d2 (d+eps)), times m_i at the end
-    double sx = 0.0, sy = 0.0;       // FP64 mode: the reference's `sum`
+    double sx = 0.0, sy = 0.0;       // the reference's `sum`
     uint32_t c_int = 0, c_vis = 0, c_open = 0, c_steps = 0;
 
-    // Evaluate one node for this lane.  Returns true if the lane opens it.
-    auto eval = [&](uint32_t node_index, uint32_t level, uint32_t code, bool active, float thr2, double size) -> bool {
-        const NodeRec r = a.rec[node_index];
-        const bool nz = r.flags & kNodeNonZero, leaf = r.flags & kNodeLeaf;
-        const bool self = leaf && (r.flags & kNodeSingle) && ((key >> (2 * (F - (int)level))) == code);
-        bool accept;
-        if constexpr (FP64) {
-            const double M = a.t_mass[node_index];
-            const double dx = a.t_comx[node_index] - px, dy = a.t_comy[node_index] - py;
-            const double d2 = dx * dx + dy * dy;
-            const double d = sqrt(d2) + a.dist_eps;                       // project.cu:748
-            accept = leaf || (size / d < a.theta);                        // project.cu:757
-            if (active && nz && accept && !self) {
-                const double fm = (a.G * mi * M) / d2;                    // project.cu:765
-                sx += fm * (dx / d);                                      // project.cu:768-772
-                sy += fm * (dy / d);
-            }
-        } else {
-            const float dx = (r.chx - xh) + (r.clx - xl);
-            const float dy = (r.chy - yh) + (r.cly - yl);
-            const float d2 = fmaf(dx, dx, dy * dy);
-            accept = leaf || (d2 > thr2);
-            // G M / (d2 (d + eps)), project.cu:765-769; d2 == 0 -> inf, times dx == 0 -> NaN like the reference
-            const float w = d2 * (approx_sqrt(d2) + feps);
-            float f = r.gm * approx_rcp(w);
-            f = (active && nz && accept && !self) ? f : 0.f;
-            ax = fmaf(f, dx, ax);
-            ay = fmaf(f, dy, ay);
+    auto eval = [&](uint32_t idx, bool active) -> bool {
+        const uint32_t fl = a.flags[idx];
+        const bool nz = fl & kNodeNonZero, leaf = fl & kNodeLeaf;
+        const int level = (31 - __clz(3u * idx + 1u)) >> 1;                  // 3 off[l] + 1 == 4^l
+        const double M = a.t_mass[idx];
+        const double dx = a.t_comx[idx] - px, dy = a.t_comy[idx] - py;
+        const double d2 = dx * dx + dy * dy;
+        const double d = sqrt(d2) + a.dist_eps;                               // project.cu:748
+        const bool accept = leaf || (a.consts->size[level] / d < a.theta);    // project.cu:757
+        const bool use = active && nz && accept && (selfn != idx);            // project.cu:731, :760
+        if (use) {
+            const double fm = (a.G * mi * M) / d2;                            // project.cu:765
+            sx += fm * (dx / d);                                              // project.cu:768-772
+            sy += fm * (dy / d);
         }
         if constexpr (COUNT) {
             c_vis += active;
-            c_int += (active && nz && accept && !self);
+            c_int += use;
             c_open += (active && nz && !accept);
         }
         return active && nz && !accept;
     };
 
     int top = 0;
-    {   // the root (project.cu:711-715 pushes node 0)
-        bool open = eval(0u, 0u, 0u, live, a.consts->thr2[0], FP64 ? a.consts->size[0] : 0.0);
+    {
+        bool open = eval(0u, live);
         uint32_t m = __ballot_sync(0xffffffffu, open);
         if (m) {
             if (lane == 0) s_stack[warp][0] = make_uint2(0u, m);
@@ -149,44 +287,21 @@ traverse_kernel(const __grid_constant__ TravArgs a) {
     while (top > 0) {
         const uint2 e = s_stack[warp][--top];
         __syncwarp();
-        const uint32_t plevel = e.x >> 28, pcode = e.x & 0x0fffffffu;
+        const uint32_t base = 4u * e.x + 1u;
         const bool active = (e.y >> lane) & 1u;
-        const uint32_t level = plevel + 1u;
-        const uint32_t base = a.level_off[level] + 4u * pcode;
-        const float thr2 = a.consts->thr2[level];
-        const double size = FP64 ? a.consts->size[level] : 0.0;
         if constexpr (COUNT) c_steps += (lane == 0);
 #pragma unroll
         for (uint32_t q = 0; q < 4; ++q) {
-            const uint32_t code = 4u * pcode + q;
-            bool open = eval(base + q, level, code, active, thr2, size);
+            bool open = eval(base + q, active);
             uint32_t m = __ballot_sync(0xffffffffu, open);
             if (m) {
-                if (lane == 0) s_stack[warp][top] = make_uint2((level << 28) | code, m);
+                if (lane == 0) s_stack[warp][top] = make_uint2(base + q, m);
                 ++top;
             }
         }
         __syncwarp();
     }
-
-    // ---- epilogue: force, and optionally a = F/m, v += a dt, x += v dt (project.cu:827-834) ----
-    if (live) {
-        double fx, fy;
-        if constexpr (FP64) { fx = sx; fy = sy; }
-        else { fx = mi * (double)ax; fy = mi * (double)ay; }
-        a.force[body] = make_double2(fx, fy);
-        if constexpr (INTEGRATE) {
-            const double accx = __ddiv_rn(fx, mi), accy = __ddiv_rn(fy, mi);
-            double2 v = a.vel[body];
-            v.x = __dadd_rn(v.x, __dmul_rn(accx, a.dt));
-            v.y = __dadd_rn(v.y, __dmul_rn(accy, a.dt));
-            const double nx = __dadd_rn(px, __dmul_rn(v.x, a.dt));
-            const double ny = __dadd_rn(py, __dmul_rn(v.y, a.dt));
-            a.acc[body] = make_double2(accx, accy);
-            a.vel[body] = v;
-            a.pos[body] = make_double2(nx, ny);
-        }
-    }
+    if (live) finish_body<INTEGRATE>(a, body, px, py, mi, sx, sy);
     if constexpr (COUNT) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -252,28 +367,36 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, double2* pos, 
                      const uint32_t* own_list, const uint32_t* own_count_dev, int64_t own_n,
                      const bh_params& p, const Dims& d, const TreeArrays& t, const StepConsts* consts,
                      unsigned long long* counters, bool integrate, cudaStream_t st) {
-    (void)own_lo; (void)own_hi; (void)own_count_dev; (void)n;
+    (void)own_lo; (void)own_hi; (void)own_count_dev; (void)n; (void)skeys; (void)d;
     TravArgs a;
-    a.skeys = skeys; a.sidx = sidx; a.own_list = own_list;
+    a.sidx = sidx; a.own_list = own_list; a.self_node = t.self_node;
     a.pos = pos; a.vel = vel; a.acc = acc; a.force = force; a.mass = mass;
-    a.rec = t.rec; a.t_mass = t.mass; a.t_comx = t.comx; a.t_comy = t.comy;
+    a.rec = t.rec; a.flags = t.flags; a.t_mass = t.mass; a.t_comx = t.comx; a.t_comy = t.comy;
     a.consts = consts; a.counters = counters;
     a.n_slots = own_n;
     a.G = p.G; a.dt = p.dt; a.theta = p.theta; a.dist_eps = p.dist_eps;
-    a.finest = d.finest;
-    for (int l = 0; l < kMaxLevels; ++l) a.level_off[l] = (uint32_t)d.level_off[l < d.max_depth ? l : d.max_depth];
     if (own_n <= 0) return;
-    unsigned blocks = (unsigned)((own_n + kTravThreads - 1) / kTravThreads);
     const bool fp64 = p.flags & BH_FLAG_FP64_TRAVERSAL, count = p.flags & BH_FLAG_COUNTERS;
-#define BH_TRAV(F, I, C) traverse_kernel<F, I, C><<<blocks, kTravThreads, 0, st>>>(a)
+    const int bpl = (p.reserved[0] == 1 || p.reserved[0] == 2) ? p.reserved[0] : kDefaultBodiesPerLane;
     if (fp64) {
-        if (integrate) { if (count) BH_TRAV(true, true, true); else BH_TRAV(true, true, false); }
-        else { if (count) BH_TRAV(true, false, true); else BH_TRAV(true, false, false); }
+        unsigned blocks = (unsigned)((own_n + kTravThreads - 1) / kTravThreads);
+        if (integrate) { if (count) traverse_f64_kernel<true, true><<<blocks, kTravThreads, 0, st>>>(a);
+                         else traverse_f64_kernel<true, false><<<blocks, kTravThreads, 0, st>>>(a); }
+        else { if (count) traverse_f64_kernel<false, true><<<blocks, kTravThreads, 0, st>>>(a);
+               else traverse_f64_kernel<false, false><<<blocks, kTravThreads, 0, st>>>(a); }
     } else {
-        if (integrate) { if (count) BH_TRAV(false, true, true); else BH_TRAV(false, true, false); }
-        else { if (count) BH_TRAV(false, false, true); else BH_TRAV(false, false, false); }
-    }
+        const int64_t per_block = (int64_t)kTravThreads * bpl;
+        unsigned blocks = (unsigned)((own_n + per_block - 1) / per_block);
+#define BH_TRAV(B, I, C) traverse_f32_kernel<B, I, C><<<blocks, kTravThreads, 0, st>>>(a)
+        if (bpl == 2) {
+            if (integrate) { if (count) BH_TRAV(2, true, true); else BH_TRAV(2, true, false); }
+            else { if (count) BH_TRAV(2, false, true); else BH_TRAV(2, false, false); }
+        } else {
+            if (integrate) { if (count) BH_TRAV(1, true, true); else BH_TRAV(1, true, false); }
+            else { if (count) BH_TRAV(1, false, true); else BH_TRAV(1, false, false); }
+        }
 #undef BH_TRAV
+    }
     ++g_launches;
 }
 

@@ -36,8 +36,11 @@ struct Cell {
 
 // Combine four children (in order 0..3) into their parent.  `single body` parents take the body
 // itself; internal parents follow ComputeMass.
+// When the parent is internal, every child holding exactly one body is that body's own leaf: its
+// pyramid index goes to self_node[body] (the traversal's self-interaction test, project.cu:646/:760).
 __device__ __forceinline__ Cell combine4(const Cell c[4], const uint32_t* __restrict__ sidx,
-                                         const double2* __restrict__ pos, const double* __restrict__ mass) {
+                                         const double2* __restrict__ pos, const double* __restrict__ mass,
+                                         uint32_t* __restrict__ self_node, uint64_t child_base, bool write_self) {
     Cell p;
     p.cnt = c[0].cnt + c[1].cnt + c[2].cnt + c[3].cnt;
     p.first = c[0].cnt ? c[0].first : c[1].cnt ? c[1].first : c[2].cnt ? c[2].first : c[3].first;
@@ -57,24 +60,42 @@ __device__ __forceinline__ Cell combine4(const Cell c[4], const uint32_t* __rest
         }
         if (tm > 0.0) { sx = __ddiv_rn(sx, tm); sy = __ddiv_rn(sy, tm); }
         p.m = tm; p.cx = sx; p.cy = sy;
+        if (write_self) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (c[q].cnt == 1u) self_node[sidx[c[q].first]] = (uint32_t)(child_base + q);
+        }
     }
     return p;
 }
 
 // G here is G * scale^2 and `scale` the power-of-two coordinate normalisation (StepConsts::scale).
+// The traversal record folds the reference's per-node tests into two numbers:
+//   thr : the lane accepts iff !(d2 <= thr).  Leaves (and zero-mass nodes, which the reference skips
+//         before any test, project.cu:617) get thr = -1, i.e. "always accept, never open";
+//   gm  : G M; zero-mass nodes carry gm = 0 and a far-away COM so they add exactly 0.
+constexpr float kFarAway = 1.152921504606847e18f;   // 2^60 in scaled units
+
 __device__ __forceinline__ void store_cell(const TreeArrays& t, uint64_t at, const Cell& c, int level, int finest,
-                                           double G, double mass_eps, double scale) {
+                                           double G, double mass_eps, double scale, float thr2_level,
+                                           const uint32_t* __restrict__ sidx) {
     t.mass[at] = c.m; t.comx[at] = c.cx; t.comy[at] = c.cy;
     t.count[at] = c.cnt; t.first[at] = c.first;
+    const bool nz = c.m > mass_eps, leaf = (c.cnt <= 1u || level == finest);
+    t.flags[at] = (nz ? kNodeNonZero : 0u) | (leaf ? kNodeLeaf : 0u) | (c.cnt == 1u ? kNodeSingle : 0u);
     NodeRec r;
-    const double sx = c.cx * scale, sy = c.cy * scale;
-    r.chx = (float)sx; r.chy = (float)sy;
-    r.clx = (float)(sx - (double)r.chx); r.cly = (float)(sy - (double)r.chy);
-    r.gm = (float)(G * c.m);
-    r.flags = (c.m > mass_eps ? kNodeNonZero : 0u) | ((c.cnt <= 1u || level == finest) ? kNodeLeaf : 0u) |
-              (c.cnt == 1u ? kNodeSingle : 0u);
+    if (nz) {
+        const double sx = c.cx * scale, sy = c.cy * scale;
+        r.chx = (float)sx; r.chy = (float)sy;
+        r.clx = (float)(sx - (double)r.chx); r.cly = (float)(sy - (double)r.chy);
+        r.gm = (float)(G * c.m);
+        r.thr = leaf ? -1.0f : thr2_level;
+    } else {
+        r.chx = kFarAway; r.chy = kFarAway; r.clx = 0.f; r.cly = 0.f; r.gm = 0.f; r.thr = -1.0f;
+    }
     r.count = c.cnt; r.first = c.first;
     t.rec[at] = r;
+    if (level == 0 && c.cnt == 1u) t.self_node[sidx[c.first]] = 0u;   // a lone body: the root is its leaf
 }
 
 // ---- finest-cell runs from the sorted keys ------------------------------------------------------
@@ -198,7 +219,7 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
                     c.m = t.mass[offF + code]; c.cx = t.comx[offF + code]; c.cy = t.comy[offF + code];
                 }
             }
-            store_cell(t, offF + code, c, F, F, G, mass_eps, scale);
+            store_cell(t, offF + code, c, F, F, G, mass_eps, scale, consts->thr2[F], sidx);
         }
         leaf[q] = c;
     }
@@ -207,12 +228,12 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
         return;
     }
     // ---- level F-1 (registers)
-    Cell cur = combine4(leaf, sidx, pos, mass);
+    Cell cur = combine4(leaf, sidx, pos, mass, t.self_node, offF + 4 * parent_code, parent_code < (d.ncells_finest >> 2));
     int level = F - 1;
     uint64_t code = parent_code;
     uint64_t ncells = d.ncells_finest >> 2;
     if (code < ncells) {
-        store_cell(t, d.level_off[level] + code, cur, level, F, G, mass_eps, scale);
+        store_cell(t, d.level_off[level] + code, cur, level, F, G, mass_eps, scale, consts->thr2[level], sidx);
         n_internal += (cur.cnt >= 2u);
     }
     // ---- levels F-2, F-3: shuffles inside the warp (groups of 4, then 16 lanes)
@@ -222,11 +243,12 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
         Cell ch[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) ch[q] = shfl_cell(cur, (lane & ~(4 * stride - 1)) + q * stride);
+        const uint64_t child_base = d.level_off[level] + 4 * (code >> 2);
         --level; code >>= 2; ncells >>= 2;
         bool owner = (lane & (4 * stride - 1)) == 0;
-        Cell up = combine4(ch, sidx, pos, mass);
+        Cell up = combine4(ch, sidx, pos, mass, t.self_node, child_base, owner && code < ncells);
         if (owner && code < ncells) {
-            store_cell(t, d.level_off[level] + code, up, level, F, G, mass_eps, scale);
+            store_cell(t, d.level_off[level] + code, up, level, F, G, mass_eps, scale, consts->thr2[level], sidx);
             n_internal += (up.cnt >= 2u);
         }
         cur = up;
@@ -240,10 +262,10 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
             Cell ch[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) ch[q] = s_cells[tid * 4 + q];
-            Cell up = combine4(ch, sidx, pos, mass);
             uint64_t c4 = (uint64_t)blockIdx.x * 4 + tid;
+            Cell up = combine4(ch, sidx, pos, mass, t.self_node, d.level_off[level] + 4 * c4, c4 < (ncells >> 2));
             if (c4 < (ncells >> 2)) {
-                store_cell(t, d.level_off[l4] + c4, up, l4, F, G, mass_eps, scale);
+                store_cell(t, d.level_off[l4] + c4, up, l4, F, G, mass_eps, scale, consts->thr2[l4], sidx);
                 n_internal += (up.cnt >= 2u);
             }
             s_cells4[tid] = up;
@@ -251,11 +273,12 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
         __syncthreads();
         // level F-5: one cell per block
         if (l4 > 0 && tid == 0) {
-            Cell top = combine4(s_cells4, sidx, pos, mass);
             int l5 = l4 - 1;
             uint64_t c5code = blockIdx.x;
+            Cell top = combine4(s_cells4, sidx, pos, mass, t.self_node, d.level_off[l4] + 4 * c5code,
+                                c5code < (ncells >> 4));
             if (c5code < (ncells >> 4)) {
-                store_cell(t, d.level_off[l5] + c5code, top, l5, F, G, mass_eps, scale);
+                store_cell(t, d.level_off[l5] + c5code, top, l5, F, G, mass_eps, scale, consts->thr2[l5], sidx);
                 n_internal += (top.cnt >= 2u);
             }
         }
@@ -295,8 +318,8 @@ tree_top_kernel(TreeArrays t, Dims d, int top_level, const uint32_t* __restrict_
                 ch[q].m = t.mass[a]; ch[q].cx = t.comx[a]; ch[q].cy = t.comy[a];
                 ch[q].cnt = t.count[a]; ch[q].first = t.first[a];
             }
-            Cell up = combine4(ch, sidx, pos, mass);
-            store_cell(t, off + c, up, level, F, G, mass_eps, scale);
+            Cell up = combine4(ch, sidx, pos, mass, t.self_node, offc + 4 * c, true);
+            store_cell(t, off + c, up, level, F, G, mass_eps, scale, consts->thr2[level], sidx);
             n_internal += (up.cnt >= 2u);
         }
         __syncthreads();   // level `level` complete and visible to the block

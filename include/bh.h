@@ -62,7 +62,7 @@ typedef struct bh_params {
      * renumbering; each step all-gathers positions over NCCL (no reference counterpart). */
     int32_t rank;         /* 0 .. n_ranks-1 */
     int32_t n_ranks;      /* 1 = single GPU */
-    int32_t reserved[4];
+    int32_t reserved[4];  /* reserved[0]: tuning knob, bodies per traversal lane (0 = default, 1 or 2) */
 } bh_params;
 
 typedef struct bh_ctx bh_ctx; /* opaque; owns device memory, stream, CUDA graph, NCCL comm */
