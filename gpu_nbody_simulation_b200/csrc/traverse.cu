@@ -72,15 +72,6 @@ __device__ __forceinline__ float approx_rcp(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ void sts_entry(uint32_t addr, uint32_t a, uint32_t b, uint32_t c) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %3};" ::"r"(addr), "r"(a), "r"(b), "r"(c) : "memory");
-}
-__device__ __forceinline__ uint4 lds_entry(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-
 // epilogue shared by all variants: force, and optionally a = F/m, v += a dt, x += v dt
 template <bool INTEGRATE>
 __device__ __forceinline__ void finish_body(const TravArgs& a, uint32_t body, double px, double py, double mi,
@@ -102,62 +93,104 @@ __device__ __forceinline__ void finish_body(const TravArgs& a, uint32_t body, do
 // ------------------------------------------------------------------------------------------------
 // FP32 traversal, BPL bodies per lane
 // ------------------------------------------------------------------------------------------------
+constexpr float kFarLane = -1.152921504606847e18f;   // -2^60: where bodies outside a cell's mask "stand"
+
+template <int BPL> struct StackEntry;
+template <> struct StackEntry<1> {
+    static constexpr uint32_t kBytes = 8;
+    static __device__ __forceinline__ void store(uint32_t addr, uint32_t node, const uint32_t (&m)[1]) {
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(node), "r"(m[0]) : "memory");
+    }
+    static __device__ __forceinline__ void store_if(uint32_t doit, uint32_t addr, uint32_t node, const uint32_t (&m)[1]) {
+        asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %0, 0;\n @p st.shared.v2.u32 [%1], {%2, %3};\n}" ::"r"(doit),
+                     "r"(addr), "r"(node), "r"(m[0]) : "memory");
+    }
+    static __device__ __forceinline__ void load(uint32_t addr, uint32_t& node, uint32_t (&m)[1]) {
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(node), "=r"(m[0]) : "r"(addr) : "memory");
+    }
+};
+template <> struct StackEntry<2> {
+    static constexpr uint32_t kBytes = 16;
+    static __device__ __forceinline__ void store(uint32_t addr, uint32_t node, const uint32_t (&m)[2]) {
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %3};" ::"r"(addr), "r"(node), "r"(m[0]), "r"(m[1]) : "memory");
+    }
+    static __device__ __forceinline__ void store_if(uint32_t doit, uint32_t addr, uint32_t node, const uint32_t (&m)[2]) {
+        asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %0, 0;\n @p st.shared.v4.u32 [%1], {%2, %3, %4, %4};\n}" ::"r"(doit),
+                     "r"(addr), "r"(node), "r"(m[0]), "r"(m[1]) : "memory");
+    }
+    static __device__ __forceinline__ void load(uint32_t addr, uint32_t& node, uint32_t (&m)[2]) {
+        uint32_t pad;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(node), "=r"(m[0]), "=r"(m[1]), "=r"(pad) : "r"(addr) : "memory");
+    }
+};
+
 template <int BPL, bool INTEGRATE, bool COUNT>
-__global__ void __launch_bounds__(kTravThreads)
+__global__ void __launch_bounds__(kTravThreads, BPL == 1 ? 8 : 5)
 traverse_f32_kernel(const __grid_constant__ TravArgs a) {
-    __shared__ uint4 s_stack[kTravWarps][kStackCap];
+    using SE = StackEntry<BPL>;
+    __shared__ __align__(16) uint8_t s_stack[kTravWarps][kStackCap * SE::kBytes];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t warp_slot0 = ((int64_t)blockIdx.x * kTravWarps + warp) * (32 * BPL);
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&s_stack[warp][0]);
 
     uint32_t body[BPL], selfn[BPL];
-    bool live[BPL];
-    double px[BPL], py[BPL], mi[BPL];
     float2 nh[BPL], nl[BPL];     // minus the scaled body position, hi and lo floats
     float2 acc2[BPL];            // sum of G M d / (d2 (d + eps)); times m_i at the end
-    const double scale = a.consts->scale;
     const float feps = a.consts->feps;
+    {
+        const double scale = a.consts->scale;
 #pragma unroll
-    for (int b = 0; b < BPL; ++b) {
-        const int64_t slot = warp_slot0 + b * 32 + lane;
-        live[b] = slot < a.n_slots;
-        body[b] = 0; selfn[b] = 0xffffffffu; px[b] = py[b] = 0.0; mi[b] = 0.0;
-        if (live[b]) {
-            uint32_t sp = a.own_list ? a.own_list[slot] : (uint32_t)slot;
-            body[b] = a.sidx[sp];
-            selfn[b] = a.self_node[body[b]];
-            double2 p = a.pos[body[b]];
-            px[b] = p.x; py[b] = p.y;
-            mi[b] = a.mass[body[b]];
+        for (int b = 0; b < BPL; ++b) {
+            const int64_t slot = warp_slot0 + b * 32 + lane;
+            body[b] = 0xffffffffu; selfn[b] = 0xffffffffu;
+            double px = 0.0, py = 0.0;
+            if (slot < a.n_slots) {
+                uint32_t sp = a.own_list ? a.own_list[slot] : (uint32_t)slot;
+                body[b] = a.sidx[sp];
+                selfn[b] = a.self_node[body[b]];
+                double2 p = a.pos[body[b]];
+                px = p.x; py = p.y;
+            }
+            const double sx = px * scale, sy = py * scale;
+            const float xh = (float)sx, yh = (float)sy;
+            nh[b] = make_float2(-xh, -yh);
+            nl[b] = make_float2(-(float)(sx - (double)xh), -(float)(sy - (double)yh));
+            acc2[b] = make_float2(0.f, 0.f);
         }
-        const double sx = px[b] * scale, sy = py[b] * scale;
-        const float xh = (float)sx, yh = (float)sy;
-        nh[b] = make_float2(-xh, -yh);
-        nl[b] = make_float2(-(float)(sx - (double)xh), -(float)(sy - (double)yh));
-        acc2[b] = make_float2(0.f, 0.f);
     }
     uint32_t c_int = 0, c_vis = 0, c_open = 0, c_steps = 0;
 
-    // Evaluate node `idx` for body slot b of this lane.  Returns true if the body opens it.
-    auto eval = [&](const float4 A, const float2 B, uint32_t idx, int b, bool active) -> bool {
-        const float2 dh = __fadd2_rn(make_float2(A.x, A.y), nh[b]);
+    // Evaluate one node for body slot b of this lane; `mh` is minus the body's scaled position (hi
+    // floats) or the far-away stand-in when the body is not in the parent's mask: such a body accepts
+    // everything (never opens) and receives exactly 0 (w overflows to inf, 1/inf == 0).
+    // Returns the warp's ballot of the bodies (slot b of every lane) that open the node.
+    auto eval = [&](const float4 A, const float2 B, uint32_t idx, int b, const float2 mh, bool active) -> uint32_t {
+        const float2 dh = __fadd2_rn(make_float2(A.x, A.y), mh);
         const float2 dl = __fadd2_rn(make_float2(A.z, A.w), nl[b]);
         const float2 d = __fadd2_rn(dh, dl);
         const float d2 = fmaf(d.x, d.x, d.y * d.y);
-        const bool accept = !(d2 <= B.y);                                   // leaf || size/(d+eps) < theta
         // G M / (d2 (d + eps)), project.cu:765-769; d2 == 0 -> inf, times dx == 0 -> NaN like the reference
         const float w = d2 * (approx_sqrt(d2) + feps);
-        float f = B.x * approx_rcp(w);
-        const bool use = active && accept && (selfn[b] != idx);
-        f = use ? f : 0.f;
-        acc2[b] = __ffma2_rn(make_float2(f, f), d, acc2[b]);
+        const float gmr = B.x * approx_rcp(w);
+        float f;
+        uint32_t m;
         if constexpr (COUNT) {
+            const bool accept = !(d2 <= B.y);                               // leaf || size/(d+eps) < theta
+            const bool use = accept && (selfn[b] != idx);
+            f = use ? gmr : 0.f;
             const uint32_t fl = a.flags[idx];
             c_vis += active;
-            c_int += (use && (fl & kNodeNonZero));
-            c_open += (active && !accept);
+            c_int += (active && use && (fl & kNodeNonZero));
+            c_open += !accept;
+            m = __ballot_sync(0xffffffffu, !accept);
+        } else {
+            // accept = !(d2 <= thr); use = accept && not the body's own leaf; f = use ? gmr : 0; ballot(!accept)
+            asm volatile("{\n .reg .pred pa, pu;\n setp.gtu.f32 pa, %2, %3;\n setp.ne.and.u32 pu, %4, %5, pa;\n"
+                         " selp.f32 %0, %6, 0f00000000, pu;\n vote.sync.ballot.b32 %1, !pa, 0xffffffff;\n}"
+                         : "=f"(f), "=r"(m) : "f"(d2), "f"(B.y), "r"(selfn[b]), "r"(idx), "f"(gmr));
         }
-        return active && !accept;
+        acc2[b] = __ffma2_rn(make_float2(f, f), d, acc2[b]);
+        return m;
     };
 
     int top = 0;
@@ -168,25 +201,31 @@ traverse_f32_kernel(const __grid_constant__ TravArgs a) {
         uint32_t any = 0;
 #pragma unroll
         for (int b = 0; b < BPL; ++b) {
-            bool open = eval(A, B, 0u, b, live[b]);
-            m[b] = __ballot_sync(0xffffffffu, open);
+            const bool live = body[b] != 0xffffffffu;
+            const float2 mh = live ? nh[b] : make_float2(kFarLane, kFarLane);
+            m[b] = eval(A, B, 0u, b, mh, live);
             any |= m[b];
         }
         if (any) {
-            if (lane == 0) sts_entry(sbase, 0u, m[0], m[BPL - 1]);
+            if (lane == 0) SE::store(sbase, 0u, m);
             top = 1;
         }
         __syncwarp();
     }
     while (top > 0) {
         --top;
-        const uint4 e = lds_entry(sbase + (uint32_t)top * 16u);
+        uint32_t node, pm[BPL];
+        SE::load(sbase + (uint32_t)top * SE::kBytes, node, pm);
         __syncwarp();
-        const uint32_t base = 4u * e.x + 1u;
+        const uint32_t base = 4u * node + 1u;
         const NodeRec* __restrict__ rp = a.rec + base;
+        float2 mh[BPL];
         bool active[BPL];
-        active[0] = (e.y >> lane) & 1u;
-        if constexpr (BPL > 1) active[BPL - 1] = (e.z >> lane) & 1u;
+#pragma unroll
+        for (int b = 0; b < BPL; ++b) {
+            active[b] = (pm[b] >> lane) & 1u;
+            mh[b] = active[b] ? nh[b] : make_float2(kFarLane, kFarLane);
+        }
         if constexpr (COUNT) c_steps += (lane == 0);
 #pragma unroll
         for (uint32_t q = 0; q < 4; ++q) {
@@ -196,22 +235,24 @@ traverse_f32_kernel(const __grid_constant__ TravArgs a) {
             uint32_t any = 0;
 #pragma unroll
             for (int b = 0; b < BPL; ++b) {
-                bool open = eval(A, B, base + q, b, active[b]);
-                m[b] = __ballot_sync(0xffffffffu, open);
+                m[b] = eval(A, B, base + q, b, mh[b], active[b]);
                 any |= m[b];
             }
-            if (any) {
-                if (lane == 0) sts_entry(sbase + (uint32_t)top * 16u, base + q, m[0], m[BPL - 1]);
-                ++top;
-            }
+            // branch-free push: one straight-line block per step keeps four independent chains in flight
+            SE::store_if((any != 0u) & (lane == 0), sbase + (uint32_t)top * SE::kBytes, base + q, m);
+            top += (any != 0u);
         }
         __syncwarp();
     }
 
 #pragma unroll
-    for (int b = 0; b < BPL; ++b)
-        if (live[b])
-            finish_body<INTEGRATE>(a, body[b], px[b], py[b], mi[b], mi[b] * (double)acc2[b].x, mi[b] * (double)acc2[b].y);
+    for (int b = 0; b < BPL; ++b) {
+        if (body[b] != 0xffffffffu) {
+            const double2 p = a.pos[body[b]];
+            const double mi = a.mass[body[b]];
+            finish_body<INTEGRATE>(a, body[b], p.x, p.y, mi, mi * (double)acc2[b].x, mi * (double)acc2[b].y);
+        }
+    }
     if constexpr (COUNT) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -377,7 +418,9 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, double2* pos, 
     a.G = p.G; a.dt = p.dt; a.theta = p.theta; a.dist_eps = p.dist_eps;
     if (own_n <= 0) return;
     const bool fp64 = p.flags & BH_FLAG_FP64_TRAVERSAL, count = p.flags & BH_FLAG_COUNTERS;
-    const int bpl = (p.reserved[0] == 1 || p.reserved[0] == 2) ? p.reserved[0] : kDefaultBodiesPerLane;
+    // two bodies per lane halve the node traffic and the control overhead per body, but need >= ~400k
+    // bodies to keep every SM's warp slots full (ncu: profiles/r01_traverse_v4_*)
+    const int bpl = (p.reserved[0] == 1 || p.reserved[0] == 2) ? p.reserved[0] : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
     if (fp64) {
         unsigned blocks = (unsigned)((own_n + kTravThreads - 1) / kTravThreads);
         if (integrate) { if (count) traverse_f64_kernel<true, true><<<blocks, kTravThreads, 0, st>>>(a);
