@@ -125,18 +125,17 @@ keys_kernel(const double2* __restrict__ pos, int64_t n, int finest, const StepCo
         double2 p = pos[i];
         double xl = bx0, xh = bx1, yl = by0, yh = by1;
         uint32_t key = 0;
+        // project.cu:352-355 tests (x<mx && y<my) -> 0, (x>=mx && y<my) -> 1, (x<mx && y>=my) -> 2, else 3.
+        // For ordered values that is (x >= mx) | (y >= my) << 1; a NaN coordinate fails all three
+        // tests and goes to child 3 at every level.
+        const bool unordered = (p.x != p.x) || (p.y != p.y);
         for (int l = 0; l < finest; ++l) {
-            double mx = __dmul_rn(__dadd_rn(xl, xh), 0.5);   // (min + max) / 2, exact halving
-            double my = __dmul_rn(__dadd_rn(yl, yh), 0.5);
-            // project.cu:352-355 — the four explicit tests (NaN coordinates fall through to 3)
-            uint32_t q;
-            if (p.x < mx && p.y < my) q = 0;
-            else if (p.x >= mx && p.y < my) q = 1;
-            else if (p.x < mx && p.y >= my) q = 2;
-            else q = 3;
-            if (q & 1u) xl = mx; else xh = mx;               // child bounds project.cu:421-429
-            if (q & 2u) yl = my; else yh = my;
-            key = (key << 2) | q;
+            const double mx = __dmul_rn(__dadd_rn(xl, xh), 0.5);   // (min + max) / 2, exact halving
+            const double my = __dmul_rn(__dadd_rn(yl, yh), 0.5);
+            const bool bx = unordered || (p.x >= mx), by = unordered || (p.y >= my);
+            xl = bx ? mx : xl; xh = bx ? xh : mx;               // child bounds project.cu:421-429
+            yl = by ? my : yl; yh = by ? yh : my;
+            key = (key << 2) | (uint32_t)bx | ((uint32_t)by << 1);
         }
         keys[i] = key;
         idx[i] = (uint32_t)i;

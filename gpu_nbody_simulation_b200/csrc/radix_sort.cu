@@ -51,19 +51,25 @@ onesweep_pass(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__
         int64_t g = base + (int64_t)k * 32;
         key[k] = (g < n) ? keys_in[g] : 0xffffffffu;
     }
-    // warp-level stable ranking, item by item
+    // warp-level stable ranking.  First all peer masks (independent MATCH instructions, pipelined),
+    // then the running per-warp digit counts, item by item (the only sequential part).
+    uint32_t peers[kSortItems];
 #pragma unroll
     for (int k = 0; k < kSortItems; ++k) {
-        int64_t g = base + (int64_t)k * 32;
-        bool valid = g < n;
-        uint32_t d = (key[k] >> shift) & dmask;
-        uint32_t dext = valid ? d : (0x10000u | (uint32_t)lane);  // invalid lanes match nobody
-        uint32_t peers = __match_any_sync(0xffffffffu, dext);
-        uint32_t lt = peers & ((1u << lane) - 1u);
-        uint32_t running = valid ? s_warp[warp][d] : 0u;
+        const bool valid = base + (int64_t)k * 32 < n;
+        const uint32_t d = (key[k] >> shift) & dmask;
+        peers[k] = __match_any_sync(0xffffffffu, valid ? d : (0x10000u | (uint32_t)lane));  // invalid lanes match nobody
+    }
+    const uint32_t lanemask_lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const bool valid = base + (int64_t)k * 32 < n;
+        const uint32_t d = (key[k] >> shift) & dmask;
+        const uint32_t lt = peers[k] & lanemask_lt;
+        const uint32_t running = valid ? s_warp[warp][d] : 0u;
         rank[k] = running + __popc(lt);
         __syncwarp();
-        if (valid && lt == 0) s_warp[warp][d] = running + __popc(peers);
+        if (valid && lt == 0) s_warp[warp][d] = running + __popc(peers[k]);
         __syncwarp();
     }
     __syncthreads();
@@ -85,24 +91,47 @@ onesweep_pass(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__
         if (tile == 0) *st = kFlagIncl | run;
         else *st = kFlagAgg | run;
     }
+    // Decoupled look-back, kWindow predecessor states in flight per digit (the loads are
+    // independent, so the serial chain is one L2 round trip per kWindow tiles, not per tile).
+    {
+        constexpr int kWindow = 8;
+        int64_t t[PER_T];
+        bool done[PER_T];
 #pragma unroll
-    for (int j = 0; j < PER_T; ++j) {
-        int d = tid + j * kSortThreads;
-        uint32_t excl = 0;
-        if (tile > 0) {
-            int64_t t = (int64_t)tile - 1;
-            while (true) {
-                volatile uint32_t* st = tile_state + (size_t)t * NBINS + d;
-                uint32_t v = *st;
-                if (v == 0) continue;  // not published yet; the tile is resident (ticket order)
-                excl += v & kValMask;
-                if ((v >> 30) == 2u) break;
-                --t;
+        for (int j = 0; j < PER_T; ++j) { excl_prev[j] = 0; t[j] = (int64_t)tile - 1; done[j] = (tile == 0); }
+        bool all_done = (tile == 0);
+        while (!all_done) {
+            all_done = true;
+#pragma unroll
+            for (int j = 0; j < PER_T; ++j) {
+                if (done[j]) continue;
+                const int d = tid + j * kSortThreads;
+                uint32_t v[kWindow];
+#pragma unroll
+                for (int w = 0; w < kWindow; ++w) {
+                    const int64_t tt = t[j] - w;
+                    volatile uint32_t* st = tile_state + (size_t)(tt < 0 ? 0 : tt) * NBINS + d;
+                    v[w] = *st;
+                    if (tt < 0) v[w] = 2u << 30;   // tile 0 always publishes an inclusive prefix
+                }
+#pragma unroll
+                for (int w = 0; w < kWindow; ++w) {
+                    if (done[j]) break;
+                    if (v[w] == 0) break;                // not published yet: retry from here
+                    excl_prev[j] += v[w] & kValMask;
+                    --t[j];
+                    if ((v[w] >> 30) == 2u) done[j] = true;
+                }
+                all_done = all_done && done[j];
             }
-            volatile uint32_t* mine = tile_state + (size_t)tile * NBINS + d;
-            *mine = kFlagIncl | (excl + tile_count[j]);
         }
-        excl_prev[j] = excl;
+        if (tile > 0) {
+#pragma unroll
+            for (int j = 0; j < PER_T; ++j) {
+                volatile uint32_t* mine = tile_state + (size_t)tile * NBINS + (tid + j * kSortThreads);
+                *mine = kFlagIncl | (excl_prev[j] + tile_count[j]);
+            }
+        }
     }
     // exclusive scan of the global digit histogram (block-wide, NBINS values)
     {

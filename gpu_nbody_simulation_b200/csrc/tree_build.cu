@@ -105,14 +105,25 @@ __global__ void __launch_bounds__(256)
 cell_runs_kernel(const uint32_t* __restrict__ skeys, int64_t n, uint32_t* __restrict__ cnt_f,
                  uint32_t* __restrict__ first_f, uint32_t exact_leaf_max, uint32_t* __restrict__ heavy_list,
                  uint32_t* __restrict__ heavy_count) {
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    uint32_t k = skeys[j];
-    if (j + 1 < n && skeys[j + 1] == k) return;
-    int64_t lo = 0, hi = j;   // first position with key >= k
-    while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        if (skeys[mid] < k) lo = mid + 1; else hi = mid;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool in = j < n;
+    const uint32_t k = in ? skeys[j] : 0u;
+    const bool head = in && (j == 0 || skeys[j - 1] != k);
+    const bool tail = in && (j + 1 >= n || skeys[j + 1] != k);
+    // run start: the nearest head at or below this lane inside the warp, else binary search
+    const uint32_t heads = __ballot_sync(0xffffffffu, head) & (0xffffffffu >> (31 - lane));
+    if (!tail) return;
+    int64_t lo;
+    if (heads) {
+        lo = j - lane + (31 - __clz(heads));
+    } else {
+        lo = 0;
+        int64_t hi = j - lane;   // the run began before this warp's first key
+        while (lo < hi) {        // first position with key >= k
+            int64_t mid = (lo + hi) >> 1;
+            if (skeys[mid] < k) lo = mid + 1; else hi = mid;
+        }
     }
     uint32_t c = (uint32_t)(j + 1 - lo);
     cnt_f[k] = c;
@@ -161,10 +172,11 @@ heavy_cells_kernel(const uint32_t* __restrict__ heavy_list, const uint32_t* __re
 }
 
 // ---- bottom kernel: finest cells + up to five levels above -----------------------------------------
-// Block b owns finest cells [1024 b, 1024 b + 1024) = one subtree rooted five levels up.  Thread t
-// computes four sibling finest cells and their parent in registers; the next two levels are
-// combined inside a warp with shuffles, the remaining ones through shared memory.
-constexpr int kBottomThreads = 256;
+// Block b owns finest cells [256 b, 256 b + 256) = one subtree rooted four levels up; thread t
+// owns ONE finest cell (maximum parallelism for the latency-bound leaf pass).  Levels F-1 and F-2
+// are combined inside a warp with shuffles (4, then 16 lanes per parent), F-3 and F-4 through shared
+// memory.  Children are always combined in the order 0..3 (ComputeMass, project.cu:483-490).
+constexpr int kBottomThreads = 256;    // 256 finest cells per block: levels F .. F-4
 
 __device__ __forceinline__ Cell shfl_cell(const Cell& c, int src_lane) {
     Cell r;
@@ -185,58 +197,45 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
     const double G = G0 * scale * scale;
     const int tid = threadIdx.x, lane = tid & 31;
     const uint64_t offF = d.level_off[F];
-    __shared__ Cell s_cells[kBottomThreads / 16];   // level F-3 results (16 per block)
-    __shared__ Cell s_cells4[4];                    // level F-4 results (4 per block)
+    __shared__ Cell s_a[kBottomThreads / 16];     // level F-2 results (16 per block)
+    __shared__ Cell s_b[kBottomThreads / 64];     // level F-3 results (4 per block)
+    __shared__ Cell s_c[1];
     __shared__ uint32_t s_internal[kBottomThreads / 32];
     uint32_t n_internal = 0;
 
-    // ---- level F: four sibling cells per thread
-    Cell leaf[4];
-    const uint64_t parent_code = (uint64_t)blockIdx.x * kBottomThreads + tid;   // code at level F-1
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        uint64_t code = (F == 0) ? parent_code : parent_code * 4 + q;
-        Cell c; c.m = 0.0; c.cx = 0.0; c.cy = 0.0; c.cnt = 0; c.first = 0;
-        bool exists = code < d.ncells_finest && (F > 0 || q == 0);
-        if (exists) {
-            c.cnt = t.count[offF + code];
-            if (c.cnt) {
-                c.first = t.first[offF + code];
-                if (c.cnt <= exact_leaf_max) {
-                    // project.cu:367-373: running weighted average in ascending body index
-                    double em = 0.0, ex = 0.0, ey = 0.0;
-                    for (uint32_t i = 0; i < c.cnt; ++i) {
-                        uint32_t b = sidx[c.first + i];
-                        double mb = mass[b];
-                        double2 x = pos[b];
-                        double tot = __dadd_rn(em, mb);
-                        ex = __ddiv_rn(__dadd_rn(__dmul_rn(em, ex), __dmul_rn(mb, x.x)), tot);
-                        ey = __ddiv_rn(__dadd_rn(__dmul_rn(em, ey), __dmul_rn(mb, x.y)), tot);
-                        em = tot;                  // node[TOTAL_MASS] += mass
-                    }
-                    c.m = em; c.cx = ex; c.cy = ey;
-                } else {                           // summed by heavy_cells_kernel
-                    c.m = t.mass[offF + code]; c.cx = t.comx[offF + code]; c.cy = t.comy[offF + code];
+    // ---- level F: one cell per thread
+    uint64_t code = (uint64_t)blockIdx.x * kBottomThreads + tid;
+    uint64_t ncells = d.ncells_finest;
+    Cell cur; cur.m = 0.0; cur.cx = 0.0; cur.cy = 0.0; cur.cnt = 0; cur.first = 0;
+    if (code < ncells) {
+        cur.cnt = t.count[offF + code];
+        if (cur.cnt) {
+            cur.first = t.first[offF + code];
+            if (cur.cnt <= exact_leaf_max) {
+                // project.cu:367-373: running weighted average in ascending body index
+                double em = 0.0, ex = 0.0, ey = 0.0;
+                for (uint32_t i = 0; i < cur.cnt; ++i) {
+                    const uint32_t b = __ldg(sidx + cur.first + i);
+                    const double mb = __ldg(mass + b);
+                    const double2 x = __ldg(pos + b);
+                    const double tot = __dadd_rn(em, mb);
+                    ex = __ddiv_rn(__dadd_rn(__dmul_rn(em, ex), __dmul_rn(mb, x.x)), tot);
+                    ey = __ddiv_rn(__dadd_rn(__dmul_rn(em, ey), __dmul_rn(mb, x.y)), tot);
+                    em = tot;                      // node[TOTAL_MASS] += mass
                 }
+                cur.m = em; cur.cx = ex; cur.cy = ey;
+            } else {                               // summed by heavy_cells_kernel
+                cur.m = t.mass[offF + code]; cur.cx = t.comx[offF + code]; cur.cy = t.comy[offF + code];
             }
-            store_cell(t, offF + code, c, F, F, G, mass_eps, scale, consts->thr2[F], sidx);
         }
-        leaf[q] = c;
+        store_cell(t, offF + code, cur, F, F, G, mass_eps, scale, consts->thr2[F], sidx);
     }
     if (F == 0) {
         if (blockIdx.x == 0 && tid == 0) atomicAdd(&counters[4], 1ull);   // the root alone
         return;
     }
-    // ---- level F-1 (registers)
-    Cell cur = combine4(leaf, sidx, pos, mass, t.self_node, offF + 4 * parent_code, parent_code < (d.ncells_finest >> 2));
-    int level = F - 1;
-    uint64_t code = parent_code;
-    uint64_t ncells = d.ncells_finest >> 2;
-    if (code < ncells) {
-        store_cell(t, d.level_off[level] + code, cur, level, F, G, mass_eps, scale, consts->thr2[level], sidx);
-        n_internal += (cur.cnt >= 2u);
-    }
-    // ---- levels F-2, F-3: shuffles inside the warp (groups of 4, then 16 lanes)
+    int level = F;
+    // ---- levels F-1, F-2: shuffles inside the warp (groups of 4, then 16 lanes)
 #pragma unroll
     for (int stride = 1; stride <= 4; stride <<= 2) {
         if (level == 0) break;
@@ -245,42 +244,42 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
         for (int q = 0; q < 4; ++q) ch[q] = shfl_cell(cur, (lane & ~(4 * stride - 1)) + q * stride);
         const uint64_t child_base = d.level_off[level] + 4 * (code >> 2);
         --level; code >>= 2; ncells >>= 2;
-        bool owner = (lane & (4 * stride - 1)) == 0;
-        Cell up = combine4(ch, sidx, pos, mass, t.self_node, child_base, owner && code < ncells);
-        if (owner && code < ncells) {
+        const bool owner = (lane & (4 * stride - 1)) == 0 && code < ncells;
+        Cell up = combine4(ch, sidx, pos, mass, t.self_node, child_base, owner);
+        if (owner) {
             store_cell(t, d.level_off[level] + code, up, level, F, G, mass_eps, scale, consts->thr2[level], sidx);
             n_internal += (up.cnt >= 2u);
         }
         cur = up;
     }
-    // ---- levels F-4, F-5: shared memory (16 cells of level F-3 per block)
+    // ---- levels F-3, F-4: shared memory
     if (level > 0) {   // block-uniform
-        if ((lane & 15) == 0) s_cells[tid >> 4] = cur;
+        if ((lane & 15) == 0) s_a[tid >> 4] = cur;               // 16 cells of level F-2
         __syncthreads();
-        const int l4 = level - 1;
-        if (tid < 4) {
-            Cell ch[4];
+        const Cell* src = s_a;
+        Cell* dst = s_b;
+        int nthreads = kBottomThreads / 64;                      // 4 parents at level F-3, then 1 at F-4
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ch[q] = s_cells[tid * 4 + q];
-            uint64_t c4 = (uint64_t)blockIdx.x * 4 + tid;
-            Cell up = combine4(ch, sidx, pos, mass, t.self_node, d.level_off[level] + 4 * c4, c4 < (ncells >> 2));
-            if (c4 < (ncells >> 2)) {
-                store_cell(t, d.level_off[l4] + c4, up, l4, F, G, mass_eps, scale, consts->thr2[l4], sidx);
-                n_internal += (up.cnt >= 2u);
+        for (int stage = 0; stage < 2; ++stage) {
+            if (level == 0) break;                               // block-uniform
+            const uint64_t pcode = ((uint64_t)blockIdx.x * nthreads) + tid;   // parent code at level-1
+            const uint64_t npar = 1ull << (2 * (level - 1));
+            if (tid < nthreads) {
+                Cell ch[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ch[q] = src[tid * 4 + q];
+                const bool ok = pcode < npar;
+                Cell up = combine4(ch, sidx, pos, mass, t.self_node, d.level_off[level] + 4 * pcode, ok);
+                if (ok) {
+                    store_cell(t, d.level_off[level - 1] + pcode, up, level - 1, F, G, mass_eps, scale,
+                               consts->thr2[level - 1], sidx);
+                    n_internal += (up.cnt >= 2u);
+                }
+                dst[tid] = up;
             }
-            s_cells4[tid] = up;
-        }
-        __syncthreads();
-        // level F-5: one cell per block
-        if (l4 > 0 && tid == 0) {
-            int l5 = l4 - 1;
-            uint64_t c5code = blockIdx.x;
-            Cell top = combine4(s_cells4, sidx, pos, mass, t.self_node, d.level_off[l4] + 4 * c5code,
-                                c5code < (ncells >> 4));
-            if (c5code < (ncells >> 4)) {
-                store_cell(t, d.level_off[l5] + c5code, top, l5, F, G, mass_eps, scale, consts->thr2[l5], sidx);
-                n_internal += (top.cnt >= 2u);
-            }
+            __syncthreads();
+            --level;
+            src = dst; dst = s_c; nthreads >>= 2;
         }
     }
     // ---- count internal cells (reference node count = 1 + 4 * internal)
@@ -349,15 +348,14 @@ void launch_tree(const uint32_t* skeys, const uint32_t* sidx, const double2* pos
                                                 t.mass + d.level_off[F], t.comx + d.level_off[F],
                                                 t.comy + d.level_off[F]);
     ++g_launches;
-    uint64_t parents = F == 0 ? 1 : (d.ncells_finest >> 2);
-    unsigned blocks = (unsigned)((parents + kBottomThreads - 1) / kBottomThreads);
+    unsigned blocks = (unsigned)((d.ncells_finest + kBottomThreads - 1) / kBottomThreads);
     tree_bottom_kernel<<<blocks, kBottomThreads, 0, st>>>(t, d, sidx, pos, mass, p.G, p.mass_eps, exact_max,
                                                           s.counters, consts);
     ++g_launches;
-    int top_level = F - 6;   // bottom kernel covered F .. F-5
+    int top_level = F - 5;   // bottom kernel covered F .. F-4
     if (F >= 1) {
         if (top_level < 0) top_level = -1;
-        // when the bottom kernel already reached the root (F <= 5) only the node count remains
+        // when the bottom kernel already reached the root (F <= 4) only the node count remains
         tree_top_kernel<<<1, 1024, 0, st>>>(t, d, top_level, sidx, pos, mass, p.G, p.mass_eps, s.counters, consts);
         ++g_launches;
     }
