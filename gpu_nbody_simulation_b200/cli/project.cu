@@ -1,0 +1,138 @@
+// project.cu — drop-in replacement for the reference program of the same name
+// (DavidSevic/gpu-nbody-simulation, implementation/project.cu), built on the B200-native engine.
+//
+// Same build-time parameters (-DN_BODIES, -DN_THREADS, -DN_SIMULATIONS; project.cu:1-11), same
+// cwd-relative inputs (masses_init.txt, positions_init.txt, velocities_init.txt; project.cu:1065),
+// same outputs (quadtree_init_gpu.txt, quadtree_final_gpu.txt; project.cu:928-929, :962-965) and the
+// same two stdout lines the reference's plot scripts parse (project.cu:1097, :1102;
+// plot_first_scale.py:58-59, plot_second_scale.py:20):
+//
+//     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -DN_BODIES=$n_b -DN_THREADS=$n_t \
+//          -DN_SIMULATIONS=$n_s -o project project.cu
+//
+// (the reference's line plus the sm_100a target).  This translation unit is a unity build of the
+// library sources, so no extra link flags are needed; everything goes through the C-ABI of
+// include/bh.h.  The reference's source-level constants are -D macros here with its values as
+// defaults.  N_THREADS is accepted and ignored (it is the course experiment's grid-stride knob,
+// SURVEY §2.1).  Differences from the reference, all opt-in or documented in DESIGN.md:
+//   * initial conditions come from the three text files (the reference's README toggle); if they
+//     are absent, a SEEDED uniform square (project.cu:30-35 ranges) replaces the time-seeded cuRAND;
+//   * -DBH_POSITIONS_TXT=1 also writes the trajectory file positions.txt that plot_2d.py reads
+//     (format of savePositions, project.cu:855-863), which the reference's GPU path never writes;
+//   * cap-level single leaves print the occupant's real position (reference: out-of-bounds read).
+#ifndef N_BODIES
+#define N_BODIES (1000 * 40)
+#endif
+#ifndef N_THREADS
+#define N_THREADS (1024 * 1)
+#endif
+#ifndef N_SIMULATIONS
+#define N_SIMULATIONS 10
+#endif
+#ifndef G_CONST
+#define G_CONST 6.67e-11          // project.cu:27
+#endif
+#ifndef DELTA_T
+#define DELTA_T 1.0               // project.cu:29
+#endif
+#ifndef THETA
+#define THETA 5e-1                // project.cu:60
+#endif
+#ifndef QUADTREE_MAX_DEPTH
+#define QUADTREE_MAX_DEPTH 10     // project.cu:61
+#endif
+#ifndef BH_POSITIONS_TXT
+#define BH_POSITIONS_TXT 0
+#endif
+#ifndef BH_FP64
+#define BH_FP64 0
+#endif
+
+#include "../csrc/api.cu"
+#include "../csrc/bounds_keys.cu"
+#include "../csrc/radix_sort.cu"
+#include "../csrc/tree_build.cu"
+#include "../csrc/traverse.cu"
+#include "../csrc/direct.cu"
+#include "../csrc/host_io.cpp"
+
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+static void die(const char* what) {
+    fprintf(stderr, "%s: %s\n", what, bh_last_error());
+    exit(1);
+}
+
+// splitmix64: seeded stand-in for the reference's time-seeded generators (project.cu:84-101)
+static double uniform01(uint64_t& s) {
+    s += 0x9e3779b97f4a7c15ull;
+    uint64_t z = s;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+int main() {
+    const int64_t n = (int64_t)(N_BODIES);
+    const int n_steps = (int)(N_SIMULATIONS);
+    (void)(N_THREADS);
+    std::vector<double> mass(n), pos(2 * n), vel(2 * n);
+    if (bh_load_text("masses_init.txt", "positions_init.txt", "velocities_init.txt", n, mass.data(), pos.data(),
+                     vel.data()) == BH_OK) {
+        printf("Loaded %lld bodies from text files.\n", (long long)n);           // project.cu:160
+    } else {
+        fprintf(stderr, "note: %s; using a seeded uniform square instead\n", bh_last_error());
+        uint64_t s = 12345;
+        for (int64_t i = 0; i < n; ++i) mass[i] = pow(10.0, -1.0 + uniform01(s) * (log10(0.5) + 1.0));   // project.cu:30-31
+        for (int64_t i = 0; i < 2 * n; ++i) pos[i] = -0.1 + uniform01(s) * 0.2;                            // :32-33
+        for (int64_t i = 0; i < 2 * n; ++i) vel[i] = -1e-4 + uniform01(s) * 2e-4;                          // :34-35
+    }
+
+    auto t0 = std::chrono::high_resolution_clock::now();                         // project.cu:1083
+    bh_params p;
+    bh_default_params(&p);
+    p.n_bodies = n; p.G = G_CONST; p.dt = DELTA_T; p.theta = THETA; p.max_depth = QUADTREE_MAX_DEPTH;
+    if (BH_FP64) p.flags |= BH_FLAG_FP64_TRAVERSAL;
+    bh_ctx* ctx = nullptr;
+    if (bh_create(&p, &ctx) != BH_OK) die("bh_create");
+    { FILE* f = fopen("quadtree_init_gpu.txt", "w"); if (f) fclose(f); }          // project.cu:928-929 opens both
+    { FILE* f = fopen("quadtree_final_gpu.txt", "w"); if (f) fclose(f); }
+    if (bh_set_bodies(ctx, pos.data(), vel.data(), mass.data()) != BH_OK) die("bh_set_bodies");
+    if (bh_set_profiling(ctx, 1) != BH_OK) die("bh_set_profiling");
+    double t = 0.0;
+    if (BH_POSITIONS_TXT) bh_append_positions_txt("positions.txt", pos.data(), n, t, 1);
+    for (int step = 0; step < n_steps; ++step) {
+        t += DELTA_T;                                                            // project.cu:956
+        const bool first = step == 0, last = step == n_steps - 1 && step != 0;   // project.cu:962-965
+        if (first || last) {
+            if (bh_build_tree(ctx) != BH_OK) die("bh_build_tree");
+            if (bh_dump_quadtree(ctx, first ? "quadtree_init_gpu.txt" : "quadtree_final_gpu.txt") != BH_OK)
+                die("bh_dump_quadtree");
+        }
+        if (bh_step(ctx, 1) != BH_OK) die("bh_step");
+        if (BH_POSITIONS_TXT) {
+            if (bh_get_positions(ctx, pos.data()) != BH_OK) die("bh_get_positions");
+            bh_append_positions_txt("positions.txt", pos.data(), n, t, 0);
+        }
+    }
+    if (bh_get_positions(ctx, pos.data()) != BH_OK) die("bh_get_positions");     // project.cu:1010
+    bh_timers tm;
+    bh_get_timers(ctx, &tm);
+    bh_destroy(ctx);
+    auto t1 = std::chrono::high_resolution_clock::now();                         // project.cu:1087
+    long long total_ms = std::chrono::duration_cast<std::chrono::milliseconds>(t1 - t0).count();
+
+    printf("\n\n\n\n");
+    printf("GPU total computation took %lld milliseconds.\n", total_ms);          // project.cu:1097
+    printf("\n\n");
+    // "parallel" = force + update kernels summed over the steps (project.cu:985-1007): here the
+    // traversal kernel with the fused integrator, device time from CUDA events.
+    printf("GPU parallel computation took %lld microseconds.\n", (long long)llround(tm.traverse_us));   // project.cu:1102
+    return 0;
+}

@@ -295,3 +295,39 @@ def test_direct_sum_kernel_small():
         want = oracle.direct_forces(pos, mass, nthreads=oracle.max_threads())
         per_body = np.linalg.norm(f - want, axis=1) / np.linalg.norm(want, axis=1)
         assert np.median(per_body) <= 1e-4 and rel_rms(f, want) <= 1e-3     # plain FP32 coordinates
+
+
+# ------------------------------------------------------------------------------------------------
+# drop-in CLI: same -D macros, same cwd files, same stdout lines as the reference's project.cu
+# ------------------------------------------------------------------------------------------------
+def test_cli_project_drop_in(tmp_path):
+    import os
+    import re
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "gpu_nbody_simulation_b200", "cli", "project.cu")
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
+    n, steps = 3000, 3
+    pos, vel, mass, _ = golden_inputs("shipped_40000")
+    ic.write_init_files(str(tmp_path), pos[:n + 50], vel[:n + 50], mass[:n + 50])   # more lines than N: first N used
+    exe = str(tmp_path / "project")
+    # the reference's documented build line (first_scaling_script.sh:30) plus the sm_100a target
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-diag-suppress", "550",
+                           f"-DN_BODIES={n}", "-DN_THREADS=1024", f"-DN_SIMULATIONS={steps}", "-DBH_POSITIONS_TXT=1",
+                           "-o", exe, src], cwd=str(tmp_path))
+    out = subprocess.run([exe], cwd=str(tmp_path), capture_output=True, text=True, check=True).stdout
+    assert f"Loaded {n} bodies from text files." in out
+    # the regexes of plot_first_scale.py:58-59 / plot_second_scale.py:20
+    assert re.search(r"GPU parallel computation took (\d+) microseconds", out)
+    assert re.search(r"GPU total computation took (\d+) milliseconds\.", out)
+    p, v, m = pos[:n], vel[:n], mass[:n]
+    tree = oracle.Tree(p, m)
+    tree.dump(str(tmp_path / "ref_init.txt"))
+    assert open(tmp_path / "quadtree_init_gpu.txt").read() == open(tmp_path / "ref_init.txt").read()
+    final = open(tmp_path / "quadtree_final_gpu.txt").read().splitlines()
+    assert len(final) > 0 and final[0].split()[0] == "0"
+    traj = np.loadtxt(tmp_path / "positions.txt")
+    assert traj.shape == ((steps + 1) * n, 4)                 # plot_2d.py: time body x y
+    assert np.allclose(traj[:n, 2:], np.round(p, 6), atol=1e-6)
