@@ -37,6 +37,7 @@ if ROOT not in sys.path:
 BODIES_PER_GPU = 1_000_000
 SEED = 12345
 FLOP_PER_INTERACTION = 20.0
+TRAVERSE_DRAM_BYTES_NCU = 74_530_304 + 36_734_976   # profiles/r01_traverse_v4_bpl2_ncu_summary.txt
 METRIC = "body_steps_per_s"
 UNIT = "body·steps/s"
 
@@ -242,7 +243,11 @@ def run_ours(args):
         trav_s = phases["traverse_us"] * 1e-6
         achieved = inter_per_step * FLOP_PER_INTERACTION / trav_s / 1e12
         roofline = {"bound": "fp32", "kernel": "traverse_kernel<fp32,integrate>", "achieved": achieved,
-                    "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                    "traffic": TRAVERSE_DRAM_BYTES_NCU,
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full "
+                                      "capture at N=1M (profiles/r01_traverse_v4_bpl2_ncu_summary.txt); algorithmic "
+                                      "bytes = 72 B/body state + 11 MB tree = 83 MB",
                     "peak_source": f"measured here: FFMA loop, {peak_tf:.1f} TFLOP/s (implies {mhz:.0f} MHz at 128 FMA/clk/SM); "
                                    "FP32 peak is not in MEASURED_PEAKS.json (SURVEY 8d)",
                     "interactions_per_step": inter_per_step, "flop_per_interaction": FLOP_PER_INTERACTION,
@@ -266,13 +271,12 @@ def run_ours(args):
     hm = torch.from_numpy(mass).pin_memory()
     hout = torch.empty((n, 2), dtype=torch.float64).pin_memory()
     for _ in range(max(1, min(W, 3))):
-        sim.set_bodies(hp, hv, hm); sim.step(1); sim.positions(hout)
+        sim.step_host(hp, hv, hm, hout)
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        sim.set_bodies(hp, hv, hm)      # H2D of this step's inputs (pinned)
-        sim.step(1)
-        sim.positions(hout)             # D2H of this step's result (synchronizes)
+        # bh_step_host: H2D of this step's inputs (pinned), one step, D2H of its result; synchronous
+        sim.step_host(hp, hv, hm, hout)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": n * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(40 * n), "d2h_bytes_per_step": int(16 * n),

@@ -34,7 +34,7 @@ BH_FLAG_NO_GRAPH = 1 << 2
 ABI_SYMBOLS = (
     "bh_last_error", "bh_abi_version", "bh_default_params", "bh_create", "bh_destroy", "bh_nccl_unique_id",
     "bh_attach_nccl", "bh_shard_range", "bh_set_bodies", "bh_set_positions", "bh_set_velocities", "bh_snapshot",
-    "bh_restore", "bh_step", "bh_step_from_snapshot", "bh_build_tree", "bh_compute_forces", "bh_integrate",
+    "bh_restore", "bh_step", "bh_step_host", "bh_step_from_snapshot", "bh_build_tree", "bh_compute_forces", "bh_integrate",
     "bh_synchronize", "bh_get_positions", "bh_get_velocities", "bh_get_accelerations", "bh_get_forces",
     "bh_get_bounds", "bh_get_body_keys", "bh_get_sorted_order", "bh_get_tree_size", "bh_get_tree",
     "bh_dump_quadtree", "bh_get_counters", "bh_set_profiling", "bh_get_timers", "bh_reset_timers",
@@ -109,6 +109,7 @@ def lib():
         getattr(L, name).argtypes = [vp]
     L.bh_step.argtypes = [vp, C.c_int32]
     L.bh_step_from_snapshot.argtypes = [vp, C.c_int32]
+    L.bh_step_host.argtypes = [vp, vp, vp, vp, vp]
     for name in ("bh_get_positions", "bh_get_velocities", "bh_get_accelerations", "bh_get_forces"):
         getattr(L, name).argtypes = [vp, vp]
     L.bh_get_bounds.argtypes = [vp, dp]
@@ -251,6 +252,15 @@ class Simulation:
     # ---- hot path ----
     def step(self, nsteps: int = 1):
         _check(lib().bh_step(self._h, nsteps))
+
+    def step_host(self, pos, vel, mass, out_pos=None):
+        """One step with host buffers (upload, step, download of the new positions), pipelined."""
+        if not hasattr(pos, "data_ptr"):
+            pos, vel, mass = _f64(pos, (self.n, 2)), _f64(vel, (self.n, 2)), _f64(mass, (self.n,))
+        if out_pos is None:
+            out_pos = np.empty((self.n, 2), dtype=np.float64)
+        _check(lib().bh_step_host(self._h, _ptr(pos), _ptr(vel), _ptr(mass), _ptr(out_pos)))
+        return out_pos
 
     def step_from_snapshot(self, nsteps: int = 1):
         _check(lib().bh_step_from_snapshot(self._h, nsteps))

@@ -122,6 +122,8 @@ struct bh_ctx {
     uint64_t graph_kernels[2] = {0, 0};
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t copy_stream = nullptr;           // uploads of bh_step_host overlap the build on `stream`
+    cudaEvent_t ev_up[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t pev[8] = {};
     bool profiling = false;
     bh_timers timers{};
@@ -397,6 +399,8 @@ int bh_create(const bh_params* p, bh_ctx** out) {
 #undef BH_ALLOC
     bh_shard_range(n, p->n_ranks, p->rank, &c->own_lo, &c->own_hi);
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (auto& ev : c->ev_up) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto& ev : c->pev) cudaEventCreate(&ev);
     cudaMemsetAsync(c->acc, 0, sizeof(double2) * n, c->stream);
     cudaMemsetAsync(c->force, 0, sizeof(double2) * n, c->stream);
@@ -421,6 +425,8 @@ int bh_destroy(bh_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (auto& ev : c->pev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->ev_up) if (ev) cudaEventDestroy(ev);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return BH_OK;
@@ -528,6 +534,44 @@ int bh_step(bh_ctx* c, int32_t nsteps) {
 int bh_step_from_snapshot(bh_ctx* c, int32_t nsteps) {
     if (!c) { set_error("null context"); return BH_ERR_INVALID; }
     return run_steps(c, nsteps, true);
+}
+
+// One step with HOST buffers, pipelined: positions go up first and bounds / keys / sort start as soon
+// as they land; masses are only needed by the tree pass and velocities only by the integrator, so
+// their uploads overlap the build and the traversal.  out_pos_host receives the new positions.
+int bh_step_host(bh_ctx* c, const double* pos, const double* vel, const double* mass, double* out_pos) {
+    if (!c || !pos || !vel || !mass || !out_pos) { set_error("null argument"); return BH_ERR_INVALID; }
+    if (c->p.n_ranks > 1 || c->profiling) {       // multi-rank / profiling: plain sequence
+        BH_TRY(bh_set_bodies(c, pos, vel, mass));
+        BH_TRY(bh_step(c, 1));
+        return bh_get_positions(c, out_pos);
+    }
+    DeviceGuard g(c->device);
+    const int64_t n = c->d.n;
+    BH_CUDA_OK(cudaMemcpyAsync(c->pos, pos, sizeof(double2) * n, cudaMemcpyHostToDevice, c->copy_stream));
+    BH_CUDA_OK(cudaEventRecord(c->ev_up[0], c->copy_stream));
+    BH_CUDA_OK(cudaMemcpyAsync(c->mass, mass, sizeof(double) * n, cudaMemcpyHostToDevice, c->copy_stream));
+    BH_CUDA_OK(cudaEventRecord(c->ev_up[1], c->copy_stream));
+    BH_CUDA_OK(cudaMemcpyAsync(c->vel, vel, sizeof(double2) * n, cudaMemcpyHostToDevice, c->copy_stream));
+    BH_CUDA_OK(cudaEventRecord(c->ev_up[2], c->copy_stream));
+    BH_CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+    zero_scratch(c);
+    BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[0], 0));
+    launch_bounds(c->pos, n, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream);
+    launch_keys(c->pos, n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream);
+    launch_sort(c->keys, c->idx, n, c->sp, c->s, &c->sorted, c->stream);
+    BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[1], 0));
+    launch_tree(c->keys[c->sorted], c->idx[c->sorted], c->pos, c->mass, n, c->p, c->d, c->tree, c->s, c->consts, c->stream);
+    BH_TRY(check_launch());
+    BH_TRY(enqueue_forces(c, false));             // forces only: velocities may still be in flight
+    BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[2], 0));
+    launch_integrate(c->pos, c->vel, c->acc, c->force, c->mass, 0, n, c->p.dt, c->stream);
+    BH_TRY(check_launch());
+    BH_CUDA_OK(cudaMemcpyAsync(out_pos, c->pos, sizeof(double2) * n, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+    BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->bodies_set = true; c->tree_valid = false; c->timed = true;
+    return BH_OK;
 }
 
 int bh_build_tree(bh_ctx* c) {

@@ -115,6 +115,11 @@ int bh_restore(bh_ctx* ctx);
 int bh_step(bh_ctx* ctx, int32_t nsteps);
 /* same, but every step first restores the snapshot (device-to-device) */
 int bh_step_from_snapshot(bh_ctx* ctx, int32_t nsteps);
+/* one step with HOST buffers (the reference-facing call: project.cu moves the tree H2D and the
+ * positions D2H every step, :968, :1010): uploads pos / mass / vel, runs one step, downloads the new
+ * positions into out_pos_xy_host.  Uploads are pipelined against the build. Synchronous. */
+int bh_step_host(bh_ctx* ctx, const double* pos_xy_host, const double* vel_xy_host, const double* mass_host,
+                 double* out_pos_xy_host);
 /* phase-split entry points for teacher-forced parity */
 int bh_build_tree(bh_ctx* ctx);       /* replaces buildTree        project.cu:575-591 (+H2D :968) */
 int bh_compute_forces(bh_ctx* ctx);   /* replaces computeForcesGpu project.cu:679-793; needs a built tree */

@@ -331,3 +331,14 @@ def test_cli_project_drop_in(tmp_path):
     traj = np.loadtxt(tmp_path / "positions.txt")
     assert traj.shape == ((steps + 1) * n, 4)                 # plot_2d.py: time body x y
     assert np.allclose(traj[:n, 2:], np.round(p, 6), atol=1e-6)
+
+
+def test_step_host_pipelined_equals_plain_sequence():
+    pos, vel, mass, _ = golden_inputs("shipped_40000")
+    with Simulation(40000) as a, Simulation(40000) as b:
+        out = a.step_host(pos, vel, mass)
+        b.set_bodies(pos, vel, mass); b.step(1)
+        assert np.array_equal(out, b.positions())
+        assert np.array_equal(a.velocities(), b.velocities())
+        out2 = a.step_host(pos, vel, mass)           # the call is repeatable (state fully overwritten)
+        assert np.array_equal(out2, out)
