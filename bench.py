@@ -220,8 +220,18 @@ def run_ours(args):
     value = n * K / (ms * 1e-3)
 
     # ---- per-phase events + interaction count (second pass, direct launches, same work) -----------
-    simc = bh.Simulation(n, device=local, rank=rank, n_ranks=1, counters=True) if world == 1 else None
     phases, inter_per_step, roofline = None, None, None
+    if world > 1:      # collective: every rank runs the profiled pass, rank 0 reports its phases
+        sim.set_profiling(True)
+        sim.step_from_snapshot(2)
+        sim.reset_timers()
+        timed_steps(K)
+        sim.synchronize()
+        t = sim.timers()
+        sim.set_profiling(False)
+        phases = {k: t[k] / max(t["steps"], 1) for k in ("bounds_keys_us", "sort_us", "build_us", "traverse_us",
+                                                         "exchange_us", "total_us")}
+    simc = bh.Simulation(n, device=local, rank=rank, n_ranks=1, counters=True) if world == 1 else None
     if rank == 0 and simc is not None:
         simc.set_bodies(pos, vel, mass)
         simc.snapshot()

@@ -32,6 +32,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -54,6 +55,7 @@ static NcclApi* nccl_api() {
     BH_SYM(CommInitRank, "ncclCommInitRank");
     BH_SYM(CommDestroy, "ncclCommDestroy");
     BH_SYM(Broadcast, "ncclBroadcast");
+    BH_SYM(AllReduce, "ncclAllReduce");
     BH_SYM(GroupStart, "ncclGroupStart");
     BH_SYM(GroupEnd, "ncclGroupEnd");
     BH_SYM(GetErrorString, "ncclGetErrorString");
@@ -112,10 +114,15 @@ struct bh_ctx {
     float4* packed = nullptr;     // direct-sum kernel input
     // multi-GPU
     int64_t own_lo = 0, own_hi = 0;
-    uint32_t* own_list = nullptr;
+    uint32_t* own_list = nullptr;  // (unused since the sharded build; kept for ABI-internal stability)
     uint32_t* own_count = nullptr;
-    uint32_t* perm = nullptr;     // internal index -> original index (n_ranks > 1)
+    uint32_t* perm = nullptr;
     bool renumbered = false;
+    double* cell_sums = nullptr;   // [4][finest cells]: count, m, m x, m y — all-reduced every step
+    double* bbox_raw = nullptr;    // [4]: xmin, -xmax, ymin, -ymax — all-reduced (min) every step
+    SortPlan sp_own;               // sort plan for this rank's slice
+    bool tree_full = false;        // the tree on the device was built from ALL bodies (diagnostic getters)
+    bool mass_complete = true;     // multi-rank: masses of the other ranks' slices have been gathered
     ncclComm_t comm = nullptr;
     // graphs
     cudaGraphExec_t graph[2] = {nullptr, nullptr};   // [0] plain step, [1] step from snapshot
@@ -200,46 +207,76 @@ void zero_scratch(bh_ctx* c) {
     cudaMemsetAsync(c->s.zero_base, 0, c->s.zero_bytes, c->stream);
     cudaMemsetAsync(c->tree.count + c->d.level_off[c->d.finest], 0, c->d.ncells_finest * sizeof(uint32_t), c->stream);
     cudaMemsetAsync(c->tree.self_node, 0xff, c->d.n * sizeof(uint32_t), c->stream);
-    if (c->own_count) cudaMemsetAsync(c->own_count, 0, sizeof(uint32_t), c->stream);
 }
 
 void prof_mark(bh_ctx* c, int i) { if (c->profiling) cudaEventRecord(c->pev[i], c->stream); }
 
-// bounds -> keys -> sort -> tree, on the context's stream
-int enqueue_build(bh_ctx* c) {
+int allreduce_f64(bh_ctx* c, double* buf, size_t count, ncclRedOp_t op) {
+    NcclApi* api = nccl_api();
+    if (!api || !c->comm) { set_error("multi-rank context without an attached NCCL communicator"); return BH_ERR_NCCL; }
+    BH_NCCL_OK(api, api->AllReduce(buf, buf, count, ncclDouble, op, c->comm, c->stream));
+    return BH_OK;
+}
+
+// bounds -> keys -> sort -> tree, on the context's stream.
+//
+// Single GPU (or full = true: diagnostic getters of a multi-rank context after an exchange of
+// positions): everything over all N bodies.
+// Multi GPU (sharded build): every rank keys and sorts ONLY its own index slice and sums its bodies
+// per finest cell; two all-reduces make the tree global — 4 doubles (min of xmin, -xmax, ymin, -ymax)
+// and 4 doubles per finest cell (count, m, m x, m y: 8.4 MB at the default cap, independent of N).
+// The level pass then runs redundantly on the identical reduced sums.  No body data crosses NVLink.
+int enqueue_build(bh_ctx* c, bool full = false) {
     zero_scratch(c);
     prof_mark(c, 0);
-    launch_bounds(c->pos, c->d.n, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream);
-    launch_keys(c->pos, c->d.n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream);
-    prof_mark(c, 1);
-    launch_sort(c->keys, c->idx, c->d.n, c->sp, c->s, &c->sorted, c->stream);
-    prof_mark(c, 2);
-    launch_tree(c->keys[c->sorted], c->idx[c->sorted], c->pos, c->mass, c->d.n, c->p, c->d, c->tree, c->s, c->consts,
-                c->stream);
-    if (c->p.n_ranks > 1)
-        launch_own_list(c->idx[c->sorted], c->d.n, c->own_lo, c->own_hi, c->own_list, c->own_count, c->stream);
+    const bool sharded = c->p.n_ranks > 1 && !full;
+    if (!sharded) {
+        launch_bounds(c->pos, c->d.n, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream);
+        launch_keys(c->pos, c->d.n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream);
+        prof_mark(c, 1);
+        launch_sort(c->keys, c->idx, c->d.n, c->sp, c->s, &c->sorted, c->stream);
+        prof_mark(c, 2);
+        launch_tree(c->keys[c->sorted], c->idx[c->sorted], c->pos, c->mass, c->d.n, c->p, c->d, c->tree, c->s, c->consts,
+                    c->stream);
+        c->tree_full = true;
+    } else {
+        const int64_t lo = c->own_lo, n_own = c->own_hi - c->own_lo;
+        launch_bounds(c->pos + lo, n_own, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream, c->bbox_raw);
+        BH_TRY(allreduce_f64(c, c->bbox_raw, 4, ncclMin));
+        launch_bounds_finalize(c->bbox_raw, c->p, c->d, c->consts, c->stream);
+        launch_keys(c->pos + lo, n_own, c->d, c->sp_own, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream,
+                    (uint32_t)lo);
+        prof_mark(c, 1);
+        launch_sort(c->keys, c->idx, n_own, c->sp_own, c->s, &c->sorted, c->stream);
+        prof_mark(c, 2);
+        launch_tree_runs(c->keys[c->sorted], c->idx[c->sorted], c->pos, c->mass, n_own, c->p, c->d, c->tree, c->s,
+                         c->cell_sums, c->stream);
+        BH_TRY(allreduce_f64(c, c->cell_sums, 4 * c->d.ncells_finest, ncclSum));
+        launch_tree_levels(c->idx[c->sorted], c->pos, c->mass, c->p, c->d, c->tree, c->s, c->consts, c->cell_sums, c->stream);
+        c->tree_full = false;
+    }
     prof_mark(c, 3);
     return check_launch();
 }
 
 int enqueue_forces(bh_ctx* c, bool integrate) {
-    const bool multi = c->p.n_ranks > 1;
+    // after a sharded build the sorted list holds exactly this rank's bodies
+    const int64_t n_eval = (c->p.n_ranks > 1 && !c->tree_full) ? (c->own_hi - c->own_lo) : c->d.n;
     launch_traverse(c->keys[c->sorted], c->idx[c->sorted], c->pos, c->vel, c->acc, c->force, c->mass, c->d.n,
-                    c->own_lo, c->own_hi, multi ? c->own_list : nullptr, c->own_count,
-                    multi ? (c->own_hi - c->own_lo) : c->d.n, c->p, c->d, c->tree, c->consts, c->s.counters, integrate,
+                    c->own_lo, c->own_hi, nullptr, nullptr, n_eval, c->p, c->d, c->tree, c->consts, c->s.counters, integrate,
                     c->stream);
     prof_mark(c, 4);
     return check_launch();
 }
 
 int enqueue_step(bh_ctx* c, bool from_snapshot) {
-    if (from_snapshot) {
-        cudaMemcpyAsync(c->pos, c->snap_pos, sizeof(double2) * c->d.n, cudaMemcpyDeviceToDevice, c->stream);
-        cudaMemcpyAsync(c->vel, c->snap_vel, sizeof(double2) * c->d.n, cudaMemcpyDeviceToDevice, c->stream);
+    if (from_snapshot) {   // a rank only ever reads and writes its own slice of pos / vel
+        const int64_t lo = c->own_lo, cnt = c->own_hi - c->own_lo;
+        cudaMemcpyAsync(c->pos + lo, c->snap_pos + lo, sizeof(double2) * cnt, cudaMemcpyDeviceToDevice, c->stream);
+        cudaMemcpyAsync(c->vel + lo, c->snap_vel + lo, sizeof(double2) * cnt, cudaMemcpyDeviceToDevice, c->stream);
     }
     BH_TRY(enqueue_build(c));
     BH_TRY(enqueue_forces(c, true));
-    if (c->p.n_ranks > 1) BH_TRY(exchange_slices(c, c->pos, sizeof(double2)));
     prof_mark(c, 5);
     return BH_OK;
 }
@@ -299,15 +336,20 @@ int run_steps(bh_ctx* c, int nsteps, bool from_snapshot) {
 int copy_out2(bh_ctx* c, const double2* dev, double* host, bool gather_ranks) {
     if (!host) { set_error("null output buffer"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
+    // multi-rank: every rank only keeps its own slice current; getters are collective and gather first
     if (gather_ranks && c->p.n_ranks > 1) BH_TRY(exchange_slices(c, (void*)dev, sizeof(double2)));
-    const double2* src = dev;
-    if (c->renumbered) {
-        scatter2_kernel<<<(unsigned)((c->d.n + 255) / 256), 256, 0, c->stream>>>(dev, c->perm, c->d.n, c->tmp2);
-        ++g_launches;
-        src = c->tmp2;
-    }
-    BH_CUDA_OK(cudaMemcpyAsync(host, src, sizeof(double2) * c->d.n, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(host, dev, sizeof(double2) * c->d.n, cudaMemcpyDeviceToHost, c->stream));
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return BH_OK;
+}
+
+// Diagnostic getters (keys, order, node table, dump) of a multi-rank context need the tree over
+// ALL bodies with global sorted positions: gather positions, then build like a single GPU.
+int ensure_full_tree(bh_ctx* c) {
+    if (c->p.n_ranks <= 1 || c->tree_full) return BH_OK;
+    if (!c->mass_complete) { BH_TRY(exchange_slices(c, c->mass, sizeof(double))); c->mass_complete = true; }
+    BH_TRY(exchange_slices(c, c->pos, sizeof(double2)));
+    BH_TRY(enqueue_build(c, true));
     return BH_OK;
 }
 
@@ -394,10 +436,12 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     BH_ALLOC(c->s.bbox_partial, (size_t)c->bounds_grid * 4);
     BH_ALLOC(c->s.heavy_list, c->d.ncells_finest);
     if (p->n_ranks > 1) {
-        BH_ALLOC(c->own_list, n); BH_ALLOC(c->own_count, 1); BH_ALLOC(c->perm, n); BH_ALLOC(c->tmp2, n); BH_ALLOC(c->tmp1, n);
+        BH_ALLOC(c->cell_sums, 4 * c->d.ncells_finest); BH_ALLOC(c->bbox_raw, 4);
     }
 #undef BH_ALLOC
     bh_shard_range(n, p->n_ranks, p->rank, &c->own_lo, &c->own_hi);
+    c->sp_own = c->sp;
+    c->sp_own.ntiles = (int)std::max<int64_t>(1, (c->own_hi - c->own_lo + kSortTile - 1) / kSortTile);
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     for (auto& ev : c->ev_up) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -420,7 +464,7 @@ int bh_destroy(bh_ctx* c) {
     void* ptrs[] = {c->pos, c->vel, c->acc, c->force, c->snap_pos, c->snap_vel, c->tmp2, c->mass, c->tmp1, c->keys[0],
                     c->keys[1], c->idx[0], c->idx[1], c->consts, c->tree.mass, c->tree.comx, c->tree.comy,
                     c->tree.count, c->tree.first, c->tree.flags, c->rec_alloc, c->tree.self_node, c->s.zero_base, c->s.bbox_partial, c->s.heavy_list,
-                    c->packed, c->own_list, c->own_count, c->perm};
+                    c->packed, c->own_list, c->own_count, c->perm, c->cell_sums, c->bbox_raw};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -456,29 +500,14 @@ int bh_set_bodies(bh_ctx* c, const double* pos, const double* vel, const double*
     if (!c || !pos || !vel || !mass) { set_error("null argument"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     const int64_t n = c->d.n;
-    if (c->p.n_ranks == 1) {
-        BH_CUDA_OK(cudaMemcpyAsync(c->pos, pos, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
-        BH_CUDA_OK(cudaMemcpyAsync(c->vel, vel, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
-        BH_CUDA_OK(cudaMemcpyAsync(c->mass, mass, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
-    } else {
-        // Morton renumbering: internal index j = j-th body of the initial cell-key order, so that a
-        // rank's contiguous index slice is a contiguous Morton range of the initial distribution.
-        BH_CUDA_OK(cudaMemcpyAsync(c->pos, pos, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
-        zero_scratch(c);
-        launch_bounds(c->pos, n, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream);
-        launch_keys(c->pos, n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream);
-        launch_sort(c->keys, c->idx, n, c->sp, c->s, &c->sorted, c->stream);
-        BH_CUDA_OK(cudaMemcpyAsync(c->perm, c->idx[c->sorted], sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, c->stream));
-        const unsigned blocks = (unsigned)((n + 255) / 256);
-        BH_CUDA_OK(cudaMemcpyAsync(c->tmp2, pos, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
-        gather2_kernel<<<blocks, 256, 0, c->stream>>>(c->tmp2, c->perm, n, c->pos);
-        BH_CUDA_OK(cudaMemcpyAsync(c->tmp2, vel, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
-        gather2_kernel<<<blocks, 256, 0, c->stream>>>(c->tmp2, c->perm, n, c->vel);
-        BH_CUDA_OK(cudaMemcpyAsync(c->tmp1, mass, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
-        gather1_kernel<<<blocks, 256, 0, c->stream>>>(c->tmp1, c->perm, n, c->mass);
-        g_launches += 3;
-        c->renumbered = true;
-    }
+    // A rank of a multi-rank context uploads only ITS slice (the host buffers still hold all bodies,
+    // original order): the sharded build needs nothing else.  Diagnostic getters gather on demand.
+    (void)n;
+    const int64_t lo = c->own_lo, cnt = c->own_hi - c->own_lo;
+    BH_CUDA_OK(cudaMemcpyAsync(c->pos + lo, pos + 2 * lo, sizeof(double2) * cnt, cudaMemcpyHostToDevice, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(c->vel + lo, vel + 2 * lo, sizeof(double2) * cnt, cudaMemcpyHostToDevice, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(c->mass + lo, mass + lo, sizeof(double) * cnt, cudaMemcpyHostToDevice, c->stream));
+    c->mass_complete = c->p.n_ranks == 1;
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
     BH_TRY(check_launch());
     c->bodies_set = true;
@@ -491,13 +520,9 @@ static int set_vec(bh_ctx* c, double2* dst, const double* src) {
     if (!c->bodies_set) { set_error("bh_set_bodies first"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     const int64_t n = c->d.n;
-    if (!c->renumbered) {
-        BH_CUDA_OK(cudaMemcpyAsync(dst, src, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
-    } else {
-        BH_CUDA_OK(cudaMemcpyAsync(c->tmp2, src, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
-        gather2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->tmp2, c->perm, n, dst);
-        ++g_launches;
-    }
+    (void)n;
+    BH_CUDA_OK(cudaMemcpyAsync(dst + c->own_lo, src + 2 * c->own_lo, sizeof(double2) * (c->own_hi - c->own_lo),
+                               cudaMemcpyHostToDevice, c->stream));
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
     c->tree_valid = false;
     return BH_OK;
@@ -541,7 +566,18 @@ int bh_step_from_snapshot(bh_ctx* c, int32_t nsteps) {
 // their uploads overlap the build and the traversal.  out_pos_host receives the new positions.
 int bh_step_host(bh_ctx* c, const double* pos, const double* vel, const double* mass, double* out_pos) {
     if (!c || !pos || !vel || !mass || !out_pos) { set_error("null argument"); return BH_ERR_INVALID; }
-    if (c->p.n_ranks > 1 || c->profiling) {       // multi-rank / profiling: plain sequence
+    if (c->p.n_ranks > 1) {
+        // multi-rank: every rank moves only its own slice both ways (out_pos gets this rank's slice; the
+        // other entries are left untouched — one process per GPU owns one slice of the host arrays)
+        BH_TRY(bh_set_bodies(c, pos, vel, mass));
+        BH_TRY(bh_step(c, 1));
+        DeviceGuard g(c->device);
+        const int64_t lo = c->own_lo, cnt = c->own_hi - c->own_lo;
+        BH_CUDA_OK(cudaMemcpyAsync(out_pos + 2 * lo, c->pos + lo, sizeof(double2) * cnt, cudaMemcpyDeviceToHost, c->stream));
+        BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+        return BH_OK;
+    }
+    if (c->profiling) {
         BH_TRY(bh_set_bodies(c, pos, vel, mass));
         BH_TRY(bh_step(c, 1));
         return bh_get_positions(c, out_pos);
@@ -585,6 +621,7 @@ int bh_build_tree(bh_ctx* c) {
 int bh_compute_forces(bh_ctx* c) {
     if (!c || !c->tree_valid) { set_error("bh_compute_forces: build the tree first"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
+    if (c->p.n_ranks > 1 && c->tree_full) BH_TRY(enqueue_build(c));   // diagnostic getters left a full tree behind
     cudaMemsetAsync(c->s.counters, 0, 4 * sizeof(unsigned long long), c->stream);
     return enqueue_forces(c, false);
 }
@@ -594,7 +631,6 @@ int bh_integrate(bh_ctx* c) {
     DeviceGuard g(c->device);
     launch_integrate(c->pos, c->vel, c->acc, c->force, c->mass, c->own_lo, c->own_hi, c->p.dt, c->stream);
     BH_TRY(check_launch());
-    if (c->p.n_ranks > 1) BH_TRY(exchange_slices(c, c->pos, sizeof(double2)));
     c->tree_valid = false;
     return BH_OK;
 }
@@ -606,7 +642,7 @@ int bh_synchronize(bh_ctx* c) {
     return BH_OK;
 }
 
-int bh_get_positions(bh_ctx* c, double* out) { if (!c) return BH_ERR_INVALID; return copy_out2(c, c->pos, out, false); }
+int bh_get_positions(bh_ctx* c, double* out) { if (!c) return BH_ERR_INVALID; return copy_out2(c, c->pos, out, true); }
 int bh_get_velocities(bh_ctx* c, double* out) { if (!c) return BH_ERR_INVALID; return copy_out2(c, c->vel, out, true); }
 int bh_get_accelerations(bh_ctx* c, double* out) { if (!c) return BH_ERR_INVALID; return copy_out2(c, c->acc, out, true); }
 int bh_get_forces(bh_ctx* c, double* out) { if (!c) return BH_ERR_INVALID; return copy_out2(c, c->force, out, true); }
@@ -641,6 +677,7 @@ static int fetch_perm(bh_ctx* c, std::vector<uint32_t>& perm) {
 int bh_get_body_keys(bh_ctx* c, uint32_t* out) {
     if (!c || !out || !c->tree_valid) { set_error("bh_get_body_keys: no tree built"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
+    BH_TRY(ensure_full_tree(c));
     std::vector<uint32_t> keys, idx, perm;
     BH_TRY(fetch_sorted(c, keys, idx));
     BH_TRY(fetch_perm(c, perm));
@@ -654,6 +691,7 @@ int bh_get_body_keys(bh_ctx* c, uint32_t* out) {
 int bh_get_sorted_order(bh_ctx* c, uint32_t* out) {
     if (!c || !out || !c->tree_valid) { set_error("bh_get_sorted_order: no tree built"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
+    BH_TRY(ensure_full_tree(c));
     std::vector<uint32_t> keys, idx, perm;
     BH_TRY(fetch_sorted(c, keys, idx));
     BH_TRY(fetch_perm(c, perm));
@@ -696,6 +734,7 @@ static int fetch_host_tree(bh_ctx* c, HostTree& ht) {
 int bh_get_tree(bh_ctx* c, double* out_rows, int64_t cap_rows, int64_t* n_rows) {
     if (!c || !n_rows || !c->tree_valid) { set_error("bh_get_tree: no tree built"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
+    BH_TRY(ensure_full_tree(c));
     HostTree ht;
     BH_TRY(fetch_host_tree(c, ht));
     *n_rows = canonical_rows(ht, out_rows, cap_rows);
@@ -705,6 +744,7 @@ int bh_get_tree(bh_ctx* c, double* out_rows, int64_t cap_rows, int64_t* n_rows) 
 int bh_dump_quadtree(bh_ctx* c, const char* path) {
     if (!c || !path || !c->tree_valid) { set_error("bh_dump_quadtree: no tree built"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
+    BH_TRY(ensure_full_tree(c));
     HostTree ht;
     BH_TRY(fetch_host_tree(c, ht));
     return dump_quadtree_txt(ht, path);

@@ -92,9 +92,16 @@ struct Dims {
 
 // ---- kernel launchers (each in its own .cu) ------------------------------------------------
 void launch_bounds(const double2* pos, int64_t n, const bh_params& p, const Dims& d, Scratch& s,
-                   StepConsts* consts, int grid, cudaStream_t st);
+                   StepConsts* consts, int grid, cudaStream_t st, double* raw_out = nullptr);
+void launch_bounds_finalize(const double* raw, const bh_params& p, const Dims& d, StepConsts* consts, cudaStream_t st);
 void launch_keys(const double2* pos, int64_t n, const Dims& d, const SortPlan& sp, const StepConsts* consts,
-                 uint32_t* keys, uint32_t* idx, uint32_t* digit_hist, cudaStream_t st);
+                 uint32_t* keys, uint32_t* idx, uint32_t* digit_hist, cudaStream_t st, uint32_t idx_base = 0);
+void launch_tree_runs(const uint32_t* skeys, const uint32_t* sidx, const double2* pos, const double* mass,
+                      int64_t n, const bh_params& p, const Dims& d, TreeArrays& t, Scratch& s, double* sums,
+                      cudaStream_t st);
+void launch_tree_levels(const uint32_t* sidx, const double2* pos, const double* mass, const bh_params& p,
+                        const Dims& d, TreeArrays& t, Scratch& s, const StepConsts* consts, const double* sums,
+                        cudaStream_t st);
 void launch_sort(uint32_t* keys[2], uint32_t* vals[2], int64_t n, const SortPlan& sp, Scratch& s,
                  int* result_buf, cudaStream_t st);
 void launch_tree(const uint32_t* skeys, const uint32_t* sidx, const double2* pos, const double* mass,

@@ -17,10 +17,50 @@ constexpr int kBoundsThreads = 256;
 __device__ __forceinline__ double ref_min(double cur, double x) { return (x < cur) ? x : cur; }
 __device__ __forceinline__ double ref_max(double cur, double x) { return (cur < x) ? x : cur; }
 
+// Padding (project.cu:553-570), per-level cell sizes and acceptance thresholds, FP32 scale.
+__device__ void finalize_bounds(StepConsts* __restrict__ consts, double xmin, double xmax, double ymin, double ymax,
+                                double pad_frac, double pad_fallback, double theta, double dist_eps, int finest) {
+    // project.cu:553-570, same operation order, no FMA contraction
+    double dx = __dsub_rn(xmax, xmin), dy = __dsub_rn(ymax, ymin);
+    double max_dim = (dx < dy) ? dy : dx;                 // std::max(dx, dy)
+    double pad = __dmul_rn(pad_frac, max_dim);
+    if (max_dim == 0.0) pad = pad_fallback;
+    xmin = __dsub_rn(xmin, pad); xmax = __dadd_rn(xmax, pad);
+    ymin = __dsub_rn(ymin, pad); ymax = __dadd_rn(ymax, pad);
+    consts->xmin = xmin; consts->xmax = xmax; consts->ymin = ymin; consts->ymax = ymax;
+    // power-of-two normalisation of the FP32 traversal coordinates: box extent -> [2^20, 2^21)
+    double ext = fmax(__dsub_rn(xmax, xmin), __dsub_rn(ymax, ymin));
+    int e2 = (ext > 0.0 && ext < INFINITY) ? ilogb(ext) : 20;
+    int se = 20 - e2;
+    se = se > 120 ? 120 : (se < -120 ? -120 : se);
+    const double scale = scalbn(1.0, se);
+    consts->scale = scale;
+    consts->feps = (float)(dist_eps * scale);
+    // cell extent per level, following the low-side bisection chain (project.cu:417-428)
+    double xl = xmin, xh = xmax, yl = ymin, yh = ymax;
+    for (int l = 0; l < kMaxLevels; ++l) {
+        double w = __dsub_rn(xh, xl), h = __dsub_rn(yh, yl);
+        double size = (w > h) ? w : h;                    // project.cu:637-639
+        consts->size[l] = size;
+        // size / (d + eps) < theta  <=>  d > size/theta - eps
+        double thr = (theta > 0.0) ? (size / theta - dist_eps) : INFINITY;
+        consts->thr[l] = thr;
+        float t2;
+        if (!(theta > 0.0)) t2 = INFINITY;
+        else if (thr < 0.0) t2 = -1.0f;
+        else t2 = (float)((thr * scale) * (thr * scale));
+        consts->thr2[l] = t2;
+        if (l < finest) {
+            xh = __dmul_rn(__dadd_rn(xl, xh), 0.5);
+            yh = __dmul_rn(__dadd_rn(yl, yh), 0.5);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kBoundsThreads)
 bounds_kernel(const double2* __restrict__ pos, int64_t n, double* __restrict__ partial,
               uint32_t* __restrict__ ticket, StepConsts* __restrict__ consts, double pad_frac,
-              double pad_fallback, double theta, double dist_eps, int finest) {
+              double pad_fallback, double theta, double dist_eps, int finest, double* __restrict__ raw_out) {
     double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double2 p = pos[i];
@@ -73,49 +113,25 @@ bounds_kernel(const double2* __restrict__ pos, int64_t n, double* __restrict__ p
     block_reduce();
     if (threadIdx.x == 0) {
         *ticket = 0;
-        // project.cu:553-570, same operation order, no FMA contraction
-        double dx = __dsub_rn(xmax, xmin), dy = __dsub_rn(ymax, ymin);
-        double max_dim = (dx < dy) ? dy : dx;                 // std::max(dx, dy)
-        double pad = __dmul_rn(pad_frac, max_dim);
-        if (max_dim == 0.0) pad = pad_fallback;
-        xmin = __dsub_rn(xmin, pad); xmax = __dadd_rn(xmax, pad);
-        ymin = __dsub_rn(ymin, pad); ymax = __dadd_rn(ymax, pad);
-        consts->xmin = xmin; consts->xmax = xmax; consts->ymin = ymin; consts->ymax = ymax;
-        // power-of-two normalisation of the FP32 traversal coordinates: box extent -> [2^20, 2^21)
-        double ext = fmax(__dsub_rn(xmax, xmin), __dsub_rn(ymax, ymin));
-        int e2 = (ext > 0.0 && ext < INFINITY) ? ilogb(ext) : 20;
-        int se = 20 - e2;
-        se = se > 120 ? 120 : (se < -120 ? -120 : se);
-        const double scale = scalbn(1.0, se);
-        consts->scale = scale;
-        consts->feps = (float)(dist_eps * scale);
-        // cell extent per level, following the low-side bisection chain (project.cu:417-428)
-        double xl = xmin, xh = xmax, yl = ymin, yh = ymax;
-        for (int l = 0; l < kMaxLevels; ++l) {
-            double w = __dsub_rn(xh, xl), h = __dsub_rn(yh, yl);
-            double size = (w > h) ? w : h;                    // project.cu:637-639
-            consts->size[l] = size;
-            // size / (d + eps) < theta  <=>  d > size/theta - eps
-            double thr = (theta > 0.0) ? (size / theta - dist_eps) : INFINITY;
-            consts->thr[l] = thr;
-            float t2;
-            if (!(theta > 0.0)) t2 = INFINITY;
-            else if (thr < 0.0) t2 = -1.0f;
-            else t2 = (float)((thr * scale) * (thr * scale));
-            consts->thr2[l] = t2;
-            if (l < finest) {
-                xh = __dmul_rn(__dadd_rn(xl, xh), 0.5);
-                yh = __dmul_rn(__dadd_rn(yl, yh), 0.5);
-            }
+        if (raw_out) {   // multi-GPU: min / max are all-reduced over the ranks first (max sent negated)
+            raw_out[0] = xmin; raw_out[1] = -xmax; raw_out[2] = ymin; raw_out[3] = -ymax;
+        } else {
+            finalize_bounds(consts, xmin, xmax, ymin, ymax, pad_frac, pad_fallback, theta, dist_eps, finest);
         }
     }
+}
+
+__global__ void bounds_finalize_kernel(const double* __restrict__ raw, StepConsts* __restrict__ consts, double pad_frac,
+                                       double pad_fallback, double theta, double dist_eps, int finest) {
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        finalize_bounds(consts, raw[0], -raw[1], raw[2], -raw[3], pad_frac, pad_fallback, theta, dist_eps, finest);
 }
 
 // One thread per body.  Also accumulates the radix-sort digit histograms of all passes.
 __global__ void __launch_bounds__(256)
 keys_kernel(const double2* __restrict__ pos, int64_t n, int finest, const StepConsts* __restrict__ consts,
             uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ digit_hist,
-            int passes, int bits_per_pass) {
+            int passes, int bits_per_pass, uint32_t idx_base) {
     __shared__ uint32_t hist[kMaxSortPasses * kMaxBins];
     for (int i = threadIdx.x; i < passes * kMaxBins; i += blockDim.x) hist[i] = 0;
     __syncthreads();
@@ -138,7 +154,7 @@ keys_kernel(const double2* __restrict__ pos, int64_t n, int finest, const StepCo
             key = (key << 2) | (uint32_t)bx | ((uint32_t)by << 1);
         }
         keys[i] = key;
-        idx[i] = (uint32_t)i;
+        idx[i] = idx_base + (uint32_t)i;
         for (int ps = 0; ps < passes; ++ps)
             atomicAdd(&hist[ps * kMaxBins + ((key >> (ps * bits_per_pass)) & dmask)], 1u);
     }
@@ -152,19 +168,24 @@ keys_kernel(const double2* __restrict__ pos, int64_t n, int finest, const StepCo
 }  // namespace
 
 void launch_bounds(const double2* pos, int64_t n, const bh_params& p, const Dims& d, Scratch& s,
-                   StepConsts* consts, int grid, cudaStream_t st) {
+                   StepConsts* consts, int grid, cudaStream_t st, double* raw_out) {
     bounds_kernel<<<grid, kBoundsThreads, 0, st>>>(pos, n, s.bbox_partial, s.bbox_ticket, consts, p.pad_frac,
-                                                   p.pad_fallback, p.theta, p.dist_eps, d.finest);
+                                                   p.pad_fallback, p.theta, p.dist_eps, d.finest, raw_out);
+    ++g_launches;
+}
+
+void launch_bounds_finalize(const double* raw, const bh_params& p, const Dims& d, StepConsts* consts, cudaStream_t st) {
+    bounds_finalize_kernel<<<1, 32, 0, st>>>(raw, consts, p.pad_frac, p.pad_fallback, p.theta, p.dist_eps, d.finest);
     ++g_launches;
 }
 
 void launch_keys(const double2* pos, int64_t n, const Dims& d, const SortPlan& sp, const StepConsts* consts,
-                 uint32_t* keys, uint32_t* idx, uint32_t* digit_hist, cudaStream_t st) {
+                 uint32_t* keys, uint32_t* idx, uint32_t* digit_hist, cudaStream_t st, uint32_t idx_base) {
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     keys_kernel<<<(int)blocks, 256, 0, st>>>(pos, n, d.finest, consts, keys, idx, digit_hist, sp.passes,
-                                             sp.bits_per_pass);
+                                             sp.bits_per_pass, idx_base);
     ++g_launches;
 }
 

@@ -38,18 +38,31 @@ struct Cell {
 // itself; internal parents follow ComputeMass.
 // When the parent is internal, every child holding exactly one body is that body's own leaf: its
 // pyramid index goes to self_node[body] (the traversal's self-interaction test, project.cu:646/:760).
+// SHARDED (multi-GPU): `cnt` is the GLOBAL body count of the cell (all ranks), `first` the sorted
+// position of this rank's first body inside it (kNoFirst if the rank has none there); node values
+// come from all-reduced sums, so a lone body's cell copies its only non-empty child instead of
+// looking the body up (which another rank may own).
+constexpr uint32_t kNoFirst = 0xffffffffu;
+
+template <bool SHARDED>
 __device__ __forceinline__ Cell combine4(const Cell c[4], const uint32_t* __restrict__ sidx,
                                          const double2* __restrict__ pos, const double* __restrict__ mass,
                                          uint32_t* __restrict__ self_node, uint64_t child_base, bool write_self) {
     Cell p;
     p.cnt = c[0].cnt + c[1].cnt + c[2].cnt + c[3].cnt;
-    p.first = c[0].cnt ? c[0].first : c[1].cnt ? c[1].first : c[2].cnt ? c[2].first : c[3].first;
+    p.first = c[0].first != kNoFirst ? c[0].first : c[1].first != kNoFirst ? c[1].first
+            : c[2].first != kNoFirst ? c[2].first : c[3].first;
     if (p.cnt == 0) {
-        p.m = 0.0; p.cx = 0.0; p.cy = 0.0; p.first = 0;
+        p.m = 0.0; p.cx = 0.0; p.cy = 0.0; p.first = kNoFirst;
     } else if (p.cnt == 1) {                       // leaf above the cap: project.cu:400-403
-        uint32_t b = sidx[p.first];
-        double2 x = pos[b];
-        p.m = mass[b]; p.cx = x.x; p.cy = x.y;
+        if constexpr (SHARDED) {
+            const int q = c[0].cnt ? 0 : c[1].cnt ? 1 : c[2].cnt ? 2 : 3;
+            p.m = c[q].m; p.cx = c[q].cx; p.cy = c[q].cy;
+        } else {
+            uint32_t b = sidx[p.first];
+            double2 x = pos[b];
+            p.m = mass[b]; p.cx = x.x; p.cy = x.y;
+        }
     } else {                                       // project.cu:480-499
         double tm = 0.0, sx = 0.0, sy = 0.0;
 #pragma unroll
@@ -63,7 +76,7 @@ __device__ __forceinline__ Cell combine4(const Cell c[4], const uint32_t* __rest
         if (write_self) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (c[q].cnt == 1u) self_node[sidx[c[q].first]] = (uint32_t)(child_base + q);
+                if (c[q].cnt == 1u && c[q].first != kNoFirst) self_node[sidx[c[q].first]] = (uint32_t)(child_base + q);
         }
     }
     return p;
@@ -95,7 +108,7 @@ __device__ __forceinline__ void store_cell(const TreeArrays& t, uint64_t at, con
     }
     r.count = c.cnt; r.first = c.first;
     t.rec[at] = r;
-    if (level == 0 && c.cnt == 1u) t.self_node[sidx[c.first]] = 0u;   // a lone body: the root is its leaf
+    if (level == 0 && c.cnt == 1u && c.first != kNoFirst) t.self_node[sidx[c.first]] = 0u;   // a lone body: the root is its leaf
 }
 
 // ---- finest-cell runs from the sorted keys ------------------------------------------------------
@@ -138,7 +151,7 @@ heavy_cells_kernel(const uint32_t* __restrict__ heavy_list, const uint32_t* __re
                    const uint32_t* __restrict__ cnt_f, const uint32_t* __restrict__ first_f,
                    const uint32_t* __restrict__ sidx, const double2* __restrict__ pos,
                    const double* __restrict__ mass, double* __restrict__ m_f, double* __restrict__ cx_f,
-                   double* __restrict__ cy_f) {
+                   double* __restrict__ cy_f, bool raw_sums) {
     __shared__ double sm[3][256];
     const uint32_t nheavy = *heavy_count;
     for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
@@ -164,11 +177,36 @@ heavy_cells_kernel(const uint32_t* __restrict__ heavy_list, const uint32_t* __re
         if (threadIdx.x == 0) {
             double tm = sm[0][0];
             m_f[cell] = tm;
-            cx_f[cell] = tm > 0.0 ? sm[1][0] / tm : 0.0;
-            cy_f[cell] = tm > 0.0 ? sm[2][0] / tm : 0.0;
+            if (raw_sums) { cx_f[cell] = sm[1][0]; cy_f[cell] = sm[2][0]; }   // sharded: divided after the all-reduce
+            else { cx_f[cell] = tm > 0.0 ? sm[1][0] / tm : 0.0; cy_f[cell] = tm > 0.0 ? sm[2][0] / tm : 0.0; }
         }
         __syncthreads();
     }
+}
+
+// ---- sharded build: this rank's partial sums per finest cell (count, m, m x, m y) ------------------
+// sums = [4][ncells] doubles, all-reduced over the ranks before the level pass.  Cells queued as
+// heavy were already summed (raw) by heavy_cells_kernel.
+__global__ void __launch_bounds__(256)
+cell_partial_kernel(const uint32_t* __restrict__ cnt_f, const uint32_t* __restrict__ first_f, uint64_t ncells,
+                    const uint32_t* __restrict__ sidx, const double2* __restrict__ pos,
+                    const double* __restrict__ mass, uint32_t exact_leaf_max, double* __restrict__ sums) {
+    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const uint32_t cnt = cnt_f[c];
+    sums[c] = (double)cnt;
+    if (cnt > exact_leaf_max) return;              // m, mx, my written by heavy_cells_kernel
+    double m = 0.0, sx = 0.0, sy = 0.0;
+    const uint32_t f = cnt ? first_f[c] : 0u;
+    for (uint32_t i = 0; i < cnt; ++i) {
+        const uint32_t b = __ldg(sidx + f + i);
+        const double mb = __ldg(mass + b);
+        const double2 x = __ldg(pos + b);
+        m = __dadd_rn(m, mb);
+        sx = __dadd_rn(sx, __dmul_rn(mb, x.x));
+        sy = __dadd_rn(sy, __dmul_rn(mb, x.y));
+    }
+    sums[ncells + c] = m; sums[2 * ncells + c] = sx; sums[3 * ncells + c] = sy;
 }
 
 // ---- bottom kernel: finest cells + up to five levels above -----------------------------------------
@@ -188,10 +226,12 @@ __device__ __forceinline__ Cell shfl_cell(const Cell& c, int src_lane) {
     return r;
 }
 
+template <bool SHARDED>
 __global__ void __launch_bounds__(kBottomThreads)
 tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, const double2* __restrict__ pos,
                    const double* __restrict__ mass, double G0, double mass_eps, uint32_t exact_leaf_max,
-                   unsigned long long* __restrict__ counters, const StepConsts* __restrict__ consts) {
+                   unsigned long long* __restrict__ counters, const StepConsts* __restrict__ consts,
+                   const double* __restrict__ sums) {
     const int F = d.finest;
     const double scale = consts->scale;
     const double G = G0 * scale * scale;
@@ -206,8 +246,18 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
     // ---- level F: one cell per thread
     uint64_t code = (uint64_t)blockIdx.x * kBottomThreads + tid;
     uint64_t ncells = d.ncells_finest;
-    Cell cur; cur.m = 0.0; cur.cx = 0.0; cur.cy = 0.0; cur.cnt = 0; cur.first = 0;
-    if (code < ncells) {
+    Cell cur; cur.m = 0.0; cur.cx = 0.0; cur.cy = 0.0; cur.cnt = 0; cur.first = kNoFirst;
+    if (SHARDED && code < ncells) {
+        // global sums of all ranks; `first` stays this rank's own run (self_node bookkeeping)
+        const uint32_t lcnt = t.count[offF + code];
+        if (lcnt) cur.first = t.first[offF + code];
+        cur.cnt = (uint32_t)llrint(sums[code]);
+        const double m = sums[ncells + code];
+        cur.m = m;
+        cur.cx = m > 0.0 ? __ddiv_rn(sums[2 * ncells + code], m) : 0.0;
+        cur.cy = m > 0.0 ? __ddiv_rn(sums[3 * ncells + code], m) : 0.0;
+        store_cell(t, offF + code, cur, F, F, G, mass_eps, scale, consts->thr2[F], sidx);
+    } else if (code < ncells) {
         cur.cnt = t.count[offF + code];
         if (cur.cnt) {
             cur.first = t.first[offF + code];
@@ -245,7 +295,7 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
         const uint64_t child_base = d.level_off[level] + 4 * (code >> 2);
         --level; code >>= 2; ncells >>= 2;
         const bool owner = (lane & (4 * stride - 1)) == 0 && code < ncells;
-        Cell up = combine4(ch, sidx, pos, mass, t.self_node, child_base, owner);
+        Cell up = combine4<SHARDED>(ch, sidx, pos, mass, t.self_node, child_base, owner);
         if (owner) {
             store_cell(t, d.level_off[level] + code, up, level, F, G, mass_eps, scale, consts->thr2[level], sidx);
             n_internal += (up.cnt >= 2u);
@@ -269,7 +319,7 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
 #pragma unroll
                 for (int q = 0; q < 4; ++q) ch[q] = src[tid * 4 + q];
                 const bool ok = pcode < npar;
-                Cell up = combine4(ch, sidx, pos, mass, t.self_node, d.level_off[level] + 4 * pcode, ok);
+                Cell up = combine4<SHARDED>(ch, sidx, pos, mass, t.self_node, d.level_off[level] + 4 * pcode, ok);
                 if (ok) {
                     store_cell(t, d.level_off[level - 1] + pcode, up, level - 1, F, G, mass_eps, scale,
                                consts->thr2[level - 1], sidx);
@@ -295,6 +345,7 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
 }
 
 // ---- top kernel: remaining levels (F-6 .. 0), one block, level by level through global memory ----
+template <bool SHARDED>
 __global__ void __launch_bounds__(1024)
 tree_top_kernel(TreeArrays t, Dims d, int top_level, const uint32_t* __restrict__ sidx,
                 const double2* __restrict__ pos, const double* __restrict__ mass, double G0, double mass_eps,
@@ -317,7 +368,7 @@ tree_top_kernel(TreeArrays t, Dims d, int top_level, const uint32_t* __restrict_
                 ch[q].m = t.mass[a]; ch[q].cx = t.comx[a]; ch[q].cy = t.comy[a];
                 ch[q].cnt = t.count[a]; ch[q].first = t.first[a];
             }
-            Cell up = combine4(ch, sidx, pos, mass, t.self_node, offc + 4 * c, true);
+            Cell up = combine4<SHARDED>(ch, sidx, pos, mass, t.self_node, offc + 4 * c, true);
             store_cell(t, off + c, up, level, F, G, mass_eps, scale, consts->thr2[level], sidx);
             n_internal += (up.cnt >= 2u);
         }
@@ -334,31 +385,62 @@ tree_top_kernel(TreeArrays t, Dims d, int top_level, const uint32_t* __restrict_
 
 }  // namespace
 
-void launch_tree(const uint32_t* skeys, const uint32_t* sidx, const double2* pos, const double* mass,
-                 int64_t n, const bh_params& p, const Dims& d, TreeArrays& t, Scratch& s,
-                 const StepConsts* consts, cudaStream_t st) {
+// Phase 1: finest-cell runs (+ heavy cells, + this rank's partial sums when sharded).
+void launch_tree_runs(const uint32_t* skeys, const uint32_t* sidx, const double2* pos, const double* mass,
+                      int64_t n, const bh_params& p, const Dims& d, TreeArrays& t, Scratch& s, double* sums,
+                      cudaStream_t st) {
     const int F = d.finest;
     uint32_t* cnt_f = t.count + d.level_off[F];
     uint32_t* first_f = t.first + d.level_off[F];
+    const uint64_t nc = d.ncells_finest;
     uint32_t exact_max = (uint32_t)(p.exact_leaf_max < 0 ? 0 : p.exact_leaf_max);
-    cell_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(skeys, n, cnt_f, first_f, exact_max, s.heavy_list,
-                                                                  s.heavy_count);
-    ++g_launches;
-    heavy_cells_kernel<<<148 * 4, 256, 0, st>>>(s.heavy_list, s.heavy_count, cnt_f, first_f, sidx, pos, mass,
-                                                t.mass + d.level_off[F], t.comx + d.level_off[F],
-                                                t.comy + d.level_off[F]);
-    ++g_launches;
+    if (n > 0) {
+        cell_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(skeys, n, cnt_f, first_f, exact_max, s.heavy_list,
+                                                                      s.heavy_count);
+        ++g_launches;
+    }
+    if (sums) {
+        heavy_cells_kernel<<<148 * 4, 256, 0, st>>>(s.heavy_list, s.heavy_count, cnt_f, first_f, sidx, pos, mass,
+                                                    sums + nc, sums + 2 * nc, sums + 3 * nc, true);
+        ++g_launches;
+        cell_partial_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(cnt_f, first_f, nc, sidx, pos, mass, exact_max,
+                                                                          sums);
+        ++g_launches;
+    } else {
+        heavy_cells_kernel<<<148 * 4, 256, 0, st>>>(s.heavy_list, s.heavy_count, cnt_f, first_f, sidx, pos, mass,
+                                                    t.mass + d.level_off[F], t.comx + d.level_off[F],
+                                                    t.comy + d.level_off[F], false);
+        ++g_launches;
+    }
+}
+
+// Phase 2: all levels bottom-up.  `sums` (sharded build) = all-reduced per-cell sums.
+void launch_tree_levels(const uint32_t* sidx, const double2* pos, const double* mass, const bh_params& p,
+                        const Dims& d, TreeArrays& t, Scratch& s, const StepConsts* consts, const double* sums,
+                        cudaStream_t st) {
+    const int F = d.finest;
+    uint32_t exact_max = (uint32_t)(p.exact_leaf_max < 0 ? 0 : p.exact_leaf_max);
     unsigned blocks = (unsigned)((d.ncells_finest + kBottomThreads - 1) / kBottomThreads);
-    tree_bottom_kernel<<<blocks, kBottomThreads, 0, st>>>(t, d, sidx, pos, mass, p.G, p.mass_eps, exact_max,
-                                                          s.counters, consts);
+    if (sums) tree_bottom_kernel<true><<<blocks, kBottomThreads, 0, st>>>(t, d, sidx, pos, mass, p.G, p.mass_eps, exact_max,
+                                                                        s.counters, consts, sums);
+    else tree_bottom_kernel<false><<<blocks, kBottomThreads, 0, st>>>(t, d, sidx, pos, mass, p.G, p.mass_eps, exact_max,
+                                                                    s.counters, consts, nullptr);
     ++g_launches;
     int top_level = F - 5;   // bottom kernel covered F .. F-4
     if (F >= 1) {
         if (top_level < 0) top_level = -1;
         // when the bottom kernel already reached the root (F <= 4) only the node count remains
-        tree_top_kernel<<<1, 1024, 0, st>>>(t, d, top_level, sidx, pos, mass, p.G, p.mass_eps, s.counters, consts);
+        if (sums) tree_top_kernel<true><<<1, 1024, 0, st>>>(t, d, top_level, sidx, pos, mass, p.G, p.mass_eps, s.counters, consts);
+        else tree_top_kernel<false><<<1, 1024, 0, st>>>(t, d, top_level, sidx, pos, mass, p.G, p.mass_eps, s.counters, consts);
         ++g_launches;
     }
+}
+
+void launch_tree(const uint32_t* skeys, const uint32_t* sidx, const double2* pos, const double* mass,
+                 int64_t n, const bh_params& p, const Dims& d, TreeArrays& t, Scratch& s,
+                 const StepConsts* consts, cudaStream_t st) {
+    launch_tree_runs(skeys, sidx, pos, mass, n, p, d, t, s, nullptr, st);
+    launch_tree_levels(sidx, pos, mass, p, d, t, s, consts, nullptr, st);
 }
 
 }  // namespace bh

@@ -1,7 +1,8 @@
 """Multi-GPU parity check, one rank per GPU (launch with torch.distributed.run).
 
-Every rank holds all bodies, owns a contiguous (Morton-renumbered) index slice, rebuilds the whole
-tree, evaluates + integrates only its slice and all-gathers positions over NCCL every step.
+Every rank owns a contiguous index slice: it keys, sorts and sums only its own bodies, two NCCL
+all-reduces (bounding box, per-cell sums) make the tree global, and it evaluates + integrates only
+its slice.  No body data is exchanged during a step; getters gather on demand.
 Rank 0 compares the result with a single-GPU context on the same bodies and with the CPU oracle.
 """
 import argparse
@@ -49,9 +50,10 @@ if rank == 0:
 
     def rel(x, y):
         return float(np.sqrt(((x - y) ** 2).sum() / (y ** 2).sum()))
-    # the Morton renumbering changes the summation order inside cap-level cells from step 1 on (ulp-level
-    # COM differences, amplified by near-COM interactions), so FP64 is compared at 1e-10, not bit for bit
-    tol = 1e-10 if a.fp64 else 1e-6
+    # the sharded build sums every finest cell's bodies rank by rank and all-reduces (instead of the
+    # reference's sequential running average): node COMs differ by ~1e-16 relative, which the
+    # self-inclusive near-COM interactions amplify to ~1e-9 of the force
+    tol = 1e-8 if a.fp64 else 1e-6
     errs = {"pos": rel(p_multi, p_one), "vel": rel(v_multi, v_one), "force": rel(f_multi, f_one)}
     print(f"world={world} n={a.n} steps={a.steps} fp64={a.fp64} multi-vs-single rel-RMS {errs} (tol {tol})", flush=True)
     ok = all(e <= tol for e in errs.values())
@@ -64,7 +66,7 @@ if rank == 0:
             p, v = r["pos"], r["vel"]
         e = rel(p_multi, p)
         print(f"multi-GPU vs CPU oracle after {a.steps} steps: position rel-RMS {e:.3e}", flush=True)
-        ok = ok and e <= (1e-10 if a.fp64 else 1e-5)
+        ok = ok and e <= (1e-8 if a.fp64 else 1e-5)
     print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL", flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, 0)
