@@ -29,6 +29,7 @@ LIB_PATH = os.path.join(_HERE, "libbh.so")
 BH_FLAG_FP64_TRAVERSAL = 1 << 0
 BH_FLAG_COUNTERS = 1 << 1
 BH_FLAG_NO_GRAPH = 1 << 2
+BH_FLAG_EXACT_EPS = 1 << 3
 
 # every symbol include/bh.h declares (checked by tests/test_abi.py against the header text)
 ABI_SYMBOLS = (
@@ -195,7 +196,8 @@ def _f64(a, shape):
 class Simulation:
     """Host-side mirror of ``runSimulationGpu`` (project.cu:918-1024) over the C-ABI."""
 
-    def __init__(self, n_bodies: int, fp64: bool = False, counters: bool = False, graph: bool = True, **over):
+    def __init__(self, n_bodies: int, fp64: bool = False, counters: bool = False, graph: bool = True,
+                 exact_eps: bool = False, **over):
         flags = int(over.pop("flags", 0))
         if fp64:
             flags |= BH_FLAG_FP64_TRAVERSAL
@@ -203,6 +205,8 @@ class Simulation:
             flags |= BH_FLAG_COUNTERS
         if not graph:
             flags |= BH_FLAG_NO_GRAPH
+        if exact_eps:
+            flags |= BH_FLAG_EXACT_EPS
         bpl = int(over.pop("bodies_per_lane", 0))
         self.params = default_params(n_bodies=n_bodies, flags=flags, **over)
         self.params.reserved[0] = bpl      # traversal tuning knob (include/bh.h)

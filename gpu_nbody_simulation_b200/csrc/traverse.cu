@@ -67,6 +67,11 @@ __device__ __forceinline__ float approx_sqrt(float x) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float approx_rsqrt(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float approx_rcp(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -93,6 +98,10 @@ __device__ __forceinline__ void finish_body(const TravArgs& a, uint32_t body, do
 // ------------------------------------------------------------------------------------------------
 // FP32 traversal, BPL bodies per lane
 // ------------------------------------------------------------------------------------------------
+#ifndef BH_PAIR_MIN_BLOCKS
+#define BH_PAIR_MIN_BLOCKS 5
+#endif
+constexpr int kPairMinBlocks = BH_PAIR_MIN_BLOCKS;
 constexpr float kFarLane = -1.152921504606847e18f;   // -2^60: where bodies outside a cell's mask "stand"
 
 template <int BPL> struct StackEntry;
@@ -270,6 +279,134 @@ traverse_f32_kernel(const __grid_constant__ TravArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// FP32 traversal, two bodies per lane with the FP32x2 instructions packed ACROSS the two bodies:
+// every arithmetic step of the evaluation (displacement, d2, d2 (d + eps), G M / w, accumulation)
+// is one packed instruction for both bodies; only the two MUFU pairs and the predicate tails are
+// per body.  Same semantics as traverse_f32_kernel<2, ...>; this is the production variant.
+// ------------------------------------------------------------------------------------------------
+// EXACT_EPS = false (default): 1 / (d + eps) is taken to first order in eps / d, one MUFU.RSQ per body
+// (the SFU pipe, 16 lanes/clk/SM on B200, is this kernel's scarcest resource: ncu math_pipe_throttle);
+// relative error (eps/d)^2, i.e. < 1e-6 for separations above 1e-12 (eps = 1e-15).
+// EXACT_EPS = true (BH_FLAG_EXACT_EPS): MUFU.SQRT + MUFU.RCP, exact for any separation.
+template <bool INTEGRATE, bool EXACT_EPS>
+__global__ void __launch_bounds__(kTravThreads, kPairMinBlocks)
+traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
+    using SE = StackEntry<2>;
+    __shared__ __align__(16) uint8_t s_stack[kTravWarps][kStackCap * SE::kBytes];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warp_slot0 = ((int64_t)blockIdx.x * kTravWarps + warp) * 64;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&s_stack[warp][0]);
+
+    uint32_t body[2], selfn[2];
+    float2 nxh, nyh, nxl, nyl;   // minus the scaled positions of body 0 (.x) and body 1 (.y), hi / lo floats
+    float2 accx = make_float2(0.f, 0.f), accy = make_float2(0.f, 0.f);
+    const float feps = a.consts->feps;
+    {
+        const double scale = a.consts->scale;
+        float t[2][4];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int64_t slot = warp_slot0 + b * 32 + lane;
+            body[b] = 0xffffffffu; selfn[b] = 0xffffffffu;
+            double px = 0.0, py = 0.0;
+            if (slot < a.n_slots) {
+                uint32_t sp = a.own_list ? a.own_list[slot] : (uint32_t)slot;
+                body[b] = a.sidx[sp];
+                selfn[b] = a.self_node[body[b]];
+                double2 p = a.pos[body[b]];
+                px = p.x; py = p.y;
+            }
+            const double sx = px * scale, sy = py * scale;
+            const float xh = (float)sx, yh = (float)sy;
+            t[b][0] = -xh; t[b][1] = -yh;
+            t[b][2] = -(float)(sx - (double)xh); t[b][3] = -(float)(sy - (double)yh);
+        }
+        nxh = make_float2(t[0][0], t[1][0]); nyh = make_float2(t[0][1], t[1][1]);
+        nxl = make_float2(t[0][2], t[1][2]); nyl = make_float2(t[0][3], t[1][3]);
+    }
+    const float2 eps2 = make_float2(feps, feps), neg_eps2 = make_float2(-feps, -feps);
+    (void)eps2; (void)neg_eps2;
+
+    // Evaluate one node for both bodies of this lane; returns the two ballots of "opens".
+    auto eval = [&](const float4 A, const float2 B, uint32_t idx, const float2 mxh, const float2 myh, uint32_t& m0,
+                    uint32_t& m1) {
+        const float2 dx = __fadd2_rn(__fadd2_rn(make_float2(A.x, A.x), mxh), __fadd2_rn(make_float2(A.z, A.z), nxl));
+        const float2 dy = __fadd2_rn(__fadd2_rn(make_float2(A.y, A.y), myh), __fadd2_rn(make_float2(A.w, A.w), nyl));
+        const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+        // G M / (d2 (d + eps)), project.cu:765-769; d2 == 0 -> inf, times dx == 0 -> NaN like the reference
+        float2 g;
+        if constexpr (EXACT_EPS) {
+            const float2 w = __fmul2_rn(d2, __fadd2_rn(make_float2(approx_sqrt(d2.x), approx_sqrt(d2.y)), eps2));
+            g = __fmul2_rn(make_float2(B.x, B.x), make_float2(approx_rcp(w.x), approx_rcp(w.y)));
+        } else {
+            const float2 inv = make_float2(approx_rsqrt(d2.x), approx_rsqrt(d2.y));
+            const float2 t = __fmul2_rn(inv, inv);                       // 1 / d2
+            const float2 u = __ffma2_rn(neg_eps2, t, inv);               // 1 / (d + eps) ~= 1/d - eps/d2
+            g = __fmul2_rn(make_float2(B.x, B.x), __fmul2_rn(t, u));
+        }
+        float2 f;
+        // per body: accept = !(d2 <= thr); use = accept && not the body's own leaf; f = use ? g : 0; ballot(!accept)
+        asm volatile("{\n .reg .pred pa, pu;\n setp.gtu.f32 pa, %2, %3;\n setp.ne.and.u32 pu, %4, %5, pa;\n"
+                     " selp.f32 %0, %6, 0f00000000, pu;\n vote.sync.ballot.b32 %1, !pa, 0xffffffff;\n}"
+                     : "=f"(f.x), "=r"(m0) : "f"(d2.x), "f"(B.y), "r"(selfn[0]), "r"(idx), "f"(g.x));
+        asm volatile("{\n .reg .pred pa, pu;\n setp.gtu.f32 pa, %2, %3;\n setp.ne.and.u32 pu, %4, %5, pa;\n"
+                     " selp.f32 %0, %6, 0f00000000, pu;\n vote.sync.ballot.b32 %1, !pa, 0xffffffff;\n}"
+                     : "=f"(f.y), "=r"(m1) : "f"(d2.y), "f"(B.y), "r"(selfn[1]), "r"(idx), "f"(g.y));
+        accx = __ffma2_rn(f, dx, accx);
+        accy = __ffma2_rn(f, dy, accy);
+    };
+
+    // Depth-first walk over a warp-shared stack.  (Keeping the first opened child in registers and
+    // prefetching its children was tried — profiles/r01_traverse_v7_pair_ncu_summary.txt — and lost:
+    // +28 % instructions for the bookkeeping, no latency gain.)
+    uint32_t sp = sbase;              // shared-memory address of the next free stack slot
+    {   // the root (project.cu:711-715 pushes node 0)
+        const float4 A = __ldg(reinterpret_cast<const float4*>(a.rec));
+        const float2 B = __ldg(reinterpret_cast<const float2*>(a.rec) + 2);
+        const bool l0 = body[0] != 0xffffffffu, l1 = body[1] != 0xffffffffu;
+        const float2 mxh = make_float2(l0 ? nxh.x : kFarLane, l1 ? nxh.y : kFarLane);
+        const float2 myh = make_float2(l0 ? nyh.x : kFarLane, l1 ? nyh.y : kFarLane);
+        uint32_t m[2];
+        eval(A, B, 0u, mxh, myh, m[0], m[1]);
+        const bool push = (m[0] | m[1]) != 0u;
+        SE::store_if(push & (lane == 0), sp, 0u, m);
+        sp += push ? SE::kBytes : 0u;
+    }
+    while (sp != sbase) {
+        sp -= SE::kBytes;
+        uint32_t node, pm[2];
+        __syncwarp();             // lane 0's stores of earlier steps are visible to the whole warp
+        SE::load(sp, node, pm);
+        __syncwarp();             // nobody overwrites the slot before everybody has read it
+        const uint32_t base = 4u * node + 1u;
+        const NodeRec* __restrict__ rp = a.rec + base;
+        const bool a0 = (pm[0] >> lane) & 1u, a1 = (pm[1] >> lane) & 1u;
+        const float2 mxh = make_float2(a0 ? nxh.x : kFarLane, a1 ? nxh.y : kFarLane);
+        const float2 myh = make_float2(a0 ? nyh.x : kFarLane, a1 ? nyh.y : kFarLane);
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) {
+            const float4 A = __ldg(reinterpret_cast<const float4*>(rp + q));        // chx chy clx cly
+            const float2 B = __ldg(reinterpret_cast<const float2*>(rp + q) + 2);    // gm thr
+            uint32_t m[2];
+            eval(A, B, base + q, mxh, myh, m[0], m[1]);
+            // branch-free push: one straight-line block per step keeps four independent chains in flight
+            const bool push = (m[0] | m[1]) != 0u;
+            SE::store_if(push & (lane == 0), sp, base + q, m);
+            sp += push ? SE::kBytes : 0u;
+        }
+    }
+    const float ax[2] = {accx.x, accx.y}, ay[2] = {accy.x, accy.y};
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        if (body[b] != 0xffffffffu) {
+            const double2 p = a.pos[body[b]];
+            const double mi = a.mass[body[b]];
+            finish_body<INTEGRATE>(a, body[b], p.x, p.y, mi, mi * (double)ax[b], mi * (double)ay[b]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP64 verification traversal: the reference's expressions, one body per lane
 // ------------------------------------------------------------------------------------------------
 template <bool INTEGRATE, bool COUNT>
@@ -420,7 +557,7 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, double2* pos, 
     const bool fp64 = p.flags & BH_FLAG_FP64_TRAVERSAL, count = p.flags & BH_FLAG_COUNTERS;
     // two bodies per lane halve the node traffic and the control overhead per body, but need >= ~400k
     // bodies to keep every SM's warp slots full (ncu: profiles/r01_traverse_v4_*)
-    const int bpl = (p.reserved[0] == 1 || p.reserved[0] == 2) ? p.reserved[0] : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
+    const int bpl = (p.reserved[0] == 1) ? 1 : (p.reserved[0] == 2 || p.reserved[0] == 3) ? 2 : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
     if (fp64) {
         unsigned blocks = (unsigned)((own_n + kTravThreads - 1) / kTravThreads);
         if (integrate) { if (count) traverse_f64_kernel<true, true><<<blocks, kTravThreads, 0, st>>>(a);
@@ -431,7 +568,13 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, double2* pos, 
         const int64_t per_block = (int64_t)kTravThreads * bpl;
         unsigned blocks = (unsigned)((own_n + per_block - 1) / per_block);
 #define BH_TRAV(B, I, C) traverse_f32_kernel<B, I, C><<<blocks, kTravThreads, 0, st>>>(a)
-        if (bpl == 2) {
+        if (bpl == 2 && !count && p.reserved[0] != 3) {
+            const bool exact = p.flags & BH_FLAG_EXACT_EPS;
+            if (integrate) { if (exact) traverse_f32_pair_kernel<true, true><<<blocks, kTravThreads, 0, st>>>(a);
+                             else traverse_f32_pair_kernel<true, false><<<blocks, kTravThreads, 0, st>>>(a); }
+            else { if (exact) traverse_f32_pair_kernel<false, true><<<blocks, kTravThreads, 0, st>>>(a);
+                   else traverse_f32_pair_kernel<false, false><<<blocks, kTravThreads, 0, st>>>(a); }
+        } else if (bpl == 2) {
             if (integrate) { if (count) BH_TRAV(2, true, true); else BH_TRAV(2, true, false); }
             else { if (count) BH_TRAV(2, false, true); else BH_TRAV(2, false, false); }
         } else {
