@@ -24,7 +24,7 @@ import numpy as np
 from . import initial_conditions  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbh.so")
+LIB_PATH = os.environ.get("BH_LIB", os.path.join(_HERE, "libbh.so"))   # BH_LIB: A/B builds of the same ABI
 
 BH_FLAG_FP64_TRAVERSAL = 1 << 0
 BH_FLAG_COUNTERS = 1 << 1

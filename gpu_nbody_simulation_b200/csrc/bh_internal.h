@@ -15,7 +15,7 @@ constexpr int kSortItems = 16;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per tile
 constexpr int kMaxSortPasses = 4;
 constexpr int kMaxBins = 512;
-constexpr int64_t kTwoBodiesPerLaneMin = 400000;   // traversal: 2 bodies per lane from this many bodies on (bh_params.reserved[0] overrides)
+constexpr int64_t kTwoBodiesPerLaneMin = 500000;   // traversal: 2 bodies per lane from this many bodies on (bh_params.reserved[0] overrides)
 
 // node flags (packed FP32 traversal record and FP64 verification path share them)
 constexpr uint32_t kNodeNonZero = 1u;  // mass > mass_eps         (project.cu:617 / :731)

@@ -38,7 +38,10 @@ namespace bh {
 
 namespace {
 
-constexpr int kTravThreads = 256;
+#ifndef BH_TRAV_THREADS
+#define BH_TRAV_THREADS 128   // A/B on B200 at N=1M (pair kernel): 256 thr/48 regs 463 us, 256/67 412 us, 128/67 404 us
+#endif
+constexpr int kTravThreads = BH_TRAV_THREADS;
 constexpr int kTravWarps = kTravThreads / 32;
 constexpr int kStackCap = 3 * kMaxDepthDense + 8;
 
@@ -99,7 +102,7 @@ __device__ __forceinline__ void finish_body(const TravArgs& a, uint32_t body, do
 // FP32 traversal, BPL bodies per lane
 // ------------------------------------------------------------------------------------------------
 #ifndef BH_PAIR_MIN_BLOCKS
-#define BH_PAIR_MIN_BLOCKS 5
+#define BH_PAIR_MIN_BLOCKS 3   // per 256 threads: leaves the register allocator free (67 regs); 5 (48 regs) is 13 % slower
 #endif
 constexpr int kPairMinBlocks = BH_PAIR_MIN_BLOCKS;
 constexpr float kFarLane = -1.152921504606847e18f;   // -2^60: where bodies outside a cell's mask "stand"
@@ -133,8 +136,11 @@ template <> struct StackEntry<2> {
     }
 };
 
+#ifndef BH_GENERIC_MIN_BLOCKS
+#define BH_GENERIC_MIN_BLOCKS 4   // 48 registers; 8 (32 regs) is 25 % slower at N = 40k
+#endif
 template <int BPL, bool INTEGRATE, bool COUNT>
-__global__ void __launch_bounds__(kTravThreads, BPL == 1 ? 8 : 5)
+__global__ void __launch_bounds__(kTravThreads, (BPL == 1 ? BH_GENERIC_MIN_BLOCKS : 4) * (256 / kTravThreads))
 traverse_f32_kernel(const __grid_constant__ TravArgs a) {
     using SE = StackEntry<BPL>;
     __shared__ __align__(16) uint8_t s_stack[kTravWarps][kStackCap * SE::kBytes];
@@ -289,7 +295,7 @@ traverse_f32_kernel(const __grid_constant__ TravArgs a) {
 // relative error (eps/d)^2, i.e. < 1e-6 for separations above 1e-12 (eps = 1e-15).
 // EXACT_EPS = true (BH_FLAG_EXACT_EPS): MUFU.SQRT + MUFU.RCP, exact for any separation.
 template <bool INTEGRATE, bool EXACT_EPS>
-__global__ void __launch_bounds__(kTravThreads, kPairMinBlocks)
+__global__ void __launch_bounds__(kTravThreads, kPairMinBlocks * (256 / kTravThreads))
 traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
     using SE = StackEntry<2>;
     __shared__ __align__(16) uint8_t s_stack[kTravWarps][kStackCap * SE::kBytes];
