@@ -37,7 +37,7 @@ if ROOT not in sys.path:
 BODIES_PER_GPU = 1_000_000
 SEED = 12345
 FLOP_PER_INTERACTION = 20.0
-TRAVERSE_DRAM_BYTES_NCU = 74_530_304 + 36_734_976   # profiles/r01_traverse_v4_bpl2_ncu_summary.txt
+TRAVERSE_DRAM_BYTES_NCU = 74_801_152 + 37_312_768   # profiles/r01_traverse_v8_pair_ncu_summary.txt
 METRIC = "body_steps_per_s"
 UNIT = "body·steps/s"
 
@@ -256,7 +256,7 @@ def run_ours(args):
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                     "traffic": TRAVERSE_DRAM_BYTES_NCU,
                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full "
-                                      "capture at N=1M (profiles/r01_traverse_v4_bpl2_ncu_summary.txt); algorithmic "
+                                      "capture at N=1M (profiles/r01_traverse_v8_pair_ncu_summary.txt); algorithmic "
                                       "bytes = 72 B/body state + 11 MB tree = 83 MB",
                     "peak_source": f"measured here: FFMA loop, {peak_tf:.1f} TFLOP/s (implies {mhz:.0f} MHz at 128 FMA/clk/SM); "
                                    "FP32 peak is not in MEASURED_PEAKS.json (SURVEY 8d)",

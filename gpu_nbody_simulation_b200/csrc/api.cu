@@ -207,6 +207,7 @@ void zero_scratch(bh_ctx* c) {
     cudaMemsetAsync(c->s.zero_base, 0, c->s.zero_bytes, c->stream);
     cudaMemsetAsync(c->tree.count + c->d.level_off[c->d.finest], 0, c->d.ncells_finest * sizeof(uint32_t), c->stream);
     cudaMemsetAsync(c->tree.self_node, 0xff, c->d.n * sizeof(uint32_t), c->stream);
+    cudaMemsetAsync(c->s.huge_tickets, 0, (c->s.max_huge + 1) * sizeof(uint32_t), c->stream);
 }
 
 void prof_mark(bh_ctx* c, int i) { if (c->profiling) cudaEventRecord(c->pev[i], c->stream); }
@@ -435,6 +436,11 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     c->bounds_grid = (int)std::max<int64_t>(1, std::min<int64_t>(bg, prop.multiProcessorCount * 4));
     BH_ALLOC(c->s.bbox_partial, (size_t)c->bounds_grid * 4);
     BH_ALLOC(c->s.heavy_list, c->d.ncells_finest);
+    c->s.max_huge = n / kHugeCellMin + 1;
+    BH_ALLOC(c->s.huge_list, c->s.max_huge);
+    BH_ALLOC(c->s.huge_tickets, c->s.max_huge + 1);   // [max_huge] = huge_count
+    c->s.huge_count = c->s.huge_tickets + c->s.max_huge;
+    BH_ALLOC(c->s.huge_partial, (size_t)c->s.max_huge * kHugeParts * 3);
     if (p->n_ranks > 1) {
         BH_ALLOC(c->cell_sums, 4 * c->d.ncells_finest); BH_ALLOC(c->bbox_raw, 4);
     }
@@ -463,7 +469,7 @@ int bh_destroy(bh_ctx* c) {
     if (c->comm) { NcclApi* api = nccl_api(); if (api) api->CommDestroy(c->comm); }
     void* ptrs[] = {c->pos, c->vel, c->acc, c->force, c->snap_pos, c->snap_vel, c->tmp2, c->mass, c->tmp1, c->keys[0],
                     c->keys[1], c->idx[0], c->idx[1], c->consts, c->tree.mass, c->tree.comx, c->tree.comy,
-                    c->tree.count, c->tree.first, c->tree.flags, c->rec_alloc, c->tree.self_node, c->s.zero_base, c->s.bbox_partial, c->s.heavy_list,
+                    c->tree.count, c->tree.first, c->tree.flags, c->rec_alloc, c->tree.self_node, c->s.zero_base, c->s.bbox_partial, c->s.heavy_list, c->s.huge_list, c->s.huge_tickets, c->s.huge_partial,
                     c->packed, c->own_list, c->own_count, c->perm, c->cell_sums, c->bbox_raw};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);

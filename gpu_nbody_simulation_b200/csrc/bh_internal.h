@@ -15,6 +15,8 @@ constexpr int kSortItems = 16;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per tile
 constexpr int kMaxSortPasses = 4;
 constexpr int kMaxBins = 512;
+constexpr uint32_t kHugeCellMin = 8192;    // finest cells above this many bodies are summed by kHugeParts blocks
+constexpr int kHugeParts = 64;
 constexpr int64_t kTwoBodiesPerLaneMin = 500000;   // traversal: 2 bodies per lane from this many bodies on (bh_params.reserved[0] overrides)
 
 // node flags (packed FP32 traversal record and FP64 verification path share them)
@@ -74,6 +76,11 @@ struct Scratch {
     // not zeroed:
     double* bbox_partial;     // [grid][4]
     uint32_t* heavy_list;     // finest cell ids
+    uint32_t* huge_list;      // heavy cells with more than kHugeCellMin bodies (summed by many blocks)
+    uint32_t* huge_count;     // 1 (zeroed)
+    uint32_t* huge_tickets;   // per huge cell (zeroed)
+    double* huge_partial;     // [huge cells][kHugeParts][3]
+    int64_t max_huge;
 };
 
 struct SortPlan {

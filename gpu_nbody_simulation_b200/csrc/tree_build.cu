@@ -145,40 +145,101 @@ cell_runs_kernel(const uint32_t* __restrict__ skeys, int64_t n, uint32_t* __rest
 }
 
 // ---- parallel (non-sequential) summation for very full finest cells -------------------------------
-// One block per queued cell; fixed reduction shape => deterministic and identical on all ranks.
+// heavy_cells_kernel: one block per queued cell (fixed reduction shape => deterministic, identical
+// on all ranks); cells above kHugeCellMin bodies (the collapsed regime of the reference's own
+// dynamics: almost all bodies in a handful of cells) are re-queued for huge_cells_kernel, where
+// kHugeParts blocks sum fixed, contiguous parts of the run and the last block to finish combines
+// the parts in part order (atomic ticket) — still a fixed summation order.
+__device__ __forceinline__ void block_sum3(double& m, double& sx, double& sy, double (*sm)[256]) {
+    sm[0][threadIdx.x] = m; sm[1][threadIdx.x] = sx; sm[2][threadIdx.x] = sy;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            sm[0][threadIdx.x] += sm[0][threadIdx.x + o];
+            sm[1][threadIdx.x] += sm[1][threadIdx.x + o];
+            sm[2][threadIdx.x] += sm[2][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    m = sm[0][0]; sx = sm[1][0]; sy = sm[2][0];
+    __syncthreads();
+}
+
+__device__ __forceinline__ void write_cell_sums(double* m_f, double* cx_f, double* cy_f, uint32_t cell, double tm,
+                                                double sx, double sy, bool raw_sums) {
+    m_f[cell] = tm;
+    if (raw_sums) { cx_f[cell] = sx; cy_f[cell] = sy; }   // sharded: divided after the all-reduce
+    else { cx_f[cell] = tm > 0.0 ? sx / tm : 0.0; cy_f[cell] = tm > 0.0 ? sy / tm : 0.0; }
+}
+
 __global__ void __launch_bounds__(256)
 heavy_cells_kernel(const uint32_t* __restrict__ heavy_list, const uint32_t* __restrict__ heavy_count,
                    const uint32_t* __restrict__ cnt_f, const uint32_t* __restrict__ first_f,
                    const uint32_t* __restrict__ sidx, const double2* __restrict__ pos,
                    const double* __restrict__ mass, double* __restrict__ m_f, double* __restrict__ cx_f,
-                   double* __restrict__ cy_f, bool raw_sums) {
+                   double* __restrict__ cy_f, bool raw_sums, uint32_t* __restrict__ huge_list,
+                   uint32_t* __restrict__ huge_count) {
     __shared__ double sm[3][256];
     const uint32_t nheavy = *heavy_count;
     for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
-        uint32_t cell = heavy_list[h];
-        uint32_t c = cnt_f[cell], f = first_f[cell];
+        const uint32_t cell = heavy_list[h];
+        const uint32_t c = cnt_f[cell], f = first_f[cell];
+        if (c > kHugeCellMin) {                      // block-uniform
+            if (threadIdx.x == 0) huge_list[atomicAdd(huge_count, 1u)] = cell;
+            continue;
+        }
         double m = 0.0, sx = 0.0, sy = 0.0;
         for (uint32_t i = threadIdx.x; i < c; i += 256) {
-            uint32_t b = sidx[f + i];
-            double mb = mass[b];
-            double2 x = pos[b];
+            const uint32_t b = sidx[f + i];
+            const double mb = mass[b];
+            const double2 x = pos[b];
             m += mb; sx += mb * x.x; sy += mb * x.y;
         }
-        sm[0][threadIdx.x] = m; sm[1][threadIdx.x] = sx; sm[2][threadIdx.x] = sy;
-        __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) {
-            if ((int)threadIdx.x < o) {
-                sm[0][threadIdx.x] += sm[0][threadIdx.x + o];
-                sm[1][threadIdx.x] += sm[1][threadIdx.x + o];
-                sm[2][threadIdx.x] += sm[2][threadIdx.x + o];
-            }
-            __syncthreads();
+        block_sum3(m, sx, sy, sm);
+        if (threadIdx.x == 0) write_cell_sums(m_f, cx_f, cy_f, cell, m, sx, sy, raw_sums);
+    }
+}
+
+// grid = (kHugeParts, slots): block (p, s) sums part p of huge cell s, s + slots, ...
+__global__ void __launch_bounds__(256)
+huge_cells_kernel(const uint32_t* __restrict__ huge_list, const uint32_t* __restrict__ huge_count,
+                  const uint32_t* __restrict__ cnt_f, const uint32_t* __restrict__ first_f,
+                  const uint32_t* __restrict__ sidx, const double2* __restrict__ pos,
+                  const double* __restrict__ mass, double* __restrict__ m_f, double* __restrict__ cx_f,
+                  double* __restrict__ cy_f, bool raw_sums, double* __restrict__ partial,
+                  uint32_t* __restrict__ tickets) {
+    __shared__ double sm[3][256];
+    __shared__ bool last;
+    const uint32_t nhuge = *huge_count;
+    const uint32_t p = blockIdx.x;
+    for (uint32_t h = blockIdx.y; h < nhuge; h += gridDim.y) {
+        const uint32_t cell = huge_list[h];
+        const uint32_t c = cnt_f[cell], f = first_f[cell];
+        const uint32_t per = (c + kHugeParts - 1) / kHugeParts;
+        const uint32_t lo = p * per, hi = min(c, lo + per);
+        double m = 0.0, sx = 0.0, sy = 0.0;
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += 256) {
+            const uint32_t b = sidx[f + i];
+            const double mb = mass[b];
+            const double2 x = pos[b];
+            m += mb; sx += mb * x.x; sy += mb * x.y;
         }
+        block_sum3(m, sx, sy, sm);
         if (threadIdx.x == 0) {
-            double tm = sm[0][0];
-            m_f[cell] = tm;
-            if (raw_sums) { cx_f[cell] = sm[1][0]; cy_f[cell] = sm[2][0]; }   // sharded: divided after the all-reduce
-            else { cx_f[cell] = tm > 0.0 ? sm[1][0] / tm : 0.0; cy_f[cell] = tm > 0.0 ? sm[2][0] / tm : 0.0; }
+            double* out = partial + ((size_t)h * kHugeParts + p) * 3;
+            out[0] = m; out[1] = sx; out[2] = sy;
+            __threadfence();
+            last = (atomicAdd(&tickets[h], 1u) == kHugeParts - 1);
+        }
+        __syncthreads();
+        if (last && threadIdx.x == 0) {
+            __threadfence();
+            double tm = 0.0, tx = 0.0, ty = 0.0;
+            for (int q = 0; q < kHugeParts; ++q) {   // fixed order
+                const volatile double* in = partial + ((size_t)h * kHugeParts + q) * 3;
+                tm += in[0]; tx += in[1]; ty += in[2];
+            }
+            write_cell_sums(m_f, cx_f, cy_f, cell, tm, tx, ty, raw_sums);
         }
         __syncthreads();
     }
@@ -401,16 +462,23 @@ void launch_tree_runs(const uint32_t* skeys, const uint32_t* sidx, const double2
     }
     if (sums) {
         heavy_cells_kernel<<<148 * 4, 256, 0, st>>>(s.heavy_list, s.heavy_count, cnt_f, first_f, sidx, pos, mass,
-                                                    sums + nc, sums + 2 * nc, sums + 3 * nc, true);
-        ++g_launches;
+                                                    sums + nc, sums + 2 * nc, sums + 3 * nc, true, s.huge_list, s.huge_count);
+        huge_cells_kernel<<<dim3(kHugeParts, 16), 256, 0, st>>>(s.huge_list, s.huge_count, cnt_f, first_f, sidx, pos, mass,
+                                                                sums + nc, sums + 2 * nc, sums + 3 * nc, true,
+                                                                s.huge_partial, s.huge_tickets);
+        g_launches += 2;
         cell_partial_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(cnt_f, first_f, nc, sidx, pos, mass, exact_max,
                                                                           sums);
         ++g_launches;
     } else {
         heavy_cells_kernel<<<148 * 4, 256, 0, st>>>(s.heavy_list, s.heavy_count, cnt_f, first_f, sidx, pos, mass,
                                                     t.mass + d.level_off[F], t.comx + d.level_off[F],
-                                                    t.comy + d.level_off[F], false);
-        ++g_launches;
+                                                    t.comy + d.level_off[F], false, s.huge_list, s.huge_count);
+        huge_cells_kernel<<<dim3(kHugeParts, 16), 256, 0, st>>>(s.huge_list, s.huge_count, cnt_f, first_f, sidx, pos, mass,
+                                                                t.mass + d.level_off[F], t.comx + d.level_off[F],
+                                                                t.comy + d.level_off[F], false, s.huge_partial,
+                                                                s.huge_tickets);
+        g_launches += 2;
     }
 }
 
