@@ -159,7 +159,8 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    n = BODIES_PER_GPU * world
+    strong = args.total_bodies > 0
+    n = args.total_bodies if strong else BODIES_PER_GPU * world
     pos, vel, mass = make_workload(n)
     K, W = args.steps, args.warmup
 
@@ -299,9 +300,10 @@ def run_ours(args):
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+                "vs_baseline": None,
                 "dtype": "f32 (double-float displacement; FP64 state, tree and integrator)", "data": "synthetic",
-                "config": {"workload": f"uniform disk N={n} ({BODIES_PER_GPU} per GPU), R=0.1, seed {SEED}, theta=0.5, "
+                "config": {"workload": f"uniform disk N={n} ({n // world} per GPU), R=0.1, seed {SEED}, theta=0.5, "
                                        "G=6.67e-11, dt=1, depth cap 10; every step restarts from the initial distribution "
                                        "(device-to-device restore inside the timed region)",
                            "l2": "flushed before every timed step (512 MB written); steps timed one by one with CUDA "
@@ -311,6 +313,12 @@ def run_ours(args):
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "phases_us": phases,
                 "value_back_to_back": n * K / (ms_b2b * 1e-3)}
         print(json.dumps(line), flush=True)
+        if args.reference_lines:
+            # the reference program's two stdout lines (project.cu:1097, :1102) for the K timed steps, so that
+            # scripts/gpu_scaling_script.sh can feed the reference's plot scripts
+            par_us = (phases["traverse_us"] if phases else ms / K * 1e3) * K
+            print(f"GPU total computation took {int(round(ms))} milliseconds. "
+                  f"GPU parallel computation took {int(round(par_us))} microseconds.", flush=True)
     sim.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -323,6 +331,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--total-bodies", type=int, default=0,
+                    help="strong scaling: total body count over all GPUs (default: weak scaling, 1M per GPU)")
+    ap.add_argument("--reference-lines", action="store_true",
+                    help="also print the reference program's two timing lines (for scripts/gpu_scaling_script.sh)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
