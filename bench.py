@@ -194,7 +194,12 @@ def run_ours(args):
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(bh.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
-        sim.attach_nccl(bytes(idt.cpu().numpy().tobytes()))
+        sim.attach_nccl(bytes(idt.cpu().numpy().tobytes()))   # NCCL: getters (ragged all-gather of slices)
+        if not args.no_p2p:
+            # per-step exchange over NVLink peer memory, fused with the kernels (csrc/peer_comm.cu)
+            handles = [None] * world
+            dist.all_gather_object(handles, sim.comm_handle())
+            sim.attach_peers(handles)
     sim.set_bodies(pos, vel, mass)
     sim.snapshot()
 
@@ -321,7 +326,8 @@ def run_ours(args):
                            "l2": "flushed before every timed step (512 MB written); steps timed one by one with CUDA "
                                  "events and summed; value_back_to_back is the same K steps in one call without flush",
                            "parallelism": (f"morton-shard x{world}: bodies handed over in Morton order, contiguous index "
-                                           f"slice per rank, sharded build + 2 all-reduces per step") if world > 1
+                                           f"slice per rank, sharded build, " + ("2 NCCL all-reduces per step" if args.no_p2p else
+                                           "box + cell-sum exchange by NVLink peer stores fused with the kernels")) if world > 1
                            else "single GPU"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "phases_us": phases,
@@ -345,6 +351,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-reduces instead of the peer-memory exchange")
     ap.add_argument("--total-bodies", type=int, default=0,
                     help="strong scaling: total body count over all GPUs (default: weak scaling, 1M per GPU)")
     ap.add_argument("--reference-lines", action="store_true",

@@ -34,7 +34,7 @@ BH_FLAG_EXACT_EPS = 1 << 3
 # every symbol include/bh.h declares (checked by tests/test_abi.py against the header text)
 ABI_SYMBOLS = (
     "bh_last_error", "bh_abi_version", "bh_default_params", "bh_create", "bh_destroy", "bh_nccl_unique_id",
-    "bh_attach_nccl", "bh_shard_range", "bh_set_bodies", "bh_set_positions", "bh_set_velocities", "bh_snapshot",
+    "bh_attach_nccl", "bh_comm_handle", "bh_attach_peers", "bh_shard_range", "bh_set_bodies", "bh_set_positions", "bh_set_velocities", "bh_snapshot",
     "bh_restore", "bh_step", "bh_step_host", "bh_step_from_snapshot", "bh_build_tree", "bh_compute_forces", "bh_integrate",
     "bh_synchronize", "bh_get_positions", "bh_get_velocities", "bh_get_accelerations", "bh_get_forces",
     "bh_get_bounds", "bh_get_body_keys", "bh_get_sorted_order", "bh_get_tree_size", "bh_get_tree",
@@ -101,6 +101,8 @@ def lib():
     L.bh_destroy.argtypes = [vp]
     L.bh_nccl_unique_id.argtypes = [vp]
     L.bh_attach_nccl.argtypes = [vp, vp]
+    L.bh_comm_handle.argtypes = [vp, vp]
+    L.bh_attach_peers.argtypes = [vp, vp, C.c_int32]
     L.bh_shard_range.argtypes = [C.c_int64, C.c_int32, C.c_int32, i64p, i64p]
     L.bh_set_bodies.argtypes = [vp, vp, vp, vp]
     L.bh_set_positions.argtypes = [vp, vp]
@@ -231,6 +233,17 @@ class Simulation:
     def attach_nccl(self, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)
         _check(lib().bh_attach_nccl(self._h, buf))
+
+    def comm_handle(self) -> bytes:
+        """64-byte cudaIpc handle of this rank's peer-exchange buffer (all-gather, then attach_peers)."""
+        buf = C.create_string_buffer(64)
+        _check(lib().bh_comm_handle(self._h, buf))
+        return buf.raw
+
+    def attach_peers(self, handles):
+        blob = b"".join(handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        _check(lib().bh_attach_peers(self._h, buf, len(handles)))
 
     def set_bodies(self, pos, vel, mass):
         if not hasattr(pos, "data_ptr"):

@@ -54,6 +54,7 @@
 #include "../csrc/tree_build.cu"
 #include "../csrc/traverse.cu"
 #include "../csrc/direct.cu"
+#include "../csrc/peer_comm.cu"
 #include "../csrc/host_io.cpp"
 
 #include <chrono>

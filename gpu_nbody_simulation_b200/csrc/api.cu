@@ -123,6 +123,10 @@ struct bh_ctx {
     SortPlan sp_own;               // sort plan for this rank's slice
     bool tree_full = false;        // the tree on the device was built from ALL bodies (diagnostic getters)
     bool mass_complete = true;     // multi-rank: masses of the other ranks' slices have been gathered
+    PeerComm pc{};                 // NVLink peer-memory exchange (peer_comm.cu)
+    uint8_t* comm_buf = nullptr;   // this rank's cudaIpc-shared buffer
+    size_t comm_bytes = 0;
+    bool p2p_ready = false;
     ncclComm_t comm = nullptr;
     // graphs
     cudaGraphExec_t graph[2] = {nullptr, nullptr};   // [0] plain step, [1] step from snapshot
@@ -242,9 +246,13 @@ int enqueue_build(bh_ctx* c, bool full = false) {
         c->tree_full = true;
     } else {
         const int64_t lo = c->own_lo, n_own = c->own_hi - c->own_lo;
-        launch_bounds(c->pos + lo, n_own, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream, c->bbox_raw);
-        BH_TRY(allreduce_f64(c, c->bbox_raw, 4, ncclMin));
-        launch_bounds_finalize(c->bbox_raw, c->p, c->d, c->consts, c->stream);
+        if (c->p2p_ready) {   // box exchange fused into the bounds kernel (peer stores + flags)
+            launch_bounds(c->pos + lo, n_own, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream, nullptr, &c->pc);
+        } else {
+            launch_bounds(c->pos + lo, n_own, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream, c->bbox_raw);
+            BH_TRY(allreduce_f64(c, c->bbox_raw, 4, ncclMin));
+            launch_bounds_finalize(c->bbox_raw, c->p, c->d, c->consts, c->stream);
+        }
         launch_keys(c->pos + lo, n_own, c->d, c->sp_own, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream,
                     (uint32_t)lo);
         prof_mark(c, 1);
@@ -252,8 +260,14 @@ int enqueue_build(bh_ctx* c, bool full = false) {
         prof_mark(c, 2);
         launch_tree_runs(c->keys[c->sorted], c->idx[c->sorted], c->pos, c->mass, n_own, c->p, c->d, c->tree, c->s,
                          c->cell_sums, c->stream);
-        BH_TRY(allreduce_f64(c, c->cell_sums, 4 * c->d.ncells_finest, ncclSum));
-        launch_tree_levels(c->idx[c->sorted], c->pos, c->mass, c->p, c->d, c->tree, c->s, c->consts, c->cell_sums, c->stream);
+        const double* reduced = c->cell_sums;
+        if (c->p2p_ready) {   // reduce-scatter + all-gather by direct peer stores, summed in rank order
+            launch_peer_allreduce_cells(c->pc, c->cell_sums, c->stream);
+            reduced = reinterpret_cast<const double*>(c->comm_buf + c->pc.off_sums);
+        } else {
+            BH_TRY(allreduce_f64(c, c->cell_sums, 4 * c->d.ncells_finest, ncclSum));
+        }
+        launch_tree_levels(c->idx[c->sorted], c->pos, c->mass, c->p, c->d, c->tree, c->s, c->consts, reduced, c->stream);
         c->tree_full = false;
     }
     prof_mark(c, 3);
@@ -301,7 +315,8 @@ int run_steps(bh_ctx* c, int nsteps, bool from_snapshot) {
     if (from_snapshot && !c->have_snapshot) { set_error("no snapshot taken"); return BH_ERR_INVALID; }
     if (nsteps < 0) { set_error("nsteps < 0"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
-    const bool use_graph = !(c->p.flags & BH_FLAG_NO_GRAPH) && !c->profiling && c->p.n_ranks == 1;
+    // NCCL calls are not captured; the peer-memory exchange is plain kernels, so multi-rank steps replay too
+    const bool use_graph = !(c->p.flags & BH_FLAG_NO_GRAPH) && !c->profiling && (c->p.n_ranks == 1 || c->p2p_ready);
     const int gi = from_snapshot ? 1 : 0;
     BH_CUDA_OK(cudaEventRecord(c->ev0, c->stream));
     if (use_graph && nsteps > 0) {
@@ -467,6 +482,10 @@ int bh_destroy(bh_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& gr : c->graph) if (gr) cudaGraphExecDestroy(gr);
     if (c->comm) { NcclApi* api = nccl_api(); if (api) api->CommDestroy(c->comm); }
+    if (c->p2p_ready)
+        for (int r = 0; r < c->p.n_ranks; ++r)
+            if (r != c->p.rank && c->pc.peer_base[r]) cudaIpcCloseMemHandle(c->pc.peer_base[r]);
+    if (c->comm_buf) cudaFree(c->comm_buf);
     void* ptrs[] = {c->pos, c->vel, c->acc, c->force, c->snap_pos, c->snap_vel, c->tmp2, c->mass, c->tmp1, c->keys[0],
                     c->keys[1], c->idx[0], c->idx[1], c->consts, c->tree.mass, c->tree.comx, c->tree.comy,
                     c->tree.count, c->tree.first, c->tree.flags, c->rec_alloc, c->tree.self_node, c->s.zero_base, c->s.bbox_partial, c->s.heavy_list, c->s.huge_list, c->s.huge_tickets, c->s.huge_partial,
@@ -499,6 +518,40 @@ int bh_attach_nccl(bh_ctx* c, const void* id128) {
     ncclUniqueId id;
     memcpy(&id, id128, sizeof id);
     BH_NCCL_OK(api, api->CommInitRank(&c->comm, c->p.n_ranks, id, c->p.rank));
+    return BH_OK;
+}
+
+int bh_comm_handle(bh_ctx* c, void* handle64) {
+    if (!c || !handle64) { set_error("null argument"); return BH_ERR_INVALID; }
+    if (c->p.n_ranks < 2 || c->p.n_ranks > kMaxPeers) { set_error("peer exchange needs 2..%d ranks", kMaxPeers); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    if (!c->comm_buf) {
+        peer_comm_layout(c->pc, c->p.rank, c->p.n_ranks, c->d.ncells_finest, &c->comm_bytes);
+        BH_CUDA_OK(cudaMalloc((void**)&c->comm_buf, c->comm_bytes));
+        BH_CUDA_OK(cudaMemset(c->comm_buf, 0, c->comm_bytes));
+        for (int r = 0; r < kMaxPeers; ++r) c->pc.peer_base[r] = nullptr;
+        c->pc.peer_base[c->p.rank] = c->comm_buf;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    BH_CUDA_OK(cudaIpcGetMemHandle(&h, c->comm_buf));
+    memcpy(handle64, &h, sizeof h);
+    return BH_OK;
+}
+
+int bh_attach_peers(bh_ctx* c, const void* handles, int32_t n_handles) {
+    if (!c || !handles) { set_error("null argument"); return BH_ERR_INVALID; }
+    if (n_handles != c->p.n_ranks || !c->comm_buf) { set_error("bh_attach_peers: call bh_comm_handle on every rank first and pass n_ranks handles"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    for (int r = 0; r < c->p.n_ranks; ++r) {
+        if (r == c->p.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + 64 * (size_t)r, sizeof h);
+        void* ptr = nullptr;
+        BH_CUDA_OK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->pc.peer_base[r] = (uint8_t*)ptr;
+    }
+    c->p2p_ready = true;
     return BH_OK;
 }
 
@@ -645,6 +698,11 @@ int bh_synchronize(bh_ctx* c) {
     if (!c) { set_error("null context"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (c->p2p_ready) {
+        uint32_t err = 0;
+        BH_CUDA_OK(cudaMemcpy(&err, c->comm_buf + c->pc.off_err, sizeof err, cudaMemcpyDeviceToHost));
+        if (err) { set_error("peer-memory exchange timed out (a rank did not reach the step)"); return BH_ERR_NCCL; }
+    }
     return BH_OK;
 }
 

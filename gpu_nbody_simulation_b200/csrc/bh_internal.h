@@ -83,6 +83,16 @@ struct Scratch {
     int64_t max_huge;
 };
 
+constexpr int kMaxPeers = 8;   // GPUs of one NVSwitch box
+
+// Peer-memory exchange (peer_comm.cu): every rank owns one cudaIpc-shared buffer with this layout.
+struct PeerComm {
+    int rank, n_ranks;
+    uint8_t* peer_base[kMaxPeers];   // peer_base[rank] is this rank's own buffer
+    size_t off_bbox, off_bbox_flag, off_rs_flag, off_ag_flag, off_err, off_rs, off_sums;
+    uint64_t ncells, slice;          // finest cells, cells per rank slice
+};
+
 struct SortPlan {
     int key_bits, passes, bits_per_pass, nbins_log2;  // nbins_log2 in {8, 9}
     int ntiles;
@@ -99,7 +109,10 @@ struct Dims {
 
 // ---- kernel launchers (each in its own .cu) ------------------------------------------------
 void launch_bounds(const double2* pos, int64_t n, const bh_params& p, const Dims& d, Scratch& s,
-                   StepConsts* consts, int grid, cudaStream_t st, double* raw_out = nullptr);
+                   StepConsts* consts, int grid, cudaStream_t st, double* raw_out = nullptr,
+                   const PeerComm* pc = nullptr);
+void peer_comm_layout(PeerComm& pc, int rank, int n_ranks, uint64_t ncells, size_t* total_bytes);
+void launch_peer_allreduce_cells(const PeerComm& pc, const double* local_sums, cudaStream_t st);
 void launch_bounds_finalize(const double* raw, const bh_params& p, const Dims& d, StepConsts* consts, cudaStream_t st);
 void launch_keys(const double2* pos, int64_t n, const Dims& d, const SortPlan& sp, const StepConsts* consts,
                  uint32_t* keys, uint32_t* idx, uint32_t* digit_hist, cudaStream_t st, uint32_t idx_base = 0);

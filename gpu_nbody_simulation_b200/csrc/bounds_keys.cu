@@ -6,6 +6,7 @@
 // order with contraction disabled (__dmul_rn / __dadd_rn), and the key is produced by the same
 // FP64 bisection `mid = (min + max) / 2` with the same four-way comparison the reference uses.
 #include "bh_internal.h"
+#include "peer_comm.cuh"
 
 namespace bh {
 
@@ -60,7 +61,8 @@ __device__ void finalize_bounds(StepConsts* __restrict__ consts, double xmin, do
 __global__ void __launch_bounds__(kBoundsThreads)
 bounds_kernel(const double2* __restrict__ pos, int64_t n, double* __restrict__ partial,
               uint32_t* __restrict__ ticket, StepConsts* __restrict__ consts, double pad_frac,
-              double pad_fallback, double theta, double dist_eps, int finest, double* __restrict__ raw_out) {
+              double pad_fallback, double theta, double dist_eps, int finest, double* __restrict__ raw_out,
+              const __grid_constant__ PeerComm pc) {
     double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double2 p = pos[i];
@@ -111,9 +113,21 @@ bounds_kernel(const double2* __restrict__ pos, int64_t n, double* __restrict__ p
         ymin = ref_min(ymin, o[2]); ymax = ref_max(ymax, o[3]);
     }
     block_reduce();
+    if (pc.n_ranks > 1) {
+        // fused exchange over NVLink peer memory: this block publishes the rank's box to every peer, waits
+        // for theirs and finalises; the step's sequence number lives in the rank's own comm buffer
+        __shared__ uint32_t s_seq;
+        if (threadIdx.x == 0) {
+            uint32_t* seq_dev = reinterpret_cast<uint32_t*>(pc.peer_base[pc.rank] + pc.off_err) + 1;
+            s_seq = *seq_dev + 1u;
+            *seq_dev = s_seq;
+        }
+        __syncthreads();
+        peer_bbox_exchange(pc, s_seq, xmin, xmax, ymin, ymax);
+    }
     if (threadIdx.x == 0) {
         *ticket = 0;
-        if (raw_out) {   // multi-GPU: min / max are all-reduced over the ranks first (max sent negated)
+        if (raw_out) {   // NCCL fallback: min / max are all-reduced over the ranks first (max sent negated)
             raw_out[0] = xmin; raw_out[1] = -xmax; raw_out[2] = ymin; raw_out[3] = -ymax;
         } else {
             finalize_bounds(consts, xmin, xmax, ymin, ymax, pad_frac, pad_fallback, theta, dist_eps, finest);
@@ -168,9 +182,12 @@ keys_kernel(const double2* __restrict__ pos, int64_t n, int finest, const StepCo
 }  // namespace
 
 void launch_bounds(const double2* pos, int64_t n, const bh_params& p, const Dims& d, Scratch& s,
-                   StepConsts* consts, int grid, cudaStream_t st, double* raw_out) {
+                   StepConsts* consts, int grid, cudaStream_t st, double* raw_out, const PeerComm* pc) {
+    PeerComm none{};
+    none.n_ranks = 1;
     bounds_kernel<<<grid, kBoundsThreads, 0, st>>>(pos, n, s.bbox_partial, s.bbox_ticket, consts, p.pad_frac,
-                                                   p.pad_fallback, p.theta, p.dist_eps, d.finest, raw_out);
+                                                   p.pad_fallback, p.theta, p.dist_eps, d.finest, raw_out,
+                                                   pc ? *pc : none);
     ++g_launches;
 }
 

@@ -99,6 +99,12 @@ int bh_destroy(bh_ctx* ctx);
  * rank (e.g. torch.distributed broadcast), every rank calls bh_attach_nccl before bh_step. */
 int bh_nccl_unique_id(void* id128);
 int bh_attach_nccl(bh_ctx* ctx, const void* id128);
+/* NVLink peer-memory exchange (optional, 2..8 ranks of one box; replaces the per-step NCCL calls by
+ * stores into cudaIpc-mapped peer buffers fused with the kernels, and lets multi-rank steps replay as
+ * CUDA graphs): every rank calls bh_comm_handle, the host application all-gathers the 64-byte handles
+ * (rank order), every rank calls bh_attach_peers with the n_ranks * 64 bytes. */
+int bh_comm_handle(bh_ctx* ctx, void* handle64);
+int bh_attach_peers(bh_ctx* ctx, const void* handles, int32_t n_handles);
 /* index range [lo, hi) of bodies owned by `rank` (pure integer logic, usable without a GPU) */
 int bh_shard_range(int64_t n_bodies, int32_t n_ranks, int32_t rank, int64_t* lo, int64_t* hi);
 

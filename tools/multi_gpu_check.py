@@ -21,6 +21,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--bodies", dest="n", type=int, default=200_000)
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--fp64", action="store_true")
+ap.add_argument("--no-p2p", action="store_true", help="NCCL all-reduces instead of the peer-memory exchange")
 a = ap.parse_args()
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -36,6 +37,10 @@ if rank == 0:
 dist.broadcast(idt, 0)
 sim = bh.Simulation(a.n, device=local, rank=rank, n_ranks=world, **kw)
 sim.attach_nccl(bytes(idt.cpu().numpy().tobytes()))
+if not a.no_p2p:
+    handles = [None] * world
+    dist.all_gather_object(handles, sim.comm_handle())
+    sim.attach_peers(handles)
 sim.set_bodies(pos, vel, mass)
 sim.step(a.steps)
 p_multi, v_multi, f_multi = sim.positions(), sim.velocities(), sim.forces()
@@ -55,7 +60,7 @@ if rank == 0:
     # self-inclusive near-COM interactions amplify to ~1e-9 of the force
     tol = 1e-8 if a.fp64 else 1e-6
     errs = {"pos": rel(p_multi, p_one), "vel": rel(v_multi, v_one), "force": rel(f_multi, f_one)}
-    print(f"world={world} n={a.n} steps={a.steps} fp64={a.fp64} multi-vs-single rel-RMS {errs} (tol {tol})", flush=True)
+    print(f"world={world} n={a.n} steps={a.steps} fp64={a.fp64} p2p={not a.no_p2p} multi-vs-single rel-RMS {errs} (tol {tol})", flush=True)
     ok = all(e <= tol for e in errs.values())
     if a.n <= 300_000:
         import oracle
