@@ -342,3 +342,59 @@ def test_step_host_pipelined_equals_plain_sequence():
         assert np.array_equal(a.velocities(), b.velocities())
         out2 = a.step_host(pos, vel, mass)           # the call is repeatable (state fully overwritten)
         assert np.array_equal(out2, out)
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel variants and the collapsed regime
+# ------------------------------------------------------------------------------------------------
+def test_traversal_variants_agree(shipped40k):
+    """generic 1 / 2 bodies per lane, the packed pair kernel, exact vs first-order eps: same forces."""
+    g = shipped40k
+    pos, vel, mass = g["pos"], g["vel"], g["mass"]
+    want, _ = oracle.Tree(pos, mass).forces(nthreads=oracle.max_threads())
+    out = {}
+    for name, kw in {"bpl1": dict(bodies_per_lane=1), "pair": dict(bodies_per_lane=2),
+                     "pair_exact_eps": dict(bodies_per_lane=2, exact_eps=True), "bpl2_generic": dict(bodies_per_lane=3)}.items():
+        with build(pos, vel, mass, **kw) as sim:
+            sim.compute_forces()
+            out[name] = sim.forces()
+        assert rel_rms(out[name], want) <= 1e-5, name
+    for name in out:
+        assert rel_rms(out[name], out["bpl1"]) <= 2e-6, name
+
+
+def test_huge_cell_collapsed_regime():
+    """> 8192 bodies in one finest cell (what the reference's own dynamics produce after one step):
+    the multi-block summation must give the reference's topology and node values to rounding."""
+    rng = np.random.default_rng(11)
+    n = 30000
+    pos = np.concatenate([rng.normal(0.0, 1e-7, size=(n - 200, 2)), rng.uniform(-1.0, 1.0, size=(200, 2))])
+    mass = rng.uniform(0.1, 0.5, size=n)
+    vel = np.zeros((n, 2))
+    with build(pos, vel, mass, fp64=True, counters=True) as sim:
+        tree = oracle.Tree(pos, mass)
+        got, want = sim.tree(), tree.canonical()
+        assert sim.counters()["heavy_cells"] >= 1
+        assert np.array_equal(got[:, [0, 1, 2, 3, 4, 8, 9]], want[:, [0, 1, 2, 3, 4, 8, 9]])
+        assert np.allclose(got[:, 5:8], want[:, 5:8], rtol=1e-12, atol=1e-22)
+        sim.compute_forces()
+        f = sim.forces()
+        fw, _ = tree.forces(nthreads=oracle.max_threads())
+        assert rel_rms(f, fw) <= 1e-6      # COM rounding differences, amplified by near-COM interactions
+
+
+def test_free_running_reference_dynamics_stay_finite(shipped40k):
+    """10 steps with the reference's constants: the tree collapses after step 0; the
+    engine must follow without NaNs / hangs and agree with the oracle on the node count per step."""
+    g = shipped40k
+    pos, vel, mass = g["pos"][:8000], g["vel"][:8000], g["mass"][:8000]
+    with Simulation(8000, fp64=True) as sim:
+        sim.set_bodies(pos, vel, mass)
+        p, v = pos.copy(), vel.copy()
+        for s in range(4):
+            sim.build_tree()
+            assert sim.tree_size() == oracle.Tree(p, mass).size, f"step {s}"
+            sim.step(1)
+            r = oracle.step(p, v, mass)
+            p, v = r["pos"], r["vel"]
+            assert rel_rms(sim.positions(), p) <= 1e-8, f"step {s}"
