@@ -1,7 +1,7 @@
 """Multi-GPU path: Morton-range sharding + per-step all-gather of positions.
 
 * `gpu` test: 2 ranks over NCCL on a box with >= 2 GPUs (skipped on the 1-GPU round-end box);
-  tools/multi_gpu_check.py compares against a single-GPU context and the CPU oracle.
+  tests/multi_gpu_check.py compares against a single-GPU context and the CPU oracle.
 * CPU tests (gloo, world_size 2, run everywhere): the host-side protocol — shard ranges from the
   C-ABI (bh_shard_range), owned-slice update, all-gather — with the oracle standing in for the
   device kernels, against the single-rank oracle trajectory.
@@ -22,7 +22,7 @@ def test_two_gpus_match_single_gpu_and_oracle():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "multi_gpu_check.py"), "--bodies", "100001",
+           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_check.py"), "--bodies", "100001",
            "--steps", "2"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "MULTI_GPU_CHECK PASS" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
