@@ -45,11 +45,12 @@ METRIC = "body_steps_per_s"
 UNIT = "body·steps/s"
 
 
-def make_workload(n):
+def make_workload(n, dist="disk"):
     from gpu_nbody_simulation_b200 import initial_conditions as ic
     # values pass through the reference writers' "%.6g" text format (round6) up to 2M bodies; above that
     # the string round trip alone takes minutes per rank, so the raw FP64 draws are used
-    return ic.uniform_disk(n, seed=SEED, round6=n <= 2_000_000)
+    gen = {"disk": ic.uniform_disk, "plummer": ic.plummer_2d, "square": ic.uniform_square}[dist]
+    return gen(n, seed=SEED, round6=n <= 2_000_000)
 
 
 class ClockSampler:
@@ -166,7 +167,7 @@ def run_ours(args):
 
     strong = args.total_bodies > 0
     n = args.total_bodies if strong else BODIES_PER_GPU * world
-    pos, vel, mass = make_workload(n)
+    pos, vel, mass = make_workload(n, args.dist)
     K, W = args.steps, args.warmup
 
     def barrier():
@@ -325,7 +326,7 @@ def run_ours(args):
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak",
                 "vs_baseline": None,
                 "dtype": "f32 (double-float displacement; FP64 state, tree and integrator)", "data": "synthetic",
-                "config": {"workload": f"uniform disk N={n} ({n // world} per GPU), R=0.1, seed {SEED}, theta=0.5, "
+                "config": {"workload": f"{'uniform disk' if args.dist == 'disk' else args.dist} N={n} ({n // world} per GPU), R=0.1, seed {SEED}, theta=0.5, "
                                        "G=6.67e-11, dt=1, depth cap 10; every step restarts from the initial distribution "
                                        "(device-to-device restore inside the timed region)",
                            "l2": "inputs larger than L2: the per-rank working set that every step reads and rewrites is "
@@ -358,6 +359,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dist", choices=["disk", "plummer", "square"], default="disk",
+                    help="synthetic distribution (BASELINE config 2: disk; config 3: plummer)")
     ap.add_argument("--no-graph", action="store_true", help="direct kernel launches instead of CUDA-graph replay")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-reduces instead of the peer-memory exchange")
     ap.add_argument("--total-bodies", type=int, default=0,
