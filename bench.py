@@ -62,23 +62,34 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.lines, self.proc = index, [], None
 
-    def start(self):
+    def start(self, wait_s=20.0):
+        """Starts ONE long-running nvidia-smi (loop mode) and returns only after its first sample has
+        arrived: nvidia-smi's start-up attaches to every GPU of the box and takes 1-2 s on an 8-GPU
+        node, during which kernel launches of all ranks stall for milliseconds — started right before
+        the timed bracket (as an earlier version did, once per rank) it cost the 4- and 8-GPU runs
+        30-60 % (gpurun_out/final_weak_g8.json vs bench_weak_g8.log).  Polling afterwards is cheap."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < wait_s and self.proc.poll() is None:
+                time.sleep(0.02)
         except OSError:
             self.proc = None
+
+    def mark(self):
+        """Index of the next sample: samples from here on were taken inside the timed region."""
+        self.first = len(self.lines)
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         self.t.join(timeout=2)
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "first", 0):]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -91,6 +102,30 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pin_to_gpu_numa_node(dev):
+    """Binds this process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that the pinned
+    host buffers of the e2e leg are allocated next to the GPU's PCIe root.  Best effort: returns the
+    node number or None (no sysfs entry, single node, restricted cpuset)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(dev)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
 
 
 def cpu_reference_run(n_bodies, steps, warmup, budget_s=150.0):
@@ -133,6 +168,33 @@ def cpu_reference_run(n_bodies, steps, warmup, budget_s=150.0):
                    "ms_per_step": secs * 1e3}
 
 
+def reference_gpu_run(pos, vel, mass, device):
+    """The reference's OWN GPU program path on this GPU (north_star's second baseline): unmodified
+    project.cu, runSimulationGpu with N_THREADS = N_BODIES, compiled for sm_100a (oracle/_ref/
+    ref_gpu_N1000000_S1: one step per call = the non-degenerate step 0, host tree build + tree H2D +
+    force and update kernels + positions D2H), timed with the reference's own two timers.  Call 0 pays
+    the CUDA context creation and is dropped."""
+    import oracle
+    n = mass.shape[0]
+    if not oracle.ref_gpu_available(n, 1):
+        return {"unavailable": f"oracle/_ref/ref_gpu_N{n}_S1 not built"}
+    try:
+        calls, _ = oracle.run_ref_gpu(pos, vel, mass, steps=1, calls=4, device=device, timeout=300)
+    except Exception as e:   # the baseline must never take the bench line down with it
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    timed = calls[1:]
+    total_ms = statistics.median(c["total_ms"] for c in timed)
+    par_us = statistics.median(c["parallel_us"] for c in timed)
+    return {"value": n / (total_ms * 1e-3), "unit": UNIT, "kind": "reference project.cu (unmodified, runSimulationGpu, "
+            "N_THREADS = N_BODIES, nvcc -O2 sm_100a) on this GPU",
+            "total_ms_per_step": total_ms, "gpu_parallel_us_per_step": par_us,
+            "value_kernels_only": n / (par_us * 1e-6),
+            "sample": f"median of {len(timed)} calls of runSimulationGpu with N_SIMULATIONS = 1 on the same {n} bodies (step 0, "
+                      f"{timed[-1]['last_tree_nodes']} tree nodes); total = the reference's 'GPU total computation' timer "
+                      "(mallocs, host tree build, quadtree_init_gpu.txt, copies), gpu_parallel = its 'GPU parallel "
+                      "computation' timer (force + update kernels)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -160,6 +222,7 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -224,11 +287,19 @@ def run_ours(args):
             tot += sim.last_step_ms()
         return tot
 
+    # clocks: ONE nvidia-smi for the whole job (rank 0 samples every GPU of the job), started and
+    # producing samples BEFORE the warm-up so that its start-up cannot disturb the timed bracket
+    vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+    smi_ids = [vis[i] if i < len(vis) else str(i) for i in range(world)]   # nvidia-smi ignores CUDA_VISIBLE_DEVICES
+    sampler = ClockSampler(",".join(smi_ids)) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
     sim.step_from_snapshot(W)
     sim.synchronize()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    if sampler:
+        sampler.mark()
     # headline: EXACTLY K steps between two barrier + synchronize brackets, device time from CUDA events on
     # the library's stream (recorded around the K steps), max over ranks
     sim.reset_timers()
@@ -240,7 +311,7 @@ def run_ours(args):
     # ranks this one also charges every host-side skew between the ranks to the waiting rank
     ms_flushed = max_over_ranks(timed_steps(K))
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     value = n * K / (ms * 1e-3)
 
     # ---- per-phase events + interaction count (second pass, direct launches, same work) -----------
@@ -321,6 +392,10 @@ def run_ours(args):
         _, cpu_baseline = cpu_reference_run(1_000_000, 1, 0, budget_s=30.0)
         cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    gpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline and not strong and args.dist == "disk":
+        gpu_baseline = reference_gpu_run(pos, vel, mass, local)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak",
@@ -336,9 +411,10 @@ def run_ours(args):
                            "parallelism": (f"morton-shard x{world}: bodies handed over in Morton order, contiguous index "
                                            f"slice per rank, sharded build, " + ("2 NCCL all-reduces per step" if args.no_p2p else
                                            "box + cell-sum exchange by NVLink peer stores fused with the kernels")) if world > 1
-                           else "single GPU"},
+                           else "single GPU", "host_numa_node": numa},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "phases_us": phases,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "gpu_baseline": gpu_baseline,
+                "phases_us": phases,
                 "value_l2_flushed": n * K / (ms_flushed * 1e-3)}
         print(json.dumps(line), flush=True)
         if args.reference_lines:
@@ -359,6 +435,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference project.cu run on this GPU")
     ap.add_argument("--dist", choices=["disk", "plummer", "square"], default="disk",
                     help="synthetic distribution (BASELINE config 2: disk; config 3: plummer)")
     ap.add_argument("--no-graph", action="store_true", help="direct kernel launches instead of CUDA-graph replay")

@@ -256,3 +256,41 @@ def run_ref(pos, vel, mass, steps=1, dump="tree,forces,state", dump_steps="all",
         timings = [json.loads(l) for l in res.stdout.splitlines() if l.startswith("{")]
         recs = read_dump(outp) if keep_dump else {}
     return recs, timings
+
+
+# ----------------------------------------------------------------------------------------------
+# The reference's own GPU program path (runSimulationGpu, unmodified project.cu compiled for
+# sm_100a by oracle/build_ref.sh gpu <N> <steps>) — the "reference project.cu on one B200" baseline.
+# ----------------------------------------------------------------------------------------------
+def ref_gpu_path(n: int, steps: int) -> str:
+    return os.path.join(_HERE, "_ref", f"ref_gpu_N{n}_S{steps}")
+
+
+def ref_gpu_available(n: int, steps: int) -> bool:
+    return os.access(ref_gpu_path(n, steps), os.X_OK)
+
+
+def run_ref_gpu(pos, vel, mass, steps=1, calls=2, want_positions=False, device=None, timeout=600):
+    """Run the reference's runSimulationGpu (`steps` = its compile-time N_SIMULATIONS) `calls` times,
+    every call from these initial bodies.  Returns (per-call JSON dicts, positions after the last
+    call or None).  Call 0 includes the CUDA context creation: treat it as warm-up."""
+    mass = _f64(mass, (-1,))
+    n = mass.shape[0]
+    exe = ref_gpu_path(n, steps)
+    if not os.access(exe, os.X_OK):
+        raise FileNotFoundError(f"{exe} not built (oracle/build_ref.sh gpu {n} {steps})")
+    env = dict(os.environ)
+    if device is not None:
+        vis = [v for v in env.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+        env["CUDA_VISIBLE_DEVICES"] = vis[device] if device < len(vis) else str(device)
+    with tempfile.TemporaryDirectory() as td:
+        inp = os.path.join(td, "bodies.bin")
+        outp = os.path.join(td, "positions.bin")
+        write_bodies_bin(inp, pos, vel, mass)
+        cmd = [exe, "--in", inp, "--calls", str(calls)] + (["--out", outp] if want_positions else [])
+        res = subprocess.run(cmd, cwd=td, env=env, capture_output=True, text=True, timeout=timeout)
+        if res.returncode != 0:
+            raise RuntimeError(f"{os.path.basename(exe)} exited {res.returncode}: {res.stderr.strip()[-300:]}")
+        calls_out = [json.loads(l) for l in res.stdout.splitlines() if l.startswith("{")]
+        p = np.fromfile(outp, dtype=np.float64).reshape(n, 2) if want_positions else None
+    return calls_out, p

@@ -5,6 +5,7 @@
 # (project.cu:1-3, :38-43).  Outputs go ONLY to oracle/_ref/ (git-ignored, travels with gpurun).
 #
 #   oracle/build_ref.sh 40000 1000000        -> oracle/_ref/ref_harness_N40000, ..._N1000000
+#   oracle/build_ref.sh gpu 1000000 1        -> oracle/_ref/ref_gpu_N1000000_S1 (runSimulationGpu, sm_100a)
 set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 ref="${BH_REFERENCE_ROOT:-/root/reference}/implementation/project.cu"
@@ -13,6 +14,17 @@ if [ ! -f "$ref" ]; then
     exit 0
 fi
 mkdir -p "$here/_ref"
+if [ "${1:-}" = "gpu" ]; then
+    # the reference's GPU program path (runSimulationGpu) for the B200 baseline: oracle/build_ref.sh gpu <N> <steps>
+    # unmodified project.cu, -O2, sm_100a, N_THREADS = N_BODIES.
+    n="$2"; s="$3"
+    out="$here/_ref/ref_gpu_N${n}_S${s}"
+    if [ -x "$out" ] && [ "$out" -nt "$here/ref_gpu_harness.cu" ] && [ "$out" -nt "$ref" ]; then exit 0; fi
+    nvcc -O2 -w -std=c++17 -gencode arch=compute_100a,code=sm_100a -DN_BODIES="$n" -DN_THREADS="$n" \
+         -DN_SIMULATIONS="$s" -DREF_SOURCE="\"$ref\"" -o "$out" "$here/ref_gpu_harness.cu" -lpthread
+    echo "built $out"
+    exit 0
+fi
 for n in "$@"; do
     out="$here/_ref/ref_harness_N$n"
     if [ -x "$out" ] && [ "$out" -nt "$here/ref_harness.cu" ] && [ "$out" -nt "$ref" ]; then continue; fi

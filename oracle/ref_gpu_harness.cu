@@ -1,0 +1,106 @@
+// TEST / BENCH INFRASTRUCTURE — not part of the product path.
+//
+// Times the UNMODIFIED reference GPU program path on the machine's GPU: `runSimulationGpu`
+// (project.cu:918-1024: host tree build + H2D of the tree + computeForcesGpu + updateAccVelPos +
+// D2H of positions, every step) exactly as the reference's `main` calls it (project.cu:1083-1088),
+// with the reference's own two timers:
+//     total_ms     wall clock around runSimulationGpu             (project.cu:1083-1088, :1097)
+//     parallel_us  gpu_parallel_duration, force + update kernels   (project.cu:985-1007, :1102)
+// The reference translation unit is compiled *where it lies* under /root/reference by textual
+// inclusion (-DREF_SOURCE=...), only its `main` is renamed; nothing of it is copied into this
+// repository.  N_BODIES / N_THREADS / N_SIMULATIONS are compile-time macros in the reference, hence
+// one binary per (N, steps):  oracle/build_ref.sh gpu <N> <steps>  ->  oracle/_ref/ref_gpu_N<N>_S<steps>
+// (built with -DN_THREADS=N_BODIES as SURVEY 8(d) "GPU baseline timing" prescribes, sm_100a).
+//
+// usage: ref_gpu_N<N>_S<S> --in bodies.bin [--calls R] [--out positions.bin]
+//   bodies.bin : u64 N | mass[N] | pos[2N] | vel[2N]   (FP64, host endian — same file ref_harness reads)
+//   every call restarts from the initial bodies; call 0 also pays the CUDA context creation, so
+//   callers discard it as warm-up.  --out receives the positions after the LAST call (FP64 [N][2]).
+// stdout: one JSON line per call.  Runs in the current directory (writes quadtree_*_gpu.txt there,
+// like the reference).
+#define main bh_reference_main_unused
+#include REF_SOURCE
+#undef main
+
+#include <pthread.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+
+namespace {
+
+struct Job {
+    const char* in = nullptr;
+    const char* out = nullptr;
+    int calls = 2;
+    int rc = 0;
+};
+
+void* worker(void* arg) {
+    Job* job = static_cast<Job*>(arg);
+    const size_t N = N_BODIES;
+    auto masses = std::make_unique<Masses>();
+    auto pos0 = std::make_unique<Positions>();
+    auto vel0 = std::make_unique<Velocities>();
+    auto positions = std::make_unique<Positions>();
+    FILE* fi = fopen(job->in, "rb");
+    if (!fi) { perror(job->in); job->rc = 1; return nullptr; }
+    uint64_t n_in = 0;
+    if (fread(&n_in, 8, 1, fi) != 1 || n_in != N) {
+        fprintf(stderr, "input holds %llu bodies, binary built for %zu\n", (unsigned long long)n_in, N);
+        job->rc = 1; return nullptr;
+    }
+    if (fread(masses->data(), 8, N, fi) != N || fread(pos0->data(), 8, 2 * N, fi) != 2 * N ||
+        fread(vel0->data(), 8, 2 * N, fi) != 2 * N) { fprintf(stderr, "short input\n"); job->rc = 1; return nullptr; }
+    fclose(fi);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { fprintf(stderr, "no CUDA device\n"); job->rc = 3; return nullptr; }
+    for (int call = 0; call < job->calls; ++call) {
+        *positions = *pos0;
+        gpu_parallel_duration = 0;
+        auto t0 = std::chrono::high_resolution_clock::now();
+        runSimulationGpu(*masses, *positions, *vel0);            // project.cu:1085 (arrays by value, like main)
+        auto t1 = std::chrono::high_resolution_clock::now();
+        cudaError_t e = cudaGetLastError();
+        printf("{\"call\": %d, \"n_bodies\": %zu, \"n_steps\": %d, \"total_ms\": %.3f, \"parallel_us\": %lld, "
+               "\"last_tree_nodes\": %zu, \"cuda_error\": \"%s\"}\n",
+               call, N, (int)N_SIMULATIONS, std::chrono::duration<double, std::milli>(t1 - t0).count(),
+               (long long)gpu_parallel_duration, quadtree.size(), e == cudaSuccess ? "" : cudaGetErrorString(e));
+        fflush(stdout);
+        if (e != cudaSuccess) { job->rc = 4; return nullptr; }
+    }
+    if (job->out) {
+        FILE* fo = fopen(job->out, "wb");
+        if (!fo) { perror(job->out); job->rc = 1; return nullptr; }
+        fwrite((*positions)[0].data(), 8, 2 * N, fo);
+        fclose(fo);
+    }
+    return nullptr;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    Job job;
+    for (int i = 1; i < argc; ++i) {
+        if (!strcmp(argv[i], "--in") && i + 1 < argc) job.in = argv[++i];
+        else if (!strcmp(argv[i], "--out") && i + 1 < argc) job.out = argv[++i];
+        else if (!strcmp(argv[i], "--calls") && i + 1 < argc) job.calls = atoi(argv[++i]);
+        else { fprintf(stderr, "bad arg %s\n", argv[i]); return 2; }
+    }
+    if (!job.in) { fprintf(stderr, "--in required\n"); return 2; }
+    // The reference passes its std::array state BY VALUE (project.cu:918, :1085): 24 B/body of stack per
+    // call plus buildTree's copies — it needs `ulimit -s unlimited` from 1M bodies on.  Same effect
+    // without touching the shell: run on a thread with a stack sized for N.
+    pthread_attr_t attr;
+    pthread_attr_init(&attr);
+    size_t stack = (size_t)256 << 20;
+    stack += (size_t)N_BODIES * 256;
+    if (pthread_attr_setstacksize(&attr, stack) != 0) { fprintf(stderr, "cannot reserve %zu bytes of stack\n", stack); return 1; }
+    pthread_t th;
+    if (pthread_create(&th, &attr, worker, &job) != 0) { perror("pthread_create"); return 1; }
+    pthread_join(th, nullptr);
+    return job.rc;
+}
