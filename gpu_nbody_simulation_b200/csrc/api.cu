@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -140,6 +141,9 @@ struct bh_ctx {
     bh_timers timers{};
     uint64_t launches_base = 0;
     bool bodies_set = false, tree_valid = false, have_snapshot = false, timed = false;
+    size_t step_zero_bytes = 0;      // see zero_scratch
+    bool keys_bisect = false;        // env BH_KEYS_BISECT=1: per-body FP64 bisection instead of the boundary table
+    bool snapshot_by_copy = false;   // env BH_SNAPSHOT_COPY=1 (A/B switch, see enqueue_step)
     int bounds_grid = 1;
 };
 
@@ -207,11 +211,11 @@ int exchange_slices(bh_ctx* c, void* base, size_t elem_bytes) {
     return BH_OK;
 }
 
+// Per-step zeroing: ONE memset over [finest-level body counts | sort histograms, tile states, tickets,
+// counters | huge-cell tickets] (laid out back to back by bh_create) and one 0xff fill of self_node.
 void zero_scratch(bh_ctx* c) {
-    cudaMemsetAsync(c->s.zero_base, 0, c->s.zero_bytes, c->stream);
-    cudaMemsetAsync(c->tree.count + c->d.level_off[c->d.finest], 0, c->d.ncells_finest * sizeof(uint32_t), c->stream);
+    cudaMemsetAsync(c->tree.count + c->d.level_off[c->d.finest], 0, c->step_zero_bytes, c->stream);
     cudaMemsetAsync(c->tree.self_node, 0xff, c->d.n * sizeof(uint32_t), c->stream);
-    cudaMemsetAsync(c->s.huge_tickets, 0, (c->s.max_huge + 1) * sizeof(uint32_t), c->stream);
 }
 
 void prof_mark(bh_ctx* c, int i) { if (c->profiling) cudaEventRecord(c->pev[i], c->stream); }
@@ -231,34 +235,39 @@ int allreduce_f64(bh_ctx* c, double* buf, size_t count, ncclRedOp_t op) {
 // per finest cell; two all-reduces make the tree global — 4 doubles (min of xmin, -xmax, ymin, -ymax)
 // and 4 doubles per finest cell (count, m, m x, m y: 8.4 MB at the default cap, independent of N).
 // The level pass then runs redundantly on the identical reduced sums.  No body data crosses NVLink.
-int enqueue_build(bh_ctx* c, bool full = false) {
+// `src` = the positions the tree is built from: c->pos, or the snapshot when a step restarts from it
+// (out-of-place step: every kernel reads the snapshot, only the fused integrator writes c->pos / c->vel,
+// so no restore copy is needed).
+int enqueue_build(bh_ctx* c, bool full = false, const double2* src = nullptr) {
+    if (!src) src = c->pos;
     zero_scratch(c);
     prof_mark(c, 0);
     const bool sharded = c->p.n_ranks > 1 && !full;
     if (!sharded) {
-        launch_bounds(c->pos, c->d.n, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream);
-        launch_keys(c->pos, c->d.n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream);
+        launch_bounds(src, c->d.n, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream);
+        launch_keys(src, c->d.n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream, 0,
+                    c->keys_bisect ? nullptr : c->s.cell_bnd);
         prof_mark(c, 1);
         launch_sort(c->keys, c->idx, c->d.n, c->sp, c->s, &c->sorted, c->stream);
         prof_mark(c, 2);
-        launch_tree(c->keys[c->sorted], c->idx[c->sorted], c->pos, c->mass, c->d.n, c->p, c->d, c->tree, c->s, c->consts,
+        launch_tree(c->keys[c->sorted], c->idx[c->sorted], src, c->mass, c->d.n, c->p, c->d, c->tree, c->s, c->consts,
                     c->stream);
         c->tree_full = true;
     } else {
         const int64_t lo = c->own_lo, n_own = c->own_hi - c->own_lo;
         if (c->p2p_ready) {   // box exchange fused into the bounds kernel (peer stores + flags)
-            launch_bounds(c->pos + lo, n_own, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream, nullptr, &c->pc);
+            launch_bounds(src + lo, n_own, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream, nullptr, &c->pc);
         } else {
-            launch_bounds(c->pos + lo, n_own, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream, c->bbox_raw);
+            launch_bounds(src + lo, n_own, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream, c->bbox_raw);
             BH_TRY(allreduce_f64(c, c->bbox_raw, 4, ncclMin));
-            launch_bounds_finalize(c->bbox_raw, c->p, c->d, c->consts, c->stream);
+            launch_bounds_finalize(c->bbox_raw, c->p, c->d, c->s, c->consts, c->stream);
         }
-        launch_keys(c->pos + lo, n_own, c->d, c->sp_own, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream,
-                    (uint32_t)lo);
+        launch_keys(src + lo, n_own, c->d, c->sp_own, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream,
+                    (uint32_t)lo, c->keys_bisect ? nullptr : c->s.cell_bnd);
         prof_mark(c, 1);
         launch_sort(c->keys, c->idx, n_own, c->sp_own, c->s, &c->sorted, c->stream);
         prof_mark(c, 2);
-        launch_tree_runs(c->keys[c->sorted], c->idx[c->sorted], c->pos, c->mass, n_own, c->p, c->d, c->tree, c->s,
+        launch_tree_runs(c->keys[c->sorted], c->idx[c->sorted], src, c->mass, n_own, c->p, c->d, c->tree, c->s,
                          c->cell_sums, c->stream);
         const double* reduced = c->cell_sums;
         if (c->p2p_ready) {   // reduce-scatter + all-gather by direct peer stores, summed in rank order
@@ -267,17 +276,18 @@ int enqueue_build(bh_ctx* c, bool full = false) {
         } else {
             BH_TRY(allreduce_f64(c, c->cell_sums, 4 * c->d.ncells_finest, ncclSum));
         }
-        launch_tree_levels(c->idx[c->sorted], c->pos, c->mass, c->p, c->d, c->tree, c->s, c->consts, reduced, c->stream);
+        launch_tree_levels(c->idx[c->sorted], src, c->mass, c->p, c->d, c->tree, c->s, c->consts, reduced, c->stream);
         c->tree_full = false;
     }
     prof_mark(c, 3);
     return check_launch();
 }
 
-int enqueue_forces(bh_ctx* c, bool integrate) {
+int enqueue_forces(bh_ctx* c, bool integrate, const double2* src_pos = nullptr, const double2* src_vel = nullptr) {
     // after a sharded build the sorted list holds exactly this rank's bodies
     const int64_t n_eval = (c->p.n_ranks > 1 && !c->tree_full) ? (c->own_hi - c->own_lo) : c->d.n;
-    launch_traverse(c->keys[c->sorted], c->idx[c->sorted], c->pos, c->vel, c->acc, c->force, c->mass, c->d.n,
+    launch_traverse(c->keys[c->sorted], c->idx[c->sorted], src_pos ? src_pos : c->pos, src_vel ? src_vel : c->vel,
+                    c->pos, c->vel, c->acc, c->force, c->mass, c->d.n,
                     c->own_lo, c->own_hi, nullptr, nullptr, n_eval, c->p, c->d, c->tree, c->consts, c->s.counters, integrate,
                     c->stream);
     prof_mark(c, 4);
@@ -285,13 +295,18 @@ int enqueue_forces(bh_ctx* c, bool integrate) {
 }
 
 int enqueue_step(bh_ctx* c, bool from_snapshot) {
-    if (from_snapshot) {   // a rank only ever reads and writes its own slice of pos / vel
-        const int64_t lo = c->own_lo, cnt = c->own_hi - c->own_lo;
-        cudaMemcpyAsync(c->pos + lo, c->snap_pos + lo, sizeof(double2) * cnt, cudaMemcpyDeviceToDevice, c->stream);
-        cudaMemcpyAsync(c->vel + lo, c->snap_vel + lo, sizeof(double2) * cnt, cudaMemcpyDeviceToDevice, c->stream);
+    const double2 *src_pos = nullptr, *src_vel = nullptr;
+    if (from_snapshot) {
+        if (c->snapshot_by_copy) {   // BH_SNAPSHOT_COPY=1: restore by device-to-device copies, then step in place
+            const int64_t lo = c->own_lo, cnt = c->own_hi - c->own_lo;   // a rank only touches its own slice
+            cudaMemcpyAsync(c->pos + lo, c->snap_pos + lo, sizeof(double2) * cnt, cudaMemcpyDeviceToDevice, c->stream);
+            cudaMemcpyAsync(c->vel + lo, c->snap_vel + lo, sizeof(double2) * cnt, cudaMemcpyDeviceToDevice, c->stream);
+        } else {                     // default: the step reads the snapshot and writes pos / vel (no copies)
+            src_pos = c->snap_pos; src_vel = c->snap_vel;
+        }
     }
-    BH_TRY(enqueue_build(c));
-    BH_TRY(enqueue_forces(c, true));
+    BH_TRY(enqueue_build(c, false, src_pos));
+    BH_TRY(enqueue_forces(c, true, src_pos, src_vel));
     prof_mark(c, 5);
     return BH_OK;
 }
@@ -427,16 +442,22 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     BH_ALLOC(c->consts, 1);
     const uint64_t np = c->d.npyramid;
     BH_ALLOC(c->tree.mass, np); BH_ALLOC(c->tree.comx, np); BH_ALLOC(c->tree.comy, np);
-    BH_ALLOC(c->tree.count, np); BH_ALLOC(c->tree.first, np); BH_ALLOC(c->tree.flags, np);
+    BH_ALLOC(c->tree.first, np); BH_ALLOC(c->tree.flags, np);
     BH_ALLOC(c->rec_alloc, np + 4);
     c->tree.rec = c->rec_alloc + 3;   // 96-byte lead-in: sibling groups (4p+1 .. 4p+4) start on 128-byte lines
     BH_ALLOC(c->tree.self_node, n);
-    // zeroed scratch block
+    // One allocation: [tree.count: all levels, finest level last][zeroed scratch block][huge-cell tickets].
+    // Everything from the finest level's counts to the end is zeroed by ONE memset per step (zero_scratch).
     const int nbins = 1 << c->sp.nbins_log2;
+    const size_t np_pad = ((size_t)np + 3) & ~(size_t)3;   // keeps the 64-bit counters 8-byte aligned
     size_t words = (size_t)kMaxSortPasses * kMaxBins + 16 /*tickets, heavy, bbox ticket*/ + 16 /*8 x u64 counters*/ +
                    (size_t)c->sp.passes * c->sp.ntiles * nbins;
-    uint32_t* zb = nullptr;
-    BH_ALLOC(zb, words);
+    words = (words + 3) & ~(size_t)3;
+    c->s.max_huge = n / kHugeCellMin + 1;
+    const size_t huge_words = (size_t)c->s.max_huge + 1;    // [max_huge] = huge_count
+    BH_ALLOC(c->tree.count, np_pad + words + huge_words);
+    uint32_t* zb = c->tree.count + np_pad;
+    c->step_zero_bytes = (np_pad - (size_t)c->d.level_off[c->d.finest] + words + huge_words) * sizeof(uint32_t);
     c->s.zero_base = (uint8_t*)zb;
     c->s.zero_bytes = words * sizeof(uint32_t);
     c->s.digit_hist = zb;
@@ -445,17 +466,17 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     c->s.bbox_ticket = c->s.tickets + 9;
     c->s.counters = (unsigned long long*)(c->s.tickets + 16);
     c->s.tile_state = c->s.tickets + 32;
+    c->s.huge_tickets = zb + words;
+    c->s.huge_count = c->s.huge_tickets + c->s.max_huge;
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, c->device)) != cudaSuccess) { set_error("%s", cudaGetErrorString(e)); return fail(BH_ERR_CUDA); }
     int64_t bg = (n + 256 * 8 - 1) / (256 * 8);
     c->bounds_grid = (int)std::max<int64_t>(1, std::min<int64_t>(bg, prop.multiProcessorCount * 4));
     BH_ALLOC(c->s.bbox_partial, (size_t)c->bounds_grid * 4);
     BH_ALLOC(c->s.heavy_list, c->d.ncells_finest);
-    c->s.max_huge = n / kHugeCellMin + 1;
     BH_ALLOC(c->s.huge_list, c->s.max_huge);
-    BH_ALLOC(c->s.huge_tickets, c->s.max_huge + 1);   // [max_huge] = huge_count
-    c->s.huge_count = c->s.huge_tickets + c->s.max_huge;
     BH_ALLOC(c->s.huge_partial, (size_t)c->s.max_huge * kHugeParts * 3);
+    BH_ALLOC(c->s.cell_bnd, 2 * (((size_t)1 << c->d.finest) + 1));
     if (p->n_ranks > 1) {
         BH_ALLOC(c->cell_sums, 4 * c->d.ncells_finest); BH_ALLOC(c->bbox_raw, 4);
     }
@@ -469,8 +490,10 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     for (auto& ev : c->pev) cudaEventCreate(&ev);
     cudaMemsetAsync(c->acc, 0, sizeof(double2) * n, c->stream);
     cudaMemsetAsync(c->force, 0, sizeof(double2) * n, c->stream);
-    cudaMemsetAsync(c->tree.count, 0, sizeof(uint32_t) * np, c->stream);
+    cudaMemsetAsync(c->tree.count, 0, sizeof(uint32_t) * (np_pad + words + huge_words), c->stream);
     if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { set_error("%s", cudaGetErrorString(e)); return fail(BH_ERR_CUDA); }
+    { const char* e = getenv("BH_SNAPSHOT_COPY"); c->snapshot_by_copy = e && e[0] == '1'; }
+    { const char* e = getenv("BH_KEYS_BISECT"); c->keys_bisect = e && e[0] == '1'; }
     c->launches_base = g_launches;
     *out = c;
     return BH_OK;
@@ -488,7 +511,8 @@ int bh_destroy(bh_ctx* c) {
     if (c->comm_buf) cudaFree(c->comm_buf);
     void* ptrs[] = {c->pos, c->vel, c->acc, c->force, c->snap_pos, c->snap_vel, c->tmp2, c->mass, c->tmp1, c->keys[0],
                     c->keys[1], c->idx[0], c->idx[1], c->consts, c->tree.mass, c->tree.comx, c->tree.comy,
-                    c->tree.count, c->tree.first, c->tree.flags, c->rec_alloc, c->tree.self_node, c->s.zero_base, c->s.bbox_partial, c->s.heavy_list, c->s.huge_list, c->s.huge_tickets, c->s.huge_partial,
+                    c->tree.count /* + scratch + tickets */, c->tree.first, c->tree.flags, c->rec_alloc, c->tree.self_node,
+                    c->s.bbox_partial, c->s.heavy_list, c->s.huge_list, c->s.huge_partial, c->s.cell_bnd,
                     c->packed, c->own_list, c->own_count, c->perm, c->cell_sums, c->bbox_raw};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -653,7 +677,8 @@ int bh_step_host(bh_ctx* c, const double* pos, const double* vel, const double* 
     zero_scratch(c);
     BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[0], 0));
     launch_bounds(c->pos, n, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream);
-    launch_keys(c->pos, n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream);
+    launch_keys(c->pos, n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream, 0,
+                c->keys_bisect ? nullptr : c->s.cell_bnd);
     launch_sort(c->keys, c->idx, n, c->sp, c->s, &c->sorted, c->stream);
     BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[1], 0));
     launch_tree(c->keys[c->sorted], c->idx[c->sorted], c->pos, c->mass, n, c->p, c->d, c->tree, c->s, c->consts, c->stream);

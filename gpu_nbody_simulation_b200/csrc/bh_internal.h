@@ -80,6 +80,7 @@ struct Scratch {
     uint32_t* huge_count;     // 1 (zeroed)
     uint32_t* huge_tickets;   // per huge cell (zeroed)
     double* huge_partial;     // [huge cells][kHugeParts][3]
+    double* cell_bnd;         // [2][2^F + 1] finest-level column / row boundaries (bounds kernel -> keys kernel)
     int64_t max_huge;
 };
 
@@ -113,9 +114,11 @@ void launch_bounds(const double2* pos, int64_t n, const bh_params& p, const Dims
                    const PeerComm* pc = nullptr);
 void peer_comm_layout(PeerComm& pc, int rank, int n_ranks, uint64_t ncells, size_t* total_bytes);
 void launch_peer_allreduce_cells(const PeerComm& pc, const double* local_sums, cudaStream_t st);
-void launch_bounds_finalize(const double* raw, const bh_params& p, const Dims& d, StepConsts* consts, cudaStream_t st);
+void launch_bounds_finalize(const double* raw, const bh_params& p, const Dims& d, Scratch& s, StepConsts* consts,
+                            cudaStream_t st);
 void launch_keys(const double2* pos, int64_t n, const Dims& d, const SortPlan& sp, const StepConsts* consts,
-                 uint32_t* keys, uint32_t* idx, uint32_t* digit_hist, cudaStream_t st, uint32_t idx_base = 0);
+                 uint32_t* keys, uint32_t* idx, uint32_t* digit_hist, cudaStream_t st, uint32_t idx_base,
+                 const double* cell_bnd);   // cell_bnd: Scratch::cell_bnd (table lookup) or nullptr (bisection)
 void launch_tree_runs(const uint32_t* skeys, const uint32_t* sidx, const double2* pos, const double* mass,
                       int64_t n, const bh_params& p, const Dims& d, TreeArrays& t, Scratch& s, double* sums,
                       cudaStream_t st);
@@ -127,7 +130,8 @@ void launch_sort(uint32_t* keys[2], uint32_t* vals[2], int64_t n, const SortPlan
 void launch_tree(const uint32_t* skeys, const uint32_t* sidx, const double2* pos, const double* mass,
                  int64_t n, const bh_params& p, const Dims& d, TreeArrays& t, Scratch& s,
                  const StepConsts* consts, cudaStream_t st);
-void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, double2* pos, double2* vel, double2* acc,
+void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2* pos_in, const double2* vel_in,
+                     double2* pos, double2* vel, double2* acc,
                      double2* force, const double* mass, int64_t n, int64_t own_lo, int64_t own_hi,
                      const uint32_t* own_list, const uint32_t* own_count_dev, int64_t own_n,
                      const bh_params& p, const Dims& d, const TreeArrays& t, const StepConsts* consts,

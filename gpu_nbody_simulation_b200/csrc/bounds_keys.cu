@@ -58,11 +58,35 @@ __device__ void finalize_bounds(StepConsts* __restrict__ consts, double xmin, do
     }
 }
 
+// Cell boundaries of the finest level along x and y: bnd[i] = lower edge of column / row i (i = 0 .. 2^F),
+// produced by the SAME chain of FP64 bisections the reference descends (project.cu:417-428: the child
+// takes [min, mid] or [mid, max] with mid = (min + max) / 2), following the bits of i from the root down.
+// The finest cell of a coordinate x is then the unique i with bnd[i] <= x < bnd[i + 1] (keys_kernel).
+// Called by every thread of the block that finalised the box (consts already written + __syncthreads).
+__device__ void fill_cell_bounds(const StepConsts* consts, int finest, double* __restrict__ bnd) {
+    if (!bnd) return;
+    const uint32_t nc = 1u << finest;
+    for (uint32_t t = threadIdx.x; t < 2u * (nc + 1u); t += blockDim.x) {
+        const bool is_y = t > nc;
+        const uint32_t i = is_y ? t - (nc + 1u) : t;
+        double lo = is_y ? consts->ymin : consts->xmin, hi = is_y ? consts->ymax : consts->xmax;
+        if (i == nc) {
+            lo = hi;
+        } else {
+            for (int l = finest - 1; l >= 0; --l) {
+                const double mid = __dmul_rn(__dadd_rn(lo, hi), 0.5);
+                if ((i >> l) & 1u) lo = mid; else hi = mid;
+            }
+        }
+        bnd[t] = lo;
+    }
+}
+
 __global__ void __launch_bounds__(kBoundsThreads)
 bounds_kernel(const double2* __restrict__ pos, int64_t n, double* __restrict__ partial,
               uint32_t* __restrict__ ticket, StepConsts* __restrict__ consts, double pad_frac,
               double pad_fallback, double theta, double dist_eps, int finest, double* __restrict__ raw_out,
-              const __grid_constant__ PeerComm pc) {
+              double* __restrict__ cell_bnd, const __grid_constant__ PeerComm pc) {
     double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double2 p = pos[i];
@@ -133,39 +157,82 @@ bounds_kernel(const double2* __restrict__ pos, int64_t n, double* __restrict__ p
             finalize_bounds(consts, xmin, xmax, ymin, ymax, pad_frac, pad_fallback, theta, dist_eps, finest);
         }
     }
+    if (!raw_out) {
+        __syncthreads();   // consts written by thread 0 are visible to the block
+        fill_cell_bounds(consts, finest, cell_bnd);
+    }
 }
 
 __global__ void bounds_finalize_kernel(const double* __restrict__ raw, StepConsts* __restrict__ consts, double pad_frac,
-                                       double pad_fallback, double theta, double dist_eps, int finest) {
-    if (threadIdx.x == 0 && blockIdx.x == 0)
+                                       double pad_fallback, double theta, double dist_eps, int finest,
+                                       double* __restrict__ cell_bnd) {
+    if (threadIdx.x == 0)
         finalize_bounds(consts, raw[0], -raw[1], raw[2], -raw[3], pad_frac, pad_fallback, theta, dist_eps, finest);
+    __syncthreads();
+    fill_cell_bounds(consts, finest, cell_bnd);
 }
 
-// One thread per body.  Also accumulates the radix-sort digit histograms of all passes.
+// Spread the low 16 bits of v to the even bit positions.
+__device__ __forceinline__ uint32_t spread_bits(uint32_t v) {
+    v &= 0xffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+// Column (or row) of coordinate x: the unique i with bnd[i] <= x < bnd[i + 1].  The multiply only
+// proposes a candidate; the comparisons against the bisection-chain boundaries decide, so the result
+// is the reference's descent bit for bit (x >= mid goes up at every level).  Typically 0 corrections.
+__device__ __forceinline__ uint32_t locate_cell(double x, double x0, double inv_w, const double* __restrict__ bnd,
+                                                uint32_t nc) {
+    double g = (x - x0) * inv_w;
+    int i = (g >= 0.0) ? ((g < (double)nc) ? (int)g : (int)nc - 1) : 0;   // NaN -> 0
+    while (i > 0 && x < __ldg(bnd + i)) --i;
+    while (i < (int)nc - 1 && x >= __ldg(bnd + i + 1)) ++i;
+    return (uint32_t)i;
+}
+
+// One thread per body.  Also accumulates the radix digit histograms of all passes.
+// TABLE = true (default): finest cell by lookup in the boundary table written by the bounds kernel
+// (2 multiplies + ~4 compares per body instead of 2 x F dependent FP64 bisections); TABLE = false
+// (BH_KEYS_BISECT=1): the descent itself.  Both are bit-exact restatements of project.cu:348-356.
+template <bool TABLE>
 __global__ void __launch_bounds__(256)
 keys_kernel(const double2* __restrict__ pos, int64_t n, int finest, const StepConsts* __restrict__ consts,
             uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ digit_hist,
-            int passes, int bits_per_pass, uint32_t idx_base) {
+            int passes, int bits_per_pass, uint32_t idx_base, const double* __restrict__ cell_bnd) {
     __shared__ uint32_t hist[kMaxSortPasses * kMaxBins];
     for (int i = threadIdx.x; i < passes * kMaxBins; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     const double bx0 = consts->xmin, bx1 = consts->xmax, by0 = consts->ymin, by1 = consts->ymax;
     const uint32_t dmask = (1u << bits_per_pass) - 1u;
+    const uint32_t nc = 1u << finest;
+    const double inv_wx = (double)nc / (bx1 - bx0), inv_wy = (double)nc / (by1 - by0);
+    const double* __restrict__ bnd_x = cell_bnd;
+    const double* __restrict__ bnd_y = cell_bnd + (nc + 1u);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double2 p = pos[i];
-        double xl = bx0, xh = bx1, yl = by0, yh = by1;
         uint32_t key = 0;
         // project.cu:352-355 tests (x<mx && y<my) -> 0, (x>=mx && y<my) -> 1, (x<mx && y>=my) -> 2, else 3.
         // For ordered values that is (x >= mx) | (y >= my) << 1; a NaN coordinate fails all three
         // tests and goes to child 3 at every level.
         const bool unordered = (p.x != p.x) || (p.y != p.y);
-        for (int l = 0; l < finest; ++l) {
-            const double mx = __dmul_rn(__dadd_rn(xl, xh), 0.5);   // (min + max) / 2, exact halving
-            const double my = __dmul_rn(__dadd_rn(yl, yh), 0.5);
-            const bool bx = unordered || (p.x >= mx), by = unordered || (p.y >= my);
-            xl = bx ? mx : xl; xh = bx ? xh : mx;               // child bounds project.cu:421-429
-            yl = by ? my : yl; yh = by ? yh : my;
-            key = (key << 2) | (uint32_t)bx | ((uint32_t)by << 1);
+        if constexpr (TABLE) {
+            const uint32_t ix = unordered ? nc - 1u : locate_cell(p.x, bx0, inv_wx, bnd_x, nc);
+            const uint32_t iy = unordered ? nc - 1u : locate_cell(p.y, by0, inv_wy, bnd_y, nc);
+            key = spread_bits(ix) | (spread_bits(iy) << 1);       // level 0 decision = most significant pair
+        } else {
+            double xl = bx0, xh = bx1, yl = by0, yh = by1;
+            for (int l = 0; l < finest; ++l) {
+                const double mx = __dmul_rn(__dadd_rn(xl, xh), 0.5);   // (min + max) / 2, exact halving
+                const double my = __dmul_rn(__dadd_rn(yl, yh), 0.5);
+                const bool bx = unordered || (p.x >= mx), by = unordered || (p.y >= my);
+                xl = bx ? mx : xl; xh = bx ? xh : mx;               // child bounds project.cu:421-429
+                yl = by ? my : yl; yh = by ? yh : my;
+                key = (key << 2) | (uint32_t)bx | ((uint32_t)by << 1);
+            }
         }
         keys[i] = key;
         idx[i] = idx_base + (uint32_t)i;
@@ -187,22 +254,29 @@ void launch_bounds(const double2* pos, int64_t n, const bh_params& p, const Dims
     none.n_ranks = 1;
     bounds_kernel<<<grid, kBoundsThreads, 0, st>>>(pos, n, s.bbox_partial, s.bbox_ticket, consts, p.pad_frac,
                                                    p.pad_fallback, p.theta, p.dist_eps, d.finest, raw_out,
-                                                   pc ? *pc : none);
+                                                   s.cell_bnd, pc ? *pc : none);
     ++g_launches;
 }
 
-void launch_bounds_finalize(const double* raw, const bh_params& p, const Dims& d, StepConsts* consts, cudaStream_t st) {
-    bounds_finalize_kernel<<<1, 32, 0, st>>>(raw, consts, p.pad_frac, p.pad_fallback, p.theta, p.dist_eps, d.finest);
+void launch_bounds_finalize(const double* raw, const bh_params& p, const Dims& d, Scratch& s, StepConsts* consts,
+                            cudaStream_t st) {
+    bounds_finalize_kernel<<<1, kBoundsThreads, 0, st>>>(raw, consts, p.pad_frac, p.pad_fallback, p.theta, p.dist_eps,
+                                                         d.finest, s.cell_bnd);
     ++g_launches;
 }
 
 void launch_keys(const double2* pos, int64_t n, const Dims& d, const SortPlan& sp, const StepConsts* consts,
-                 uint32_t* keys, uint32_t* idx, uint32_t* digit_hist, cudaStream_t st, uint32_t idx_base) {
+                 uint32_t* keys, uint32_t* idx, uint32_t* digit_hist, cudaStream_t st, uint32_t idx_base,
+                 const double* cell_bnd) {
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    keys_kernel<<<(int)blocks, 256, 0, st>>>(pos, n, d.finest, consts, keys, idx, digit_hist, sp.passes,
-                                             sp.bits_per_pass, idx_base);
+    if (cell_bnd)
+        keys_kernel<true><<<(int)blocks, 256, 0, st>>>(pos, n, d.finest, consts, keys, idx, digit_hist, sp.passes,
+                                                       sp.bits_per_pass, idx_base, cell_bnd);
+    else
+        keys_kernel<false><<<(int)blocks, 256, 0, st>>>(pos, n, d.finest, consts, keys, idx, digit_hist, sp.passes,
+                                                        sp.bits_per_pass, idx_base, nullptr);
     ++g_launches;
 }
 

@@ -49,7 +49,9 @@ struct TravArgs {
     const uint32_t* sidx;       // body index per sorted position
     const uint32_t* own_list;   // optional: sorted positions owned by this rank (multi-GPU)
     const uint32_t* self_node;  // per body: its own single-occupant leaf (pyramid index) or 0xffffffff
-    double2* pos;
+    const double2* pos_in;      // positions / velocities the step starts from (== pos / vel, or the
+    const double2* vel_in;      // snapshot when the step restarts from it: no restore copy needed)
+    double2* pos;               // outputs of the fused integrator
     double2* vel;
     double2* acc;
     double2* force;
@@ -87,7 +89,7 @@ __device__ __forceinline__ void finish_body(const TravArgs& a, uint32_t body, do
     a.force[body] = make_double2(fx, fy);
     if constexpr (INTEGRATE) {
         const double accx = __ddiv_rn(fx, mi), accy = __ddiv_rn(fy, mi);      // project.cu:827-828
-        double2 v = a.vel[body];
+        double2 v = a.vel_in[body];
         v.x = __dadd_rn(v.x, __dmul_rn(accx, a.dt));                          // project.cu:830-831
         v.y = __dadd_rn(v.y, __dmul_rn(accy, a.dt));
         const double nx = __dadd_rn(px, __dmul_rn(v.x, a.dt));               // project.cu:833-834
@@ -163,7 +165,7 @@ traverse_f32_kernel(const __grid_constant__ TravArgs a) {
                 uint32_t sp = a.own_list ? a.own_list[slot] : (uint32_t)slot;
                 body[b] = a.sidx[sp];
                 selfn[b] = a.self_node[body[b]];
-                double2 p = a.pos[body[b]];
+                double2 p = a.pos_in[body[b]];
                 px = p.x; py = p.y;
             }
             const double sx = px * scale, sy = py * scale;
@@ -263,7 +265,7 @@ traverse_f32_kernel(const __grid_constant__ TravArgs a) {
 #pragma unroll
     for (int b = 0; b < BPL; ++b) {
         if (body[b] != 0xffffffffu) {
-            const double2 p = a.pos[body[b]];
+            const double2 p = a.pos_in[body[b]];
             const double mi = a.mass[body[b]];
             finish_body<INTEGRATE>(a, body[b], p.x, p.y, mi, mi * (double)acc2[b].x, mi * (double)acc2[b].y);
         }
@@ -319,7 +321,7 @@ traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
                 uint32_t sp = a.own_list ? a.own_list[slot] : (uint32_t)slot;
                 body[b] = a.sidx[sp];
                 selfn[b] = a.self_node[body[b]];
-                double2 p = a.pos[body[b]];
+                double2 p = a.pos_in[body[b]];
                 px = p.x; py = p.y;
             }
             const double sx = px * scale, sy = py * scale;
@@ -405,7 +407,7 @@ traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
         if (body[b] != 0xffffffffu) {
-            const double2 p = a.pos[body[b]];
+            const double2 p = a.pos_in[body[b]];
             const double mi = a.mass[body[b]];
             finish_body<INTEGRATE>(a, body[b], p.x, p.y, mi, mi * (double)ax[b], mi * (double)ay[b]);
         }
@@ -428,7 +430,7 @@ traverse_f64_kernel(const __grid_constant__ TravArgs a) {
         uint32_t sp = a.own_list ? a.own_list[slot] : (uint32_t)slot;
         body = a.sidx[sp];
         selfn = a.self_node[body];
-        double2 p = a.pos[body];
+        double2 p = a.pos_in[body];
         px = p.x; py = p.y;
         mi = a.mass[body];
     }
@@ -546,7 +548,8 @@ own_list_kernel(const uint32_t* __restrict__ sidx, int64_t n, uint32_t lo, uint3
 
 }  // namespace
 
-void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, double2* pos, double2* vel, double2* acc,
+void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2* pos_in, const double2* vel_in,
+                     double2* pos, double2* vel, double2* acc,
                      double2* force, const double* mass, int64_t n, int64_t own_lo, int64_t own_hi,
                      const uint32_t* own_list, const uint32_t* own_count_dev, int64_t own_n,
                      const bh_params& p, const Dims& d, const TreeArrays& t, const StepConsts* consts,
@@ -554,6 +557,7 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, double2* pos, 
     (void)own_lo; (void)own_hi; (void)own_count_dev; (void)n; (void)skeys; (void)d;
     TravArgs a;
     a.sidx = sidx; a.own_list = own_list; a.self_node = t.self_node;
+    a.pos_in = pos_in; a.vel_in = vel_in;
     a.pos = pos; a.vel = vel; a.acc = acc; a.force = force; a.mass = mass;
     a.rec = t.rec; a.flags = t.flags; a.t_mass = t.mass; a.t_comx = t.comx; a.t_comy = t.comy;
     a.consts = consts; a.counters = counters;

@@ -324,15 +324,28 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
             cur.first = t.first[offF + code];
             if (cur.cnt <= exact_leaf_max) {
                 // project.cu:367-373: running weighted average in ascending body index
+                // The arithmetic chain is sequential by definition; the gathers feeding it are not: bodies are
+                // fetched four at a time (index loads, then mass / position loads, all independent) so that the
+                // dependent L2 round trips overlap instead of adding up per body.
                 double em = 0.0, ex = 0.0, ey = 0.0;
-                for (uint32_t i = 0; i < cur.cnt; ++i) {
-                    const uint32_t b = __ldg(sidx + cur.first + i);
-                    const double mb = __ldg(mass + b);
-                    const double2 x = __ldg(pos + b);
-                    const double tot = __dadd_rn(em, mb);
-                    ex = __ddiv_rn(__dadd_rn(__dmul_rn(em, ex), __dmul_rn(mb, x.x)), tot);
-                    ey = __ddiv_rn(__dadd_rn(__dmul_rn(em, ey), __dmul_rn(mb, x.y)), tot);
-                    em = tot;                      // node[TOTAL_MASS] += mass
+                for (uint32_t i0 = 0; i0 < cur.cnt; i0 += 4) {
+                    uint32_t b[4];
+                    double mb[4];
+                    double2 x[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) b[k] = (i0 + k < cur.cnt) ? __ldg(sidx + cur.first + i0 + k) : 0u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (i0 + k < cur.cnt) { mb[k] = __ldg(mass + b[k]); x[k] = __ldg(pos + b[k]); }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (i0 + k < cur.cnt) {
+                            const double tot = __dadd_rn(em, mb[k]);
+                            ex = __ddiv_rn(__dadd_rn(__dmul_rn(em, ex), __dmul_rn(mb[k], x[k].x)), tot);
+                            ey = __ddiv_rn(__dadd_rn(__dmul_rn(em, ey), __dmul_rn(mb[k], x[k].y)), tot);
+                            em = tot;              // node[TOTAL_MASS] += mass
+                        }
+                    }
                 }
                 cur.m = em; cur.cx = ex; cur.cy = ey;
             } else {                               // summed by heavy_cells_kernel

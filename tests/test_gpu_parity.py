@@ -229,6 +229,38 @@ def test_against_the_reference_gpu_program_on_this_gpu(shipped40k):
             assert rel_rms(p, want) <= tol, (fp64, rel_rms(p, want))
 
 
+@pytest.mark.parametrize("env", [{}, {"BH_KEYS_BISECT": "1"}, {"BH_SNAPSHOT_COPY": "1"}],
+                         ids=["default", "keys_bisect", "snapshot_copy"])
+def test_ab_switches_are_bit_identical(env, monkeypatch):
+    """Default paths (cell keys from the boundary table, out-of-place step from the snapshot) and their
+    A/B fall-backs (per-body FP64 bisection, restore by device copies) give the same bits."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(11)
+    n = 70001
+    pos = rng.uniform(-1, 1, size=(n, 2))
+    pos[: n // 3] = pos[0] + rng.normal(0, 1e-9, size=(n // 3, 2))
+    vel = rng.uniform(-1e-4, 1e-4, size=(n, 2))
+    mass = rng.uniform(0.1, 0.5, size=n)
+    for max_depth in (10, 12, 3):
+        with Simulation(n, max_depth=max_depth) as sim:
+            sim.set_bodies(pos, vel, mass)
+            sim.build_tree()
+            b = oracle.root_bounds(pos)
+            assert np.array_equal(sim.bounds(), b)
+            assert np.array_equal(sim.body_keys(), oracle.body_keys(pos, b, max_depth))
+    with Simulation(n) as a, Simulation(n) as b_:
+        a.set_bodies(pos, vel, mass); b_.set_bodies(pos, vel, mass)
+        a.snapshot()
+        a.step_from_snapshot(2)                 # second step restarts from the snapshot again
+        b_.step(1)
+        for get in ("positions", "velocities", "forces", "accelerations"):
+            assert np.array_equal(getattr(a, get)(), getattr(b_, get)(), equal_nan=True), get
+        a.step(1)                               # and the state it leaves behind is a normal one
+        b_.step(1)
+        assert np.array_equal(a.positions(), b_.positions(), equal_nan=True)
+
+
 def test_graph_and_direct_launch_paths_agree():
     pos, vel, mass, _ = golden_inputs("shipped_2048")
     out = []
