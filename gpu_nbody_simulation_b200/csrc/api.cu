@@ -115,8 +115,13 @@ struct bh_ctx {
     float4* packed = nullptr;     // direct-sum kernel input
     // multi-GPU
     int64_t own_lo = 0, own_hi = 0;
-    uint32_t* own_list = nullptr;  // (unused since the sharded build; kept for ABI-internal stability)
-    uint32_t* own_count = nullptr;
+    // pipelined host step (bh_step_host): bodies in `host_chunks` ranges of original index, each with its own
+    // traversal launch, integrator launch and download, so that downloads overlap the remaining traversals
+    int host_chunks = 4;             // env BH_HOST_CHUNKS (1 = one traversal, one download)
+    uint32_t* chunk_lists = nullptr; // [n] sorted positions, stably partitioned by chunk
+    uint32_t* chunk_counts = nullptr;
+    cudaStream_t dl_stream = nullptr;
+    cudaEvent_t ev_trav[kMaxHostChunks] = {}, ev_vel[kMaxHostChunks] = {}, ev_dl = nullptr;
     uint32_t* perm = nullptr;
     bool renumbered = false;
     double* cell_sums = nullptr;   // [4][finest cells]: count, m, m x, m y — all-reduced every step
@@ -142,7 +147,7 @@ struct bh_ctx {
     uint64_t launches_base = 0;
     bool bodies_set = false, tree_valid = false, have_snapshot = false, timed = false;
     size_t step_zero_bytes = 0;      // see zero_scratch
-    bool keys_bisect = false;        // env BH_KEYS_BISECT=1: per-body FP64 bisection instead of the boundary table
+    bool keys_table = false;         // env BH_KEYS_TABLE=1: cell keys from the boundary table instead of per-body bisection
     bool snapshot_by_copy = false;   // env BH_SNAPSHOT_COPY=1 (A/B switch, see enqueue_step)
     int bounds_grid = 1;
 };
@@ -246,7 +251,7 @@ int enqueue_build(bh_ctx* c, bool full = false, const double2* src = nullptr) {
     if (!sharded) {
         launch_bounds(src, c->d.n, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream);
         launch_keys(src, c->d.n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream, 0,
-                    c->keys_bisect ? nullptr : c->s.cell_bnd);
+                    c->s.cell_bnd);
         prof_mark(c, 1);
         launch_sort(c->keys, c->idx, c->d.n, c->sp, c->s, &c->sorted, c->stream);
         prof_mark(c, 2);
@@ -263,7 +268,7 @@ int enqueue_build(bh_ctx* c, bool full = false, const double2* src = nullptr) {
             launch_bounds_finalize(c->bbox_raw, c->p, c->d, c->s, c->consts, c->stream);
         }
         launch_keys(src + lo, n_own, c->d, c->sp_own, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream,
-                    (uint32_t)lo, c->keys_bisect ? nullptr : c->s.cell_bnd);
+                    (uint32_t)lo, c->s.cell_bnd);
         prof_mark(c, 1);
         launch_sort(c->keys, c->idx, n_own, c->sp_own, c->s, &c->sorted, c->stream);
         prof_mark(c, 2);
@@ -283,13 +288,18 @@ int enqueue_build(bh_ctx* c, bool full = false, const double2* src = nullptr) {
     return check_launch();
 }
 
-int enqueue_forces(bh_ctx* c, bool integrate, const double2* src_pos = nullptr, const double2* src_vel = nullptr) {
+// `list` / `list_n` (optional): evaluate only the bodies at these sorted positions (pipelined host step);
+// the kernel variant is still chosen from the TOTAL body count so that the bits equal a whole-set launch.
+int enqueue_forces(bh_ctx* c, bool integrate, const double2* src_pos = nullptr, const double2* src_vel = nullptr,
+                   const uint32_t* list = nullptr, int64_t list_n = 0) {
     // after a sharded build the sorted list holds exactly this rank's bodies
-    const int64_t n_eval = (c->p.n_ranks > 1 && !c->tree_full) ? (c->own_hi - c->own_lo) : c->d.n;
+    const int64_t n_all = (c->p.n_ranks > 1 && !c->tree_full) ? (c->own_hi - c->own_lo) : c->d.n;
+    bh_params p = c->p;
+    if (list && p.reserved[0] == 0) p.reserved[0] = n_all >= kTwoBodiesPerLaneMin ? 2 : 1;
     launch_traverse(c->keys[c->sorted], c->idx[c->sorted], src_pos ? src_pos : c->pos, src_vel ? src_vel : c->vel,
                     c->pos, c->vel, c->acc, c->force, c->mass, c->d.n,
-                    c->own_lo, c->own_hi, nullptr, nullptr, n_eval, c->p, c->d, c->tree, c->consts, c->s.counters, integrate,
-                    c->stream);
+                    c->own_lo, c->own_hi, list, nullptr, list ? list_n : n_all, p, c->d, c->tree, c->consts, c->s.counters,
+                    integrate, c->stream);
     prof_mark(c, 4);
     return check_launch();
 }
@@ -425,6 +435,10 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     }
     bh_ctx* c = new bh_ctx();
     c->p = *p;
+    // A/B switches (environment, read once per context)
+    { const char* e = getenv("BH_SNAPSHOT_COPY"); c->snapshot_by_copy = e && e[0] == '1'; }
+    { const char* e = getenv("BH_KEYS_TABLE"); c->keys_table = e && e[0] == '1'; }
+    { const char* e = getenv("BH_HOST_CHUNKS"); if (e && atoi(e) >= 1) c->host_chunks = std::min(atoi(e), kMaxHostChunks); }
     if (p->device >= 0) c->device = p->device; else BH_CUDA_OK(cudaGetDevice(&c->device));
     if (c->device >= ndev) { set_error("device %d of %d", c->device, ndev); delete c; return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
@@ -476,7 +490,10 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     BH_ALLOC(c->s.heavy_list, c->d.ncells_finest);
     BH_ALLOC(c->s.huge_list, c->s.max_huge);
     BH_ALLOC(c->s.huge_partial, (size_t)c->s.max_huge * kHugeParts * 3);
-    BH_ALLOC(c->s.cell_bnd, 2 * (((size_t)1 << c->d.finest) + 1));
+    // Cell keys: per-body FP64 bisection by default.  The boundary-table variant (BH_KEYS_TABLE=1, same bits)
+    // measured no faster on B200 at 1M bodies (bounds + keys 38.5 us vs 37.2 us: the key kernel is bound by its
+    // loads and shared-memory histogram atomics, not by the 2 x 9 FP64 bisections), so it stays opt-in.
+    if (c->keys_table) BH_ALLOC(c->s.cell_bnd, 2 * (((size_t)1 << c->d.finest) + 1));
     if (p->n_ranks > 1) {
         BH_ALLOC(c->cell_sums, 4 * c->d.ncells_finest); BH_ALLOC(c->bbox_raw, 4);
     }
@@ -488,12 +505,14 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     for (auto& ev : c->ev_up) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto& ev : c->pev) cudaEventCreate(&ev);
+    cudaStreamCreateWithFlags(&c->dl_stream, cudaStreamNonBlocking);
+    for (auto& ev : c->ev_trav) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (auto& ev : c->ev_vel) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_dl, cudaEventDisableTiming);
     cudaMemsetAsync(c->acc, 0, sizeof(double2) * n, c->stream);
     cudaMemsetAsync(c->force, 0, sizeof(double2) * n, c->stream);
     cudaMemsetAsync(c->tree.count, 0, sizeof(uint32_t) * (np_pad + words + huge_words), c->stream);
     if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { set_error("%s", cudaGetErrorString(e)); return fail(BH_ERR_CUDA); }
-    { const char* e = getenv("BH_SNAPSHOT_COPY"); c->snapshot_by_copy = e && e[0] == '1'; }
-    { const char* e = getenv("BH_KEYS_BISECT"); c->keys_bisect = e && e[0] == '1'; }
     c->launches_base = g_launches;
     *out = c;
     return BH_OK;
@@ -513,12 +532,16 @@ int bh_destroy(bh_ctx* c) {
                     c->keys[1], c->idx[0], c->idx[1], c->consts, c->tree.mass, c->tree.comx, c->tree.comy,
                     c->tree.count /* + scratch + tickets */, c->tree.first, c->tree.flags, c->rec_alloc, c->tree.self_node,
                     c->s.bbox_partial, c->s.heavy_list, c->s.huge_list, c->s.huge_partial, c->s.cell_bnd,
-                    c->packed, c->own_list, c->own_count, c->perm, c->cell_sums, c->bbox_raw};
+                    c->packed, c->chunk_lists, c->chunk_counts, c->perm, c->cell_sums, c->bbox_raw};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (auto& ev : c->pev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->ev_up) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->ev_trav) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->ev_vel) if (ev) cudaEventDestroy(ev);
+    if (c->ev_dl) cudaEventDestroy(c->ev_dl);
+    if (c->dl_stream) cudaStreamDestroy(c->dl_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -667,27 +690,52 @@ int bh_step_host(bh_ctx* c, const double* pos, const double* vel, const double* 
     }
     DeviceGuard g(c->device);
     const int64_t n = c->d.n;
+    // chunks of original body index: every chunk is one traversal launch, one integrator launch and one
+    // contiguous download, so the download of chunk k overlaps the traversal of chunks k+1 ..
+    const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(c->host_chunks, n / 4096));
+    ChunkBounds cb{};
+    cb.n_chunks = nch;
+    for (int k = 0; k <= nch; ++k) cb.lo[k] = (uint32_t)(((__int128)n * k) / nch);
+    if (nch > 1 && !c->chunk_lists) {
+        BH_TRY(dev_alloc(&c->chunk_lists, (size_t)n));
+        BH_TRY(dev_alloc(&c->chunk_counts, (size_t)kMaxHostChunks * ((n + 255) / 256)));
+    }
+    // uploads, in the order the step needs them: positions (bounds, keys), masses (tree), velocities per chunk
     BH_CUDA_OK(cudaMemcpyAsync(c->pos, pos, sizeof(double2) * n, cudaMemcpyHostToDevice, c->copy_stream));
     BH_CUDA_OK(cudaEventRecord(c->ev_up[0], c->copy_stream));
     BH_CUDA_OK(cudaMemcpyAsync(c->mass, mass, sizeof(double) * n, cudaMemcpyHostToDevice, c->copy_stream));
     BH_CUDA_OK(cudaEventRecord(c->ev_up[1], c->copy_stream));
-    BH_CUDA_OK(cudaMemcpyAsync(c->vel, vel, sizeof(double2) * n, cudaMemcpyHostToDevice, c->copy_stream));
-    BH_CUDA_OK(cudaEventRecord(c->ev_up[2], c->copy_stream));
+    for (int k = 0; k < nch; ++k) {
+        const int64_t lo = cb.lo[k], cnt = (int64_t)cb.lo[k + 1] - lo;
+        BH_CUDA_OK(cudaMemcpyAsync(c->vel + lo, vel + 2 * lo, sizeof(double2) * cnt, cudaMemcpyHostToDevice, c->copy_stream));
+        BH_CUDA_OK(cudaEventRecord(c->ev_vel[k], c->copy_stream));
+    }
     BH_CUDA_OK(cudaEventRecord(c->ev0, c->stream));
     zero_scratch(c);
     BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[0], 0));
     launch_bounds(c->pos, n, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream);
-    launch_keys(c->pos, n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream, 0,
-                c->keys_bisect ? nullptr : c->s.cell_bnd);
+    launch_keys(c->pos, n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream, 0, c->s.cell_bnd);
     launch_sort(c->keys, c->idx, n, c->sp, c->s, &c->sorted, c->stream);
+    if (nch > 1) launch_chunk_lists(c->idx[c->sorted], n, cb, c->chunk_counts, c->chunk_lists, c->stream);
     BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[1], 0));
     launch_tree(c->keys[c->sorted], c->idx[c->sorted], c->pos, c->mass, n, c->p, c->d, c->tree, c->s, c->consts, c->stream);
+    c->tree_full = true;
     BH_TRY(check_launch());
-    BH_TRY(enqueue_forces(c, false));             // forces only: velocities may still be in flight
-    BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[2], 0));
-    launch_integrate(c->pos, c->vel, c->acc, c->force, c->mass, 0, n, c->p.dt, c->stream);
-    BH_TRY(check_launch());
-    BH_CUDA_OK(cudaMemcpyAsync(out_pos, c->pos, sizeof(double2) * n, cudaMemcpyDeviceToHost, c->stream));
+    for (int k = 0; k < nch; ++k) {
+        const int64_t lo = cb.lo[k], hi = cb.lo[k + 1];
+        // forces only (velocities may still be in flight); integrator + download on their own stream
+        if (nch > 1) BH_TRY(enqueue_forces(c, false, nullptr, nullptr, c->chunk_lists + lo, hi - lo));
+        else BH_TRY(enqueue_forces(c, false));
+        BH_CUDA_OK(cudaEventRecord(c->ev_trav[k], c->stream));
+        BH_CUDA_OK(cudaStreamWaitEvent(c->dl_stream, c->ev_trav[k], 0));
+        BH_CUDA_OK(cudaStreamWaitEvent(c->dl_stream, c->ev_vel[k], 0));
+        launch_integrate(c->pos, c->vel, c->acc, c->force, c->mass, lo, hi, c->p.dt, c->dl_stream);
+        BH_TRY(check_launch());
+        BH_CUDA_OK(cudaMemcpyAsync(out_pos + 2 * lo, c->pos + lo, sizeof(double2) * (hi - lo), cudaMemcpyDeviceToHost,
+                                   c->dl_stream));
+    }
+    BH_CUDA_OK(cudaEventRecord(c->ev_dl, c->dl_stream));
+    BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_dl, 0));
     BH_CUDA_OK(cudaEventRecord(c->ev1, c->stream));
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
     c->bodies_set = true; c->tree_valid = false; c->timed = true;

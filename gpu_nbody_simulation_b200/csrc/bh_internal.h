@@ -84,6 +84,12 @@ struct Scratch {
     int64_t max_huge;
 };
 
+constexpr int kMaxHostChunks = 8;
+struct ChunkBounds {
+    uint32_t lo[kMaxHostChunks + 1];   // chunk k = bodies [lo[k], lo[k+1])
+    int n_chunks;
+};
+
 constexpr int kMaxPeers = 8;   // GPUs of one NVSwitch box
 
 // Peer-memory exchange (peer_comm.cu): every rank owns one cudaIpc-shared buffer with this layout.
@@ -138,8 +144,10 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
                      unsigned long long* counters, bool integrate, cudaStream_t st);
 void launch_integrate(double2* pos, double2* vel, double2* acc, const double2* force, const double* mass,
                       int64_t lo, int64_t hi, double dt, cudaStream_t st);
-void launch_own_list(const uint32_t* sidx, int64_t n, int64_t lo, int64_t hi, uint32_t* own_list,
-                     uint32_t* own_count, cudaStream_t st);
+// stable partition of the sorted positions by ranges of original body index (pipelined bh_step_host):
+// counts = scratch [n_chunks][ceil(n / 256)], lists = [n]; list k starts at lists[cb.lo[k]]
+void launch_chunk_lists(const uint32_t* sidx, int64_t n, const ChunkBounds& cb, uint32_t* counts, uint32_t* lists,
+                        cudaStream_t st);
 void launch_direct(const double2* pos, const double* mass, int64_t n, double G, float4* packed,
                    double2* force, cudaStream_t st);
 int measure_fp32_peak(int device, double* tflops, double* mhz);

@@ -195,9 +195,10 @@ __device__ __forceinline__ uint32_t locate_cell(double x, double x0, double inv_
 }
 
 // One thread per body.  Also accumulates the radix digit histograms of all passes.
-// TABLE = true (default): finest cell by lookup in the boundary table written by the bounds kernel
-// (2 multiplies + ~4 compares per body instead of 2 x F dependent FP64 bisections); TABLE = false
-// (BH_KEYS_BISECT=1): the descent itself.  Both are bit-exact restatements of project.cu:348-356.
+// TABLE = false (default): the descent itself.  TABLE = true (BH_KEYS_TABLE=1): finest cell by lookup in
+// the boundary table written by the bounds kernel (2 multiplies + ~4 compares per body instead of 2 x F
+// dependent FP64 bisections; measured no faster on B200).  Both are bit-exact restatements of
+// project.cu:348-356.
 template <bool TABLE>
 __global__ void __launch_bounds__(256)
 keys_kernel(const double2* __restrict__ pos, int64_t n, int finest, const StepConsts* __restrict__ consts,

@@ -524,26 +524,88 @@ integrate_kernel(double2* __restrict__ pos, double2* __restrict__ vel, double2* 
     pos[i] = x;
 }
 
-// Multi-GPU: sorted positions whose body index lies in [lo, hi), order preserved inside a block.
+// ---- chunk lists for the pipelined host step (bh_step_host) ----------------------------------------
+// The bodies are split into n_chunks contiguous ranges of ORIGINAL index (so that every range's results
+// are one contiguous device-to-host copy); list k holds the sorted positions of the bodies of range k, in
+// sorted (Morton) order — a stable partition of 0 .. n-1, built by count / scan / scatter so that a
+// traversal warp still gets spatially neighbouring bodies.  List k starts at lists[lo[k]] (range k has
+// exactly lo[k+1] - lo[k] bodies).
+__device__ __forceinline__ int chunk_of(uint32_t body, const ChunkBounds& cb) {
+    int c = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxHostChunks; ++k) c += (k < cb.n_chunks && body >= cb.lo[k]);
+    return c;
+}
+
 __global__ void __launch_bounds__(256)
-own_list_kernel(const uint32_t* __restrict__ sidx, int64_t n, uint32_t lo, uint32_t hi,
-                uint32_t* __restrict__ own_list, uint32_t* __restrict__ own_count) {
-    __shared__ uint32_t s_w[8];
-    __shared__ uint32_t s_base;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool mine = false;
-    if (j < n) { uint32_t b = sidx[j]; mine = b >= lo && b < hi; }
-    uint32_t m = __ballot_sync(0xffffffffu, mine);
-    if (lane == 0) s_w[warp] = __popc(m);
+chunk_count_kernel(const uint32_t* __restrict__ sidx, int64_t n, const __grid_constant__ ChunkBounds cb,
+                   uint32_t* __restrict__ counts, int nblocks) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (j < n) ? chunk_of(sidx[j], cb) : -1;
+    for (int k = 0; k < cb.n_chunks; ++k) {
+        const int cnt = __syncthreads_count(c == k);
+        if (threadIdx.x == 0) counts[(size_t)k * nblocks + blockIdx.x] = (uint32_t)cnt;
+    }
+}
+
+// exclusive scan of every row of counts[n_chunks][nblocks]; one block per row
+__global__ void __launch_bounds__(1024)
+chunk_scan_kernel(uint32_t* __restrict__ counts, int nblocks) {
+    uint32_t* row = counts + (size_t)blockIdx.x * nblocks;
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0;
-        for (int w = 0; w < 8; ++w) { uint32_t c = s_w[w]; s_w[w] = tot; tot += c; }
-        s_base = tot ? atomicAdd(own_count, tot) : 0u;
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int i = base + tid;
+        const uint32_t v = (i < nblocks) ? row[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = s_warp[lane];
+            uint32_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += u;
+            }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        const uint32_t excl = s_carry + s_warp[warp] + inc - v;
+        if (i < nblocks) row[i] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+chunk_scatter_kernel(const uint32_t* __restrict__ sidx, int64_t n, const __grid_constant__ ChunkBounds cb,
+                     const uint32_t* __restrict__ offsets, int nblocks, uint32_t* __restrict__ lists) {
+    __shared__ uint32_t s_w[kMaxHostChunks][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (j < n) ? chunk_of(sidx[j], cb) : -1;
+    uint32_t mine = 0;
+    for (int k = 0; k < cb.n_chunks; ++k) {
+        const uint32_t m = __ballot_sync(0xffffffffu, c == k);
+        if (lane == 0) s_w[k][warp] = __popc(m);
+        if (c == k) mine = m;
     }
     __syncthreads();
-    if (mine) own_list[s_base + s_w[warp] + __popc(m & ((1u << lane) - 1u))] = (uint32_t)j;
+    if (c >= 0) {
+        uint32_t pre = 0;
+        for (int w = 0; w < warp; ++w) pre += s_w[c][w];
+        lists[cb.lo[c] + offsets[(size_t)c * nblocks + blockIdx.x] + pre + __popc(mine & ((1u << lane) - 1u))] = (uint32_t)j;
+    }
 }
 
 }  // namespace
@@ -603,11 +665,13 @@ void launch_integrate(double2* pos, double2* vel, double2* acc, const double2* f
     ++g_launches;
 }
 
-void launch_own_list(const uint32_t* sidx, int64_t n, int64_t lo, int64_t hi, uint32_t* own_list,
-                     uint32_t* own_count, cudaStream_t st) {
-    own_list_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sidx, n, (uint32_t)lo, (uint32_t)hi, own_list,
-                                                                 own_count);
-    ++g_launches;
+void launch_chunk_lists(const uint32_t* sidx, int64_t n, const ChunkBounds& cb, uint32_t* counts, uint32_t* lists,
+                        cudaStream_t st) {
+    const int nblocks = (int)((n + 255) / 256);
+    chunk_count_kernel<<<nblocks, 256, 0, st>>>(sidx, n, cb, counts, nblocks);
+    chunk_scan_kernel<<<cb.n_chunks, 1024, 0, st>>>(counts, nblocks);
+    chunk_scatter_kernel<<<nblocks, 256, 0, st>>>(sidx, n, cb, counts, nblocks, lists);
+    g_launches += 3;
 }
 
 }  // namespace bh

@@ -28,6 +28,8 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <new>
+#include <vector>
 
 namespace {
 
@@ -44,7 +46,13 @@ void* worker(void* arg) {
     auto masses = std::make_unique<Masses>();
     auto pos0 = std::make_unique<Positions>();
     auto vel0 = std::make_unique<Velocities>();
-    auto positions = std::make_unique<Positions>();
+    // TraverseTreeToFile indexes positions[] with the NEGATIVE encoded occupant of cap-level leaves
+    // (project.cu:514-518): it reads up to (N + 1) entries BELOW the array.  In the reference
+    // that memory is main's stack frame (the other arrays); here the array sits in the upper half of a
+    // zero-filled arena so that the same out-of-bounds reads stay inside mapped memory.
+    std::vector<char> arena(2 * sizeof(Positions) + 64, 0);
+    static_assert(alignof(Positions) <= 16 && (sizeof(Positions) + 64) % 16 == 0, "arena offset keeps the alignment");
+    Positions* positions = new (arena.data() + sizeof(Positions) + 64) Positions();
     FILE* fi = fopen(job->in, "rb");
     if (!fi) { perror(job->in); job->rc = 1; return nullptr; }
     uint64_t n_in = 0;

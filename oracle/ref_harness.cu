@@ -33,6 +33,8 @@
 #include <cstring>
 #include <cstdint>
 #include <memory>
+#include <new>
+#include <vector>
 
 static void put(FILE* f, const char* name, uint64_t step, const double* d, uint64_t n) {
     if (!f) return;
@@ -63,7 +65,12 @@ int main(int argc, char** argv) {
     const size_t N = N_BODIES;
     // heap, not stack: the reference keeps these in main's frame (project.cu:1055-1057)
     auto masses = std::make_unique<Masses>();
-    auto positions = std::make_unique<Positions>();
+    // TraverseTreeToFile indexes positions[] with the NEGATIVE encoded occupant of cap-level leaves
+    // (project.cu:514-518), i.e. it reads up to (N + 1) entries BELOW the array: keep the array
+    // in the upper half of a zero-filled arena so that those reads stay inside mapped memory.
+    std::vector<char> arena(2 * sizeof(Positions) + 64, 0);
+    static_assert(alignof(Positions) <= 16 && (sizeof(Positions) + 64) % 16 == 0, "arena offset keeps the alignment");
+    Positions* positions = new (arena.data() + sizeof(Positions) + 64) Positions();
     auto velocities = std::make_unique<Velocities>();
     auto accelerations = std::make_unique<Accelerations>();
     auto forces = std::make_unique<Forces>();

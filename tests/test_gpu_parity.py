@@ -229,8 +229,8 @@ def test_against_the_reference_gpu_program_on_this_gpu(shipped40k):
             assert rel_rms(p, want) <= tol, (fp64, rel_rms(p, want))
 
 
-@pytest.mark.parametrize("env", [{}, {"BH_KEYS_BISECT": "1"}, {"BH_SNAPSHOT_COPY": "1"}],
-                         ids=["default", "keys_bisect", "snapshot_copy"])
+@pytest.mark.parametrize("env", [{}, {"BH_KEYS_TABLE": "1"}, {"BH_SNAPSHOT_COPY": "1"}],
+                         ids=["default", "keys_table", "snapshot_copy"])
 def test_ab_switches_are_bit_identical(env, monkeypatch):
     """Default paths (cell keys from the boundary table, out-of-place step from the snapshot) and their
     A/B fall-backs (per-body FP64 bisection, restore by device copies) give the same bits."""

@@ -1,0 +1,34 @@
+#!/usr/bin/env bash
+# One-GPU validation pass (run under gpurun): parity tests, smoke, bench (default paths and the A/B
+# fall-backs), the reference GPU program baseline, and the ncu launch list of the bench command.
+# Everything lands in gpurun_out/.
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader > gpurun_out/smi.txt 2>&1
+( timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15; echo "rc=${PIPESTATUS[0]}" ) > gpurun_out/pytest.log
+( timeout 120 python __graft_entry__.py smoke 2>&1 | tail -5; echo "smoke rc=${PIPESTATUS[0]}" ) > gpurun_out/smoke.log
+timeout 400 python bench.py > gpurun_out/bench_default.log 2> gpurun_out/bench_default.err
+BH_SNAPSHOT_COPY=1 timeout 200 python bench.py --steps 100 --no-cpu-baseline --no-gpu-baseline \
+    > gpurun_out/bench_oldpaths.log 2>&1
+BH_SNAPSHOT_COPY=1 timeout 200 python bench.py --steps 100 --no-cpu-baseline --no-gpu-baseline \
+    > gpurun_out/bench_snapcopy.log 2>&1
+BH_KEYS_TABLE=1 timeout 200 python bench.py --steps 100 --no-cpu-baseline --no-gpu-baseline \
+    > gpurun_out/bench_keytable.log 2>&1
+timeout 200 python tools/ref_gpu_report.py > gpurun_out/ref_gpu_report.json 2> gpurun_out/ref_gpu_report.err
+if [ "${1:-}" = "ncu" ]; then
+    timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+        --log-file gpurun_out/launches_bench.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-baseline \
+        > gpurun_out/ncu_bench.log 2>&1
+fi
+tail -3 gpurun_out/pytest.log; cat gpurun_out/smoke.log
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/bench_*.log")):
+    for ln in open(f):
+        if ln.startswith("{"):
+            d = json.loads(ln)
+            r = d.get("roofline") or {}
+            print(f.split("/")[-1], round(d["value"] / 1e9, 3), "G/s", round(d["ms_per_step"], 4), "ms e2e",
+                  round(d["e2e"]["value"] / 1e9, 3), d.get("phases_us"), (d.get("gpu_baseline") or {}).get("value"),
+                  d["clocks"])
+PY
