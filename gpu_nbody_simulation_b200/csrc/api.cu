@@ -17,6 +17,7 @@
 namespace bh {
 
 thread_local uint64_t g_launches = 0;
+thread_local bool g_pdl = false;
 static thread_local char g_err[1024] = "";
 
 void set_error(const char* fmt, ...) {
@@ -147,6 +148,7 @@ struct bh_ctx {
     uint64_t launches_base = 0;
     bool bodies_set = false, tree_valid = false, have_snapshot = false, timed = false;
     size_t step_zero_bytes = 0;      // see zero_scratch
+    bool pdl = false;                // env BH_PDL=1: programmatic dependent launch along the single-GPU chain
     bool keys_table = false;         // env BH_KEYS_TABLE=1: cell keys from the boundary table instead of per-body bisection
     bool snapshot_by_copy = false;   // env BH_SNAPSHOT_COPY=1 (A/B switch, see enqueue_step)
     int bounds_grid = 1;
@@ -245,6 +247,7 @@ int allreduce_f64(bh_ctx* c, double* buf, size_t count, ncclRedOp_t op) {
 // so no restore copy is needed).
 int enqueue_build(bh_ctx* c, bool full = false, const double2* src = nullptr) {
     if (!src) src = c->pos;
+    g_pdl = c->pdl;
     zero_scratch(c);
     prof_mark(c, 0);
     const bool sharded = c->p.n_ranks > 1 && !full;
@@ -294,6 +297,7 @@ int enqueue_forces(bh_ctx* c, bool integrate, const double2* src_pos = nullptr, 
                    const uint32_t* list = nullptr, int64_t list_n = 0) {
     // after a sharded build the sorted list holds exactly this rank's bodies
     const int64_t n_all = (c->p.n_ranks > 1 && !c->tree_full) ? (c->own_hi - c->own_lo) : c->d.n;
+    g_pdl = c->pdl;
     bh_params p = c->p;
     if (list && p.reserved[0] == 0) p.reserved[0] = n_all >= kTwoBodiesPerLaneMin ? 2 : 1;
     launch_traverse(c->keys[c->sorted], c->idx[c->sorted], src_pos ? src_pos : c->pos, src_vel ? src_vel : c->vel,
@@ -438,6 +442,7 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     // A/B switches (environment, read once per context)
     { const char* e = getenv("BH_SNAPSHOT_COPY"); c->snapshot_by_copy = e && e[0] == '1'; }
     { const char* e = getenv("BH_KEYS_TABLE"); c->keys_table = e && e[0] == '1'; }
+    { const char* e = getenv("BH_PDL"); c->pdl = e && e[0] == '1' && p->n_ranks == 1; }
     { const char* e = getenv("BH_HOST_CHUNKS"); if (e && atoi(e) >= 1) c->host_chunks = std::min(atoi(e), kMaxHostChunks); }
     if (p->device >= 0) c->device = p->device; else BH_CUDA_OK(cudaGetDevice(&c->device));
     if (c->device >= ndev) { set_error("device %d of %d", c->device, ndev); delete c; return BH_ERR_INVALID; }
@@ -711,6 +716,7 @@ int bh_step_host(bh_ctx* c, const double* pos, const double* vel, const double* 
         BH_CUDA_OK(cudaEventRecord(c->ev_vel[k], c->copy_stream));
     }
     BH_CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+    g_pdl = false;   // event waits sit between the kernels of this path: plain launches
     zero_scratch(c);
     BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[0], 0));
     launch_bounds(c->pos, n, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream);

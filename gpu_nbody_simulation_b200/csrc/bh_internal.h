@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <utility>
 
 #include "../../include/bh.h"
 
@@ -154,6 +155,35 @@ int measure_fp32_peak(int device, double* tflops, double* mhz);
 
 int traverse_launch_count();
 extern thread_local uint64_t g_launches;  // kernels launched by this library on this thread
+
+// Programmatic dependent launch (env BH_PDL=1, set per call by the API layer): the kernels of the
+// single-GPU step chain (keys -> sort passes -> cell runs -> heavy / huge cells -> levels -> traversal) are
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization.  Each of them starts with
+// pdl_entry(): `griddepcontrol.launch_dependents` lets the NEXT kernel's blocks be scheduled as soon as
+// all blocks of this one are resident, `griddepcontrol.wait` then holds them until the PREVIOUS kernel
+// has completed and flushed — so launch latency and block scheduling overlap the predecessor's tail
+// while every memory dependency is kept (completion is transitive along the chain).  Both instructions
+// are no-ops in a kernel launched without the attribute.
+extern thread_local bool g_pdl;
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_entry() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+// Launch `kernel`; after_kernel = the previous operation on `st` is one of this library's chain kernels.
+template <typename... KArgs, typename... Args>
+inline void launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, bool after_kernel,
+                         Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (g_pdl && after_kernel) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 void set_error(const char* fmt, ...);
 #define BH_CUDA_OK(expr)                                                                          \

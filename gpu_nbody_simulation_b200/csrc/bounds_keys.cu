@@ -87,6 +87,7 @@ bounds_kernel(const double2* __restrict__ pos, int64_t n, double* __restrict__ p
               uint32_t* __restrict__ ticket, StepConsts* __restrict__ consts, double pad_frac,
               double pad_fallback, double theta, double dist_eps, int finest, double* __restrict__ raw_out,
               double* __restrict__ cell_bnd, const __grid_constant__ PeerComm pc) {
+    pdl_entry();
     double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double2 p = pos[i];
@@ -205,6 +206,7 @@ keys_kernel(const double2* __restrict__ pos, int64_t n, int finest, const StepCo
             uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ digit_hist,
             int passes, int bits_per_pass, uint32_t idx_base, const double* __restrict__ cell_bnd) {
     __shared__ uint32_t hist[kMaxSortPasses * kMaxBins];
+    pdl_entry();
     for (int i = threadIdx.x; i < passes * kMaxBins; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     const double bx0 = consts->xmin, bx1 = consts->xmax, by0 = consts->ymin, by1 = consts->ymax;
@@ -273,11 +275,11 @@ void launch_keys(const double2* pos, int64_t n, const Dims& d, const SortPlan& s
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     if (cell_bnd)
-        keys_kernel<true><<<(int)blocks, 256, 0, st>>>(pos, n, d.finest, consts, keys, idx, digit_hist, sp.passes,
-                                                       sp.bits_per_pass, idx_base, cell_bnd);
+        launch_chain(keys_kernel<true>, dim3((unsigned)blocks), dim3(256), st, true, pos, n, d.finest, consts, keys, idx,
+                     digit_hist, sp.passes, sp.bits_per_pass, idx_base, cell_bnd);
     else
-        keys_kernel<false><<<(int)blocks, 256, 0, st>>>(pos, n, d.finest, consts, keys, idx, digit_hist, sp.passes,
-                                                        sp.bits_per_pass, idx_base, nullptr);
+        launch_chain(keys_kernel<false>, dim3((unsigned)blocks), dim3(256), st, true, pos, n, d.finest, consts, keys, idx,
+                     digit_hist, sp.passes, sp.bits_per_pass, idx_base, (const double*)nullptr);
     ++g_launches;
 }
 

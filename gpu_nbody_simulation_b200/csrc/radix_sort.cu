@@ -37,6 +37,7 @@ onesweep_pass(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__
     __shared__ uint32_t s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_entry();
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     for (int i = tid; i < NWARPS * NBINS; i += kSortThreads) (&s_warp[0][0])[i] = 0;
     __syncthreads();
@@ -192,11 +193,13 @@ void launch_sort(uint32_t* keys[2], uint32_t* vals[2], int64_t n, const SortPlan
         const uint32_t* hist = s.digit_hist + (size_t)pass * kMaxBins;
         int shift = pass * sp.bits_per_pass;
         if (sp.nbins_log2 == 9)
-            onesweep_pass<9><<<sp.ntiles, kSortThreads, 0, st>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
-                                                                 shift, sp.bits_per_pass, hist, state, s.tickets + pass);
+            launch_chain(onesweep_pass<9>, dim3(sp.ntiles), dim3(kSortThreads), st, true, (const uint32_t*)keys[cur],
+                         (const uint32_t*)vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, sp.bits_per_pass, hist, state,
+                         s.tickets + pass);
         else
-            onesweep_pass<8><<<sp.ntiles, kSortThreads, 0, st>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n,
-                                                                 shift, sp.bits_per_pass, hist, state, s.tickets + pass);
+            launch_chain(onesweep_pass<8>, dim3(sp.ntiles), dim3(kSortThreads), st, true, (const uint32_t*)keys[cur],
+                         (const uint32_t*)vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, sp.bits_per_pass, hist, state,
+                         s.tickets + pass);
         ++g_launches;
         cur ^= 1;
     }

@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(kTravThreads, (BPL == 1 ? BH_GENERIC_MIN_BLOCK
 traverse_f32_kernel(const __grid_constant__ TravArgs a) {
     using SE = StackEntry<BPL>;
     __shared__ __align__(16) uint8_t s_stack[kTravWarps][kStackCap * SE::kBytes];
+    pdl_entry();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t warp_slot0 = ((int64_t)blockIdx.x * kTravWarps + warp) * (32 * BPL);
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&s_stack[warp][0]);
@@ -301,6 +302,7 @@ __global__ void __launch_bounds__(kTravThreads, kPairMinBlocks * (256 / kTravThr
 traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
     using SE = StackEntry<2>;
     __shared__ __align__(16) uint8_t s_stack[kTravWarps][kStackCap * SE::kBytes];
+    pdl_entry();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t warp_slot0 = ((int64_t)blockIdx.x * kTravWarps + warp) * 64;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&s_stack[warp][0]);
@@ -421,6 +423,7 @@ template <bool INTEGRATE, bool COUNT>
 __global__ void __launch_bounds__(kTravThreads)
 traverse_f64_kernel(const __grid_constant__ TravArgs a) {
     __shared__ uint2 s_stack[kTravWarps][kStackCap];
+    pdl_entry();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t slot = ((int64_t)blockIdx.x * kTravWarps + warp) * 32 + lane;
     const bool live = slot < a.n_slots;
@@ -630,22 +633,20 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
     // two bodies per lane halve the node traffic and the control overhead per body, but need >= ~400k
     // bodies to keep every SM's warp slots full (ncu: profiles/r01_traverse_v4_*)
     const int bpl = (p.reserved[0] == 1) ? 1 : (p.reserved[0] == 2 || p.reserved[0] == 3) ? 2 : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
+    // previous operation on the stream = tree_top_kernel (or a peer-exchange kernel; g_pdl is off there)
+#define BH_GO(K) launch_chain(K, dim3(blocks), dim3(kTravThreads), st, true, a)
     if (fp64) {
         unsigned blocks = (unsigned)((own_n + kTravThreads - 1) / kTravThreads);
-        if (integrate) { if (count) traverse_f64_kernel<true, true><<<blocks, kTravThreads, 0, st>>>(a);
-                         else traverse_f64_kernel<true, false><<<blocks, kTravThreads, 0, st>>>(a); }
-        else { if (count) traverse_f64_kernel<false, true><<<blocks, kTravThreads, 0, st>>>(a);
-               else traverse_f64_kernel<false, false><<<blocks, kTravThreads, 0, st>>>(a); }
+        if (integrate) { if (count) BH_GO((traverse_f64_kernel<true, true>)); else BH_GO((traverse_f64_kernel<true, false>)); }
+        else { if (count) BH_GO((traverse_f64_kernel<false, true>)); else BH_GO((traverse_f64_kernel<false, false>)); }
     } else {
         const int64_t per_block = (int64_t)kTravThreads * bpl;
         unsigned blocks = (unsigned)((own_n + per_block - 1) / per_block);
-#define BH_TRAV(B, I, C) traverse_f32_kernel<B, I, C><<<blocks, kTravThreads, 0, st>>>(a)
+#define BH_TRAV(B, I, C) BH_GO((traverse_f32_kernel<B, I, C>))
         if (bpl == 2 && !count && p.reserved[0] != 3) {
             const bool exact = p.flags & BH_FLAG_EXACT_EPS;
-            if (integrate) { if (exact) traverse_f32_pair_kernel<true, true><<<blocks, kTravThreads, 0, st>>>(a);
-                             else traverse_f32_pair_kernel<true, false><<<blocks, kTravThreads, 0, st>>>(a); }
-            else { if (exact) traverse_f32_pair_kernel<false, true><<<blocks, kTravThreads, 0, st>>>(a);
-                   else traverse_f32_pair_kernel<false, false><<<blocks, kTravThreads, 0, st>>>(a); }
+            if (integrate) { if (exact) BH_GO((traverse_f32_pair_kernel<true, true>)); else BH_GO((traverse_f32_pair_kernel<true, false>)); }
+            else { if (exact) BH_GO((traverse_f32_pair_kernel<false, true>)); else BH_GO((traverse_f32_pair_kernel<false, false>)); }
         } else if (bpl == 2) {
             if (integrate) { if (count) BH_TRAV(2, true, true); else BH_TRAV(2, true, false); }
             else { if (count) BH_TRAV(2, false, true); else BH_TRAV(2, false, false); }
@@ -655,6 +656,7 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
         }
 #undef BH_TRAV
     }
+#undef BH_GO
     ++g_launches;
 }
 

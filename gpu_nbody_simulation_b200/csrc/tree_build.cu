@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(256)
 cell_runs_kernel(const uint32_t* __restrict__ skeys, int64_t n, uint32_t* __restrict__ cnt_f,
                  uint32_t* __restrict__ first_f, uint32_t exact_leaf_max, uint32_t* __restrict__ heavy_list,
                  uint32_t* __restrict__ heavy_count) {
+    pdl_entry();
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool in = j < n;
@@ -180,6 +181,7 @@ heavy_cells_kernel(const uint32_t* __restrict__ heavy_list, const uint32_t* __re
                    double* __restrict__ cy_f, bool raw_sums, uint32_t* __restrict__ huge_list,
                    uint32_t* __restrict__ huge_count) {
     __shared__ double sm[3][256];
+    pdl_entry();
     const uint32_t nheavy = *heavy_count;
     for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
         const uint32_t cell = heavy_list[h];
@@ -210,6 +212,7 @@ huge_cells_kernel(const uint32_t* __restrict__ huge_list, const uint32_t* __rest
                   uint32_t* __restrict__ tickets) {
     __shared__ double sm[3][256];
     __shared__ bool last;
+    pdl_entry();
     const uint32_t nhuge = *huge_count;
     const uint32_t p = blockIdx.x;
     for (uint32_t h = blockIdx.y; h < nhuge; h += gridDim.y) {
@@ -293,6 +296,7 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
                    const double* __restrict__ mass, double G0, double mass_eps, uint32_t exact_leaf_max,
                    unsigned long long* __restrict__ counters, const StepConsts* __restrict__ consts,
                    const double* __restrict__ sums) {
+    pdl_entry();
     const int F = d.finest;
     const double scale = consts->scale;
     const double G = G0 * scale * scale;
@@ -424,6 +428,7 @@ __global__ void __launch_bounds__(1024)
 tree_top_kernel(TreeArrays t, Dims d, int top_level, const uint32_t* __restrict__ sidx,
                 const double2* __restrict__ pos, const double* __restrict__ mass, double G0, double mass_eps,
                 unsigned long long* __restrict__ counters, const StepConsts* __restrict__ consts) {
+    pdl_entry();
     const int F = d.finest;
     const double scale = consts->scale;
     const double G = G0 * scale * scale;
@@ -469,8 +474,8 @@ void launch_tree_runs(const uint32_t* skeys, const uint32_t* sidx, const double2
     const uint64_t nc = d.ncells_finest;
     uint32_t exact_max = (uint32_t)(p.exact_leaf_max < 0 ? 0 : p.exact_leaf_max);
     if (n > 0) {
-        cell_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(skeys, n, cnt_f, first_f, exact_max, s.heavy_list,
-                                                                      s.heavy_count);
+        launch_chain(cell_runs_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), st, true, skeys, n, cnt_f, first_f,
+                     exact_max, s.heavy_list, s.heavy_count);
         ++g_launches;
     }
     if (sums) {
@@ -484,13 +489,15 @@ void launch_tree_runs(const uint32_t* skeys, const uint32_t* sidx, const double2
                                                                           sums);
         ++g_launches;
     } else {
-        heavy_cells_kernel<<<148 * 4, 256, 0, st>>>(s.heavy_list, s.heavy_count, cnt_f, first_f, sidx, pos, mass,
-                                                    t.mass + d.level_off[F], t.comx + d.level_off[F],
-                                                    t.comy + d.level_off[F], false, s.huge_list, s.huge_count);
-        huge_cells_kernel<<<dim3(kHugeParts, 16), 256, 0, st>>>(s.huge_list, s.huge_count, cnt_f, first_f, sidx, pos, mass,
-                                                                t.mass + d.level_off[F], t.comx + d.level_off[F],
-                                                                t.comy + d.level_off[F], false, s.huge_partial,
-                                                                s.huge_tickets);
+        // (n > 0 here: the previous operation on the stream is cell_runs_kernel)
+        launch_chain(heavy_cells_kernel, dim3(148 * 4), dim3(256), st, n > 0, (const uint32_t*)s.heavy_list,
+                     (const uint32_t*)s.heavy_count, (const uint32_t*)cnt_f, (const uint32_t*)first_f, sidx, pos, mass,
+                     t.mass + d.level_off[F], t.comx + d.level_off[F], t.comy + d.level_off[F], false, s.huge_list,
+                     s.huge_count);
+        launch_chain(huge_cells_kernel, dim3(kHugeParts, 16), dim3(256), st, true, (const uint32_t*)s.huge_list,
+                     (const uint32_t*)s.huge_count, (const uint32_t*)cnt_f, (const uint32_t*)first_f, sidx, pos, mass,
+                     t.mass + d.level_off[F], t.comx + d.level_off[F], t.comy + d.level_off[F], false, s.huge_partial,
+                     s.huge_tickets);
         g_launches += 2;
     }
 }
@@ -504,15 +511,16 @@ void launch_tree_levels(const uint32_t* sidx, const double2* pos, const double* 
     unsigned blocks = (unsigned)((d.ncells_finest + kBottomThreads - 1) / kBottomThreads);
     if (sums) tree_bottom_kernel<true><<<blocks, kBottomThreads, 0, st>>>(t, d, sidx, pos, mass, p.G, p.mass_eps, exact_max,
                                                                         s.counters, consts, sums);
-    else tree_bottom_kernel<false><<<blocks, kBottomThreads, 0, st>>>(t, d, sidx, pos, mass, p.G, p.mass_eps, exact_max,
-                                                                    s.counters, consts, nullptr);
+    else launch_chain(tree_bottom_kernel<false>, dim3(blocks), dim3(kBottomThreads), st, true, t, d, sidx, pos, mass, p.G,
+                      p.mass_eps, exact_max, s.counters, consts, (const double*)nullptr);
     ++g_launches;
     int top_level = F - 5;   // bottom kernel covered F .. F-4
     if (F >= 1) {
         if (top_level < 0) top_level = -1;
         // when the bottom kernel already reached the root (F <= 4) only the node count remains
         if (sums) tree_top_kernel<true><<<1, 1024, 0, st>>>(t, d, top_level, sidx, pos, mass, p.G, p.mass_eps, s.counters, consts);
-        else tree_top_kernel<false><<<1, 1024, 0, st>>>(t, d, top_level, sidx, pos, mass, p.G, p.mass_eps, s.counters, consts);
+        else launch_chain(tree_top_kernel<false>, dim3(1), dim3(1024), st, true, t, d, top_level, sidx, pos, mass, p.G,
+                          p.mass_eps, s.counters, consts);
         ++g_launches;
     }
 }

@@ -229,8 +229,9 @@ def test_against_the_reference_gpu_program_on_this_gpu(shipped40k):
             assert rel_rms(p, want) <= tol, (fp64, rel_rms(p, want))
 
 
-@pytest.mark.parametrize("env", [{}, {"BH_KEYS_TABLE": "1"}, {"BH_SNAPSHOT_COPY": "1"}],
-                         ids=["default", "keys_table", "snapshot_copy"])
+@pytest.mark.parametrize("env", [{}, {"BH_KEYS_TABLE": "1"}, {"BH_SNAPSHOT_COPY": "1"}, {"BH_PDL": "1"}, {"BH_PDL": "0"},
+                                 {"BH_HOST_CHUNKS": "1"}, {"BH_HOST_CHUNKS": "3"}],
+                         ids=["default", "keys_table", "snapshot_copy", "pdl_on", "pdl_off", "host_chunks_1", "host_chunks_3"])
 def test_ab_switches_are_bit_identical(env, monkeypatch):
     """Default paths (cell keys from the boundary table, out-of-place step from the snapshot) and their
     A/B fall-backs (per-body FP64 bisection, restore by device copies) give the same bits."""
@@ -259,6 +260,11 @@ def test_ab_switches_are_bit_identical(env, monkeypatch):
         a.step(1)                               # and the state it leaves behind is a normal one
         b_.step(1)
         assert np.array_equal(a.positions(), b_.positions(), equal_nan=True)
+        out = a.step_host(pos, vel, mass)       # pipelined host step (index chunks): same bits as a plain step
+        b_.set_bodies(pos, vel, mass); b_.step(1)
+        assert np.array_equal(out, b_.positions(), equal_nan=True)
+        assert np.array_equal(a.velocities(), b_.velocities(), equal_nan=True)
+        assert np.array_equal(a.forces(), b_.forces(), equal_nan=True)
 
 
 def test_graph_and_direct_launch_paths_agree():
