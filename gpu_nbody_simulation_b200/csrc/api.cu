@@ -122,7 +122,11 @@ struct bh_ctx {
     uint32_t* chunk_lists = nullptr; // [n] sorted positions, stably partitioned by chunk
     uint32_t* chunk_counts = nullptr;
     cudaStream_t dl_stream = nullptr;
-    cudaEvent_t ev_trav[kMaxHostChunks] = {}, ev_vel[kMaxHostChunks] = {}, ev_dl = nullptr;
+    cudaEvent_t ev_trav[kMaxHostChunks] = {}, ev_vel[kMaxHostChunks] = {}, ev_dl = nullptr, ev_fork = nullptr;
+    cudaGraphExec_t host_graph = nullptr;   // bh_step_host captured for one set of (pinned) host pointers
+    const void* host_graph_key[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t host_graph_kernels = 0;
+    bool host_graph_failed = false;
     uint32_t* perm = nullptr;
     bool renumbered = false;
     double* cell_sums = nullptr;   // [4][finest cells]: count, m, m x, m y — all-reduced every step
@@ -398,6 +402,65 @@ int ensure_full_tree(bh_ctx* c) {
     return BH_OK;
 }
 
+bool host_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// One step with host buffers on three streams (all forked from / joined to c->stream, so the sequence can
+// be captured into a graph):
+//   copy_stream : positions, masses, then the velocities chunk by chunk (the order the step needs them)
+//   stream      : bounds, keys, sort, chunk lists, tree, then one forces-only traversal per index chunk
+//   dl_stream   : (high priority) per chunk: integrator as soon as the chunk's forces and velocities are
+//                 there, then the contiguous download of the chunk's new positions — the downloads overlap
+//                 the traversal of the remaining chunks.
+// Chunks are ranges of ORIGINAL body index (contiguous in the caller's arrays); chunk lists keep Morton
+// order inside a chunk (launch_chunk_lists), and per-body results do not depend on the grouping.
+int enqueue_host_step(bh_ctx* c, const double* pos, const double* vel, const double* mass, double* out_pos, int nch) {
+    const int64_t n = c->d.n;
+    ChunkBounds cb{};
+    cb.n_chunks = nch;
+    for (int k = 0; k <= nch; ++k) cb.lo[k] = (uint32_t)(((__int128)n * k) / nch);
+    g_pdl = false;   // event waits sit between the kernels of this path: plain launches
+    BH_CUDA_OK(cudaEventRecord(c->ev_fork, c->stream));
+    BH_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_fork, 0));
+    BH_CUDA_OK(cudaMemcpyAsync(c->pos, pos, sizeof(double2) * n, cudaMemcpyHostToDevice, c->copy_stream));
+    BH_CUDA_OK(cudaEventRecord(c->ev_up[0], c->copy_stream));
+    BH_CUDA_OK(cudaMemcpyAsync(c->mass, mass, sizeof(double) * n, cudaMemcpyHostToDevice, c->copy_stream));
+    BH_CUDA_OK(cudaEventRecord(c->ev_up[1], c->copy_stream));
+    for (int k = 0; k < nch; ++k) {
+        const int64_t lo = cb.lo[k], cnt = (int64_t)cb.lo[k + 1] - lo;
+        BH_CUDA_OK(cudaMemcpyAsync(c->vel + lo, vel + 2 * lo, sizeof(double2) * cnt, cudaMemcpyHostToDevice, c->copy_stream));
+        BH_CUDA_OK(cudaEventRecord(c->ev_vel[k], c->copy_stream));
+    }
+    zero_scratch(c);
+    BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[0], 0));
+    launch_bounds(c->pos, n, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream);
+    launch_keys(c->pos, n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream, 0, c->s.cell_bnd);
+    launch_sort(c->keys, c->idx, n, c->sp, c->s, &c->sorted, c->stream);
+    if (nch > 1) launch_chunk_lists(c->idx[c->sorted], n, cb, c->chunk_counts, c->chunk_lists, c->stream);
+    BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[1], 0));
+    launch_tree(c->keys[c->sorted], c->idx[c->sorted], c->pos, c->mass, n, c->p, c->d, c->tree, c->s, c->consts, c->stream);
+    c->tree_full = true;
+    BH_TRY(check_launch());
+    for (int k = 0; k < nch; ++k) {
+        const int64_t lo = cb.lo[k], hi = cb.lo[k + 1];
+        if (nch > 1) BH_TRY(enqueue_forces(c, false, nullptr, nullptr, c->chunk_lists + lo, hi - lo));
+        else BH_TRY(enqueue_forces(c, false));
+        BH_CUDA_OK(cudaEventRecord(c->ev_trav[k], c->stream));
+        BH_CUDA_OK(cudaStreamWaitEvent(c->dl_stream, c->ev_trav[k], 0));
+        BH_CUDA_OK(cudaStreamWaitEvent(c->dl_stream, c->ev_vel[k], 0));
+        launch_integrate(c->pos, c->vel, c->acc, c->force, c->mass, lo, hi, c->p.dt, c->dl_stream);
+        BH_TRY(check_launch());
+        BH_CUDA_OK(cudaMemcpyAsync(out_pos + 2 * lo, c->pos + lo, sizeof(double2) * (hi - lo), cudaMemcpyDeviceToHost,
+                                   c->dl_stream));
+    }
+    BH_CUDA_OK(cudaEventRecord(c->ev_dl, c->dl_stream));
+    BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_dl, 0));
+    return BH_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -510,7 +573,12 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     for (auto& ev : c->ev_up) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto& ev : c->pev) cudaEventCreate(&ev);
-    cudaStreamCreateWithFlags(&c->dl_stream, cudaStreamNonBlocking);
+    {   // integrator + downloads of the pipelined host step must not queue behind the next chunk's traversal blocks
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        cudaStreamCreateWithPriority(&c->dl_stream, cudaStreamNonBlocking, greatest);
+    }
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     for (auto& ev : c->ev_trav) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto& ev : c->ev_vel) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_dl, cudaEventDisableTiming);
@@ -546,6 +614,8 @@ int bh_destroy(bh_ctx* c) {
     for (auto& ev : c->ev_trav) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->ev_vel) if (ev) cudaEventDestroy(ev);
     if (c->ev_dl) cudaEventDestroy(c->ev_dl);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->host_graph) cudaGraphExecDestroy(c->host_graph);
     if (c->dl_stream) cudaStreamDestroy(c->dl_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -695,56 +765,49 @@ int bh_step_host(bh_ctx* c, const double* pos, const double* vel, const double* 
     }
     DeviceGuard g(c->device);
     const int64_t n = c->d.n;
-    // chunks of original body index: every chunk is one traversal launch, one integrator launch and one
-    // contiguous download, so the download of chunk k overlaps the traversal of chunks k+1 ..
     const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(c->host_chunks, n / 4096));
-    ChunkBounds cb{};
-    cb.n_chunks = nch;
-    for (int k = 0; k <= nch; ++k) cb.lo[k] = (uint32_t)(((__int128)n * k) / nch);
     if (nch > 1 && !c->chunk_lists) {
         BH_TRY(dev_alloc(&c->chunk_lists, (size_t)n));
         BH_TRY(dev_alloc(&c->chunk_counts, (size_t)kMaxHostChunks * ((n + 255) / 256)));
     }
-    // uploads, in the order the step needs them: positions (bounds, keys), masses (tree), velocities per chunk
-    BH_CUDA_OK(cudaMemcpyAsync(c->pos, pos, sizeof(double2) * n, cudaMemcpyHostToDevice, c->copy_stream));
-    BH_CUDA_OK(cudaEventRecord(c->ev_up[0], c->copy_stream));
-    BH_CUDA_OK(cudaMemcpyAsync(c->mass, mass, sizeof(double) * n, cudaMemcpyHostToDevice, c->copy_stream));
-    BH_CUDA_OK(cudaEventRecord(c->ev_up[1], c->copy_stream));
-    for (int k = 0; k < nch; ++k) {
-        const int64_t lo = cb.lo[k], cnt = (int64_t)cb.lo[k + 1] - lo;
-        BH_CUDA_OK(cudaMemcpyAsync(c->vel + lo, vel + 2 * lo, sizeof(double2) * cnt, cudaMemcpyHostToDevice, c->copy_stream));
-        BH_CUDA_OK(cudaEventRecord(c->ev_vel[k], c->copy_stream));
+    // With pinned host buffers the whole call (3 streams: uploads, compute, integrate + downloads) is captured
+    // once into a CUDA graph keyed by the four host pointers and replayed: one launch instead of ~40 API calls.
+    const void* key[4] = {pos, vel, mass, out_pos};
+    bool use_graph = !(c->p.flags & BH_FLAG_NO_GRAPH) && !c->host_graph_failed && host_pinned(pos) && host_pinned(vel) &&
+                     host_pinned(mass) && host_pinned(out_pos);
+    if (use_graph && (!c->host_graph || memcmp(key, c->host_graph_key, sizeof key) != 0)) {
+        if (c->host_graph) { cudaGraphExecDestroy(c->host_graph); c->host_graph = nullptr; }
+        cudaGraph_t graph = nullptr;
+        const uint64_t before = g_launches;
+        int rc = BH_ERR_CUDA;
+        if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            rc = enqueue_host_step(c, pos, vel, mass, out_pos, nch);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+            if (rc == BH_OK && e != cudaSuccess) rc = BH_ERR_CUDA;
+        }
+        c->host_graph_kernels = g_launches - before;
+        g_launches = before;   // capture launched nothing
+        if (rc == BH_OK && cudaGraphInstantiate(&c->host_graph, graph, 0) != cudaSuccess) rc = BH_ERR_CUDA;
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != BH_OK) {     // fall back to direct submission for the rest of this context's life
+            cudaGetLastError();
+            c->host_graph = nullptr;
+            c->host_graph_failed = true;
+            use_graph = false;
+        } else {
+            memcpy(c->host_graph_key, key, sizeof key);
+        }
     }
     BH_CUDA_OK(cudaEventRecord(c->ev0, c->stream));
-    g_pdl = false;   // event waits sit between the kernels of this path: plain launches
-    zero_scratch(c);
-    BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[0], 0));
-    launch_bounds(c->pos, n, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream);
-    launch_keys(c->pos, n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream, 0, c->s.cell_bnd);
-    launch_sort(c->keys, c->idx, n, c->sp, c->s, &c->sorted, c->stream);
-    if (nch > 1) launch_chunk_lists(c->idx[c->sorted], n, cb, c->chunk_counts, c->chunk_lists, c->stream);
-    BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[1], 0));
-    launch_tree(c->keys[c->sorted], c->idx[c->sorted], c->pos, c->mass, n, c->p, c->d, c->tree, c->s, c->consts, c->stream);
-    c->tree_full = true;
-    BH_TRY(check_launch());
-    for (int k = 0; k < nch; ++k) {
-        const int64_t lo = cb.lo[k], hi = cb.lo[k + 1];
-        // forces only (velocities may still be in flight); integrator + download on their own stream
-        if (nch > 1) BH_TRY(enqueue_forces(c, false, nullptr, nullptr, c->chunk_lists + lo, hi - lo));
-        else BH_TRY(enqueue_forces(c, false));
-        BH_CUDA_OK(cudaEventRecord(c->ev_trav[k], c->stream));
-        BH_CUDA_OK(cudaStreamWaitEvent(c->dl_stream, c->ev_trav[k], 0));
-        BH_CUDA_OK(cudaStreamWaitEvent(c->dl_stream, c->ev_vel[k], 0));
-        launch_integrate(c->pos, c->vel, c->acc, c->force, c->mass, lo, hi, c->p.dt, c->dl_stream);
-        BH_TRY(check_launch());
-        BH_CUDA_OK(cudaMemcpyAsync(out_pos + 2 * lo, c->pos + lo, sizeof(double2) * (hi - lo), cudaMemcpyDeviceToHost,
-                                   c->dl_stream));
+    if (use_graph) {
+        BH_CUDA_OK(cudaGraphLaunch(c->host_graph, c->stream));
+        g_launches += c->host_graph_kernels;
+    } else {
+        BH_TRY(enqueue_host_step(c, pos, vel, mass, out_pos, nch));
     }
-    BH_CUDA_OK(cudaEventRecord(c->ev_dl, c->dl_stream));
-    BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_dl, 0));
     BH_CUDA_OK(cudaEventRecord(c->ev1, c->stream));
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
-    c->bodies_set = true; c->tree_valid = false; c->timed = true;
+    c->bodies_set = true; c->tree_valid = false; c->timed = true; c->tree_full = true;
     return BH_OK;
 }
 

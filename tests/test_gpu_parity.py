@@ -265,6 +265,15 @@ def test_ab_switches_are_bit_identical(env, monkeypatch):
         assert np.array_equal(out, b_.positions(), equal_nan=True)
         assert np.array_equal(a.velocities(), b_.velocities(), equal_nan=True)
         assert np.array_equal(a.forces(), b_.forces(), equal_nan=True)
+        # the same call with PINNED host buffers is captured into a CUDA graph (3 streams) and replayed
+        import torch
+        hp, hv, hm = (torch.from_numpy(x).pin_memory() for x in (pos, vel, mass))
+        hout = torch.empty((n, 2), dtype=torch.float64).pin_memory()
+        for _ in range(3):                      # capture, then replays
+            hout.zero_()
+            a.step_host(hp, hv, hm, hout)
+            assert np.array_equal(hout.numpy(), out, equal_nan=True)
+        assert np.array_equal(a.velocities(), b_.velocities(), equal_nan=True)
 
 
 def test_graph_and_direct_launch_paths_agree():

@@ -16,15 +16,15 @@ from gpu_nbody_simulation_b200 import initial_conditions as ic  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=1_000_000)
 ap.add_argument("--steps", type=int, default=40)
-ap.add_argument("--chunks", default="1,2,4,8")
+ap.add_argument("--chunks", default="1,2,3,4,6")
 a = ap.parse_args()
 pos, vel, mass = ic.uniform_disk(a.n, seed=12345, round6=a.n <= 2_000_000)
 hp, hv, hm = (torch.from_numpy(x).pin_memory() for x in (pos, vel, mass))
 hout = torch.empty((a.n, 2), dtype=torch.float64).pin_memory()
 ref = None
-for ch in [int(x) for x in a.chunks.split(",")]:
+for ch, graph in [(int(x), g) for g in (True, False) for x in a.chunks.split(",")]:
     os.environ["BH_HOST_CHUNKS"] = str(ch)
-    with bh.Simulation(a.n, device=0) as sim:
+    with bh.Simulation(a.n, device=0, graph=graph) as sim:
         for _ in range(3):
             sim.step_host(hp, hv, hm, hout)
         t0 = time.perf_counter()
@@ -34,6 +34,6 @@ for ch in [int(x) for x in a.chunks.split(",")]:
         out = hout.numpy().copy()
         if ref is None:
             ref = out
-        print(json.dumps({"host_chunks": ch, "ms_per_step": dt * 1e3, "body_steps_per_s": a.n / dt,
+        print(json.dumps({"host_chunks": ch, "graph": graph, "ms_per_step": dt * 1e3, "body_steps_per_s": a.n / dt,
                           "device_ms": sim.last_step_ms(), "bit_identical_to_first": bool(np.array_equal(out, ref, equal_nan=True))}),
               flush=True)
