@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "bh_internal.h"
@@ -127,6 +128,9 @@ struct bh_ctx {
     const void* host_graph_key[4] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t host_graph_kernels = 0;
     bool host_graph_failed = false;
+    // BH_HOST_TRACE=1: timeline of one bh_step_host call (direct submission), printed to stderr
+    bool host_trace = false;
+    std::vector<std::pair<const char*, cudaEvent_t>> trace_ev;
     uint32_t* perm = nullptr;
     bool renumbered = false;
     double* cell_sums = nullptr;   // [4][finest cells]: count, m, m x, m y — all-reduced every step
@@ -402,6 +406,26 @@ int ensure_full_tree(bh_ctx* c) {
     return BH_OK;
 }
 
+void trace_mark(bh_ctx* c, const char* label, cudaStream_t st) {
+    if (!c->host_trace) return;
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    cudaEventRecord(ev, st);
+    c->trace_ev.emplace_back(label, ev);
+}
+
+void trace_dump(bh_ctx* c) {
+    if (!c->host_trace) return;
+    for (auto& le : c->trace_ev) {
+        float ms = 0.f;
+        cudaEventSynchronize(le.second);
+        cudaEventElapsedTime(&ms, c->ev0, le.second);
+        fprintf(stderr, "[bh_step_host trace] %-22s %8.3f ms\n", le.first, ms);
+        cudaEventDestroy(le.second);
+    }
+    c->trace_ev.clear();
+}
+
 bool host_pinned(const void* p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -427,12 +451,15 @@ int enqueue_host_step(bh_ctx* c, const double* pos, const double* vel, const dou
     BH_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_fork, 0));
     BH_CUDA_OK(cudaMemcpyAsync(c->pos, pos, sizeof(double2) * n, cudaMemcpyHostToDevice, c->copy_stream));
     BH_CUDA_OK(cudaEventRecord(c->ev_up[0], c->copy_stream));
+    trace_mark(c, "up: pos done", c->copy_stream);
     BH_CUDA_OK(cudaMemcpyAsync(c->mass, mass, sizeof(double) * n, cudaMemcpyHostToDevice, c->copy_stream));
     BH_CUDA_OK(cudaEventRecord(c->ev_up[1], c->copy_stream));
+    trace_mark(c, "up: mass done", c->copy_stream);
     for (int k = 0; k < nch; ++k) {
         const int64_t lo = cb.lo[k], cnt = (int64_t)cb.lo[k + 1] - lo;
         BH_CUDA_OK(cudaMemcpyAsync(c->vel + lo, vel + 2 * lo, sizeof(double2) * cnt, cudaMemcpyHostToDevice, c->copy_stream));
         BH_CUDA_OK(cudaEventRecord(c->ev_vel[k], c->copy_stream));
+        trace_mark(c, "up: vel chunk done", c->copy_stream);
     }
     zero_scratch(c);
     BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[0], 0));
@@ -440,21 +467,26 @@ int enqueue_host_step(bh_ctx* c, const double* pos, const double* vel, const dou
     launch_keys(c->pos, n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream, 0, c->s.cell_bnd);
     launch_sort(c->keys, c->idx, n, c->sp, c->s, &c->sorted, c->stream);
     if (nch > 1) launch_chunk_lists(c->idx[c->sorted], n, cb, c->chunk_counts, c->chunk_lists, c->stream);
+    trace_mark(c, "gpu: sort+lists done", c->stream);
     BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[1], 0));
     launch_tree(c->keys[c->sorted], c->idx[c->sorted], c->pos, c->mass, n, c->p, c->d, c->tree, c->s, c->consts, c->stream);
     c->tree_full = true;
     BH_TRY(check_launch());
+    trace_mark(c, "gpu: tree done", c->stream);
     for (int k = 0; k < nch; ++k) {
         const int64_t lo = cb.lo[k], hi = cb.lo[k + 1];
         if (nch > 1) BH_TRY(enqueue_forces(c, false, nullptr, nullptr, c->chunk_lists + lo, hi - lo));
         else BH_TRY(enqueue_forces(c, false));
         BH_CUDA_OK(cudaEventRecord(c->ev_trav[k], c->stream));
+        trace_mark(c, "gpu: traverse chunk", c->stream);
         BH_CUDA_OK(cudaStreamWaitEvent(c->dl_stream, c->ev_trav[k], 0));
         BH_CUDA_OK(cudaStreamWaitEvent(c->dl_stream, c->ev_vel[k], 0));
         launch_integrate(c->pos, c->vel, c->acc, c->force, c->mass, lo, hi, c->p.dt, c->dl_stream);
         BH_TRY(check_launch());
+        trace_mark(c, "dl: integrate chunk", c->dl_stream);
         BH_CUDA_OK(cudaMemcpyAsync(out_pos + 2 * lo, c->pos + lo, sizeof(double2) * (hi - lo), cudaMemcpyDeviceToHost,
                                    c->dl_stream));
+        trace_mark(c, "dl: download chunk", c->dl_stream);
     }
     BH_CUDA_OK(cudaEventRecord(c->ev_dl, c->dl_stream));
     BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_dl, 0));
@@ -506,6 +538,7 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     { const char* e = getenv("BH_SNAPSHOT_COPY"); c->snapshot_by_copy = e && e[0] == '1'; }
     { const char* e = getenv("BH_KEYS_TABLE"); c->keys_table = e && e[0] == '1'; }
     { const char* e = getenv("BH_PDL"); c->pdl = e && e[0] == '1' && p->n_ranks == 1; }
+    { const char* e = getenv("BH_HOST_TRACE"); c->host_trace = e && e[0] == '1'; }
     { const char* e = getenv("BH_HOST_CHUNKS"); if (e && atoi(e) >= 1) c->host_chunks = std::min(atoi(e), kMaxHostChunks); }
     if (p->device >= 0) c->device = p->device; else BH_CUDA_OK(cudaGetDevice(&c->device));
     if (c->device >= ndev) { set_error("device %d of %d", c->device, ndev); delete c; return BH_ERR_INVALID; }
@@ -773,7 +806,7 @@ int bh_step_host(bh_ctx* c, const double* pos, const double* vel, const double* 
     // With pinned host buffers the whole call (3 streams: uploads, compute, integrate + downloads) is captured
     // once into a CUDA graph keyed by the four host pointers and replayed: one launch instead of ~40 API calls.
     const void* key[4] = {pos, vel, mass, out_pos};
-    bool use_graph = !(c->p.flags & BH_FLAG_NO_GRAPH) && !c->host_graph_failed && host_pinned(pos) && host_pinned(vel) &&
+    bool use_graph = !(c->p.flags & BH_FLAG_NO_GRAPH) && !c->host_graph_failed && !c->host_trace && host_pinned(pos) && host_pinned(vel) &&
                      host_pinned(mass) && host_pinned(out_pos);
     if (use_graph && (!c->host_graph || memcmp(key, c->host_graph_key, sizeof key) != 0)) {
         if (c->host_graph) { cudaGraphExecDestroy(c->host_graph); c->host_graph = nullptr; }
@@ -807,6 +840,7 @@ int bh_step_host(bh_ctx* c, const double* pos, const double* vel, const double* 
     }
     BH_CUDA_OK(cudaEventRecord(c->ev1, c->stream));
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    trace_dump(c);
     c->bodies_set = true; c->tree_valid = false; c->timed = true; c->tree_full = true;
     return BH_OK;
 }
