@@ -119,7 +119,7 @@ struct bh_ctx {
     int64_t own_lo = 0, own_hi = 0;
     // pipelined host step (bh_step_host): bodies in `host_chunks` ranges of original index, each with its own
     // traversal launch, integrator launch and download, so that downloads overlap the remaining traversals
-    int host_chunks = 4;             // env BH_HOST_CHUNKS (1 = one traversal, one download)
+    int host_chunks = 1;             // env BH_HOST_CHUNKS (default 1 = one traversal, one download)
     uint32_t* chunk_lists = nullptr; // [n] sorted positions, stably partitioned by chunk
     uint32_t* chunk_counts = nullptr;
     cudaStream_t dl_stream = nullptr;
