@@ -8,10 +8,12 @@ Workload (config.workload): BASELINE.json configs[1] — 1 000 000 bodies, unifo
 12345, the reference's constants (G, dt = 1, theta = 0.5, depth cap 10).  A *step* is one pass of
 the whole hot path: bounds -> cell keys -> radix sort -> tree + COM -> traversal -> integrate.
 Because the reference's own physics flings bodies away after ONE step and the tree collapses to
-a few hundred nodes, every step starts from the initial distribution (the
-restore of positions / velocities is inside the timed region) — i.e. every timed step does the
-full-size, non-degenerate work of the reference's step 0.  At N > 1 GPUs the body count grows with
-N (weak scaling, 1M bodies per GPU, Morton-sharded, NCCL all-gather of positions every step).
+a few hundred nodes, every step starts from the initial distribution (a device
+snapshot that the step reads out of place; nothing is skipped: bounds, keys, sort, tree, traversal
+and integrator all run every step) — i.e. every timed step does the full-size, non-degenerate work
+of the reference's step 0.  At N > 1 GPUs the body count grows with N (weak scaling, 1M bodies per
+GPU, contiguous Morton slices, sharded tree build; the ranks exchange the bounding box and the
+per-cell sums over NVLink peer memory, not the bodies).
 
 `value`  : device-resident throughput, inputs in HBM: W warm-up steps, then EXACTLY K steps between two
            barrier + torch.cuda.synchronize() brackets, device time from CUDA events on the library's
@@ -402,12 +404,14 @@ def run_ours(args):
                 "vs_baseline": None,
                 "dtype": "f32 (double-float displacement; FP64 state, tree and integrator)", "data": "synthetic",
                 "config": {"workload": f"{'uniform disk' if args.dist == 'disk' else args.dist} N={n} ({n // world} per GPU), R=0.1, seed {SEED}, theta=0.5, "
-                                       "G=6.67e-11, dt=1, depth cap 10; every step restarts from the initial distribution "
-                                       "(device-to-device restore inside the timed region)",
+                                       "G=6.67e-11, dt=1, depth cap 10; every step restarts from the device-resident snapshot of the "
+                                       "initial distribution (out of place: the step reads the snapshot and writes the live "
+                                       "state, so every timed step is the full-size work of the reference's step 0)",
                            "l2": "inputs larger than L2: the per-rank working set that every step reads and rewrites is "
                                  "~150 MB at 1M bodies per GPU (FP64 state + snapshot 116 MB, sort buffers 16 MB, tree 23 MB) "
                                  "vs 126 MB of L2; value_l2_flushed repeats the K steps with 512 MB written before each "
-                                 "step (steps timed one by one and summed)",
+                                 "step (steps timed one by one and summed; with several ranks the un-timed flush also "
+                                 "absorbs rank skew, so the bracketed value is the one to quote)",
                            "parallelism": (f"morton-shard x{world}: bodies handed over in Morton order, contiguous index "
                                            f"slice per rank, sharded build, " + ("2 NCCL all-reduces per step" if args.no_p2p else
                                            "box + cell-sum exchange by NVLink peer stores fused with the kernels")) if world > 1

@@ -61,8 +61,9 @@ typedef struct bh_params {
     int32_t exact_leaf_max; /* finest cells with <= this many bodies accumulate mass/COM with the
                                reference's sequential running average (project.cu:367-373, bit-exact);
                                fuller cells use a fixed-shape parallel sum.  default 64 */
-    /* multi-GPU: bodies are sharded by contiguous index range after an initial Morton
-     * renumbering; each step all-gathers positions over NCCL (no reference counterpart). */
+    /* multi-GPU (no reference counterpart): rank r owns the contiguous index range bh_shard_range gives
+     * it; every rank keys / sorts / sums only its own bodies, the ranks exchange the bounding box and the
+     * per-cell sums (NVLink peer stores, or two NCCL all-reduces), never the bodies. */
     int32_t rank;         /* 0 .. n_ranks-1 */
     int32_t n_ranks;      /* 1 = single GPU */
     int32_t reserved[4];  /* reserved[0]: tuning knob, bodies per traversal lane (0 = default, 1 or 2) */
@@ -122,11 +123,13 @@ int bh_restore(bh_ctx* ctx);
 /* nsteps iterations of the loop body project.cu:955-1011: bounds -> keys -> sort -> tree -> COM ->
  * traversal -> a=F/m, v+=a dt, x+=v dt.  Asynchronous on the context's stream. */
 int bh_step(bh_ctx* ctx, int32_t nsteps);
-/* same, but every step first restores the snapshot (device-to-device) */
+/* same, but every step starts from the snapshot (read out of place; pos / vel receive the result) */
 int bh_step_from_snapshot(bh_ctx* ctx, int32_t nsteps);
 /* one step with HOST buffers (the reference-facing call: project.cu moves the tree H2D and the
  * positions D2H every step, :968, :1010): uploads pos / mass / vel, runs one step, downloads the new
- * positions into out_pos_xy_host.  Uploads are pipelined against the build. Synchronous. */
+ * positions into out_pos_xy_host.  Uploads are pipelined against the build; with pinned (page-locked)
+ * buffers the whole call is captured once into a CUDA graph keyed by the four pointers and replayed, so
+ * keep passing the same buffers.  Synchronous. */
 int bh_step_host(bh_ctx* ctx, const double* pos_xy_host, const double* vel_xy_host, const double* mass_host,
                  double* out_pos_xy_host);
 /* phase-split entry points for teacher-forced parity */

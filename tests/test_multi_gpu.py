@@ -1,4 +1,4 @@
-"""Multi-GPU path: Morton-range sharding + per-step all-gather of positions.
+"""Multi-GPU path (SURVEY 8e / DESIGN 7): contiguous index slices, sharded build, exchange of box + cell sums.
 
 * `gpu` test: 2 ranks over NCCL on a box with >= 2 GPUs (skipped on the 1-GPU round-end box);
   tests/multi_gpu_check.py compares against a single-GPU context and the CPU oracle.
