@@ -60,6 +60,7 @@ def lib():
         L.bho_tree_free.argtypes = [C.c_void_p]
         L.bho_compute_forces.argtypes = [C.c_void_p, dp, dp, C.c_int64, pp, C.c_int64, C.c_int64,
                                          C.c_int64, C.c_int, dp, i64p]
+        L.bho_compute_forces_exact_leaves.argtypes = L.bho_compute_forces.argtypes
         L.bho_update.argtypes = [dp, dp, dp, dp, dp, C.c_int64, C.c_double]
         L.bho_step.argtypes = [dp, dp, dp, dp, dp, C.c_int64, pp, C.c_int, i64p]
         L.bho_step.restype = C.c_int64
@@ -137,6 +138,16 @@ class Tree:
         cnt = (C.c_int64 * 6)()
         lib().bho_compute_forces(self._h, _dp(pos), _dp(mass), self.n, C.byref(self.params), i0, i1, stride,
                                  nthreads, _dp(f), cnt)
+        return f, dict(zip(COUNTER_NAMES, list(cnt)))
+
+    def forces_exact_leaves(self, i0=0, i1=None, stride=1, nthreads=1):
+        """EXTENSION (not reference behaviour): multi-body cap-level leaves are applied
+        as exact pair sums over their bodies, self excluded; everything else as forces()."""
+        i1 = self.n if i1 is None else i1
+        f = np.zeros((self.n, 2), dtype=np.float64)
+        cnt = (C.c_int64 * 6)()
+        lib().bho_compute_forces_exact_leaves(self._h, _dp(self.pos), _dp(self.mass), self.n, C.byref(self.params),
+                                              i0, i1, stride, nthreads, _dp(f), cnt)
         return f, dict(zip(COUNTER_NAMES, list(cnt)))
 
     def dump(self, path: str):

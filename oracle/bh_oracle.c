@@ -236,6 +236,113 @@ void bho_compute_forces(const bho_tree* t, const double* pos, const double* mass
     }
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * EXTENSION — NOT a restatement of the reference, hence not pinned by it.
+ *
+ * "Exact leaves": the traversal of bho_compute_forces above, with ONE change: a multi-body leaf at
+ * the depth cap (PARTICLE_INDEX == -1, the nodes project.cu:360-382 fills with a running average)
+ * is not applied as one monopole at its centre of mass — which in the reference includes the body
+ * itself when it sits in that leaf — but as the sum over the leaf's bodies
+ * j != i of the SAME pair expression, G m_i m_j / d2 * (dx, dy) / (d + eps).  Members are visited in
+ * ascending body index.  Every other node (internal nodes, single-body leaves, the self test) is
+ * handled exactly as above, so with every cap-level leaf holding one body the two functions agree
+ * bit for bit.  The leaf's members are found from the cell key accumulated on the way down
+ * (child index per level, as bho_body_keys builds it) in the key-sorted body list.
+ * This is the specification the CUDA flag BH_FLAG_EXACT_LEAVES is tested against.
+ * counters as above; [1] counts pair interactions inside such leaves individually. */
+void bho_body_keys(const double* pos, int64_t n, const double bounds[4], int max_depth, uint32_t* keys);
+typedef struct { uint32_t key; int64_t idx; } bho_keyidx;
+static int bho_keyidx_cmp(const void* a, const void* b) {
+    const bho_keyidx* x = (const bho_keyidx*)a; const bho_keyidx* y = (const bho_keyidx*)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+
+void bho_compute_forces_exact_leaves(const bho_tree* t, const double* pos, const double* mass, int64_t n,
+                                     const bho_params* p, int64_t i0, int64_t i1, int64_t stride,
+                                     int nthreads, double* forces, int64_t* counters) {
+    int64_t c_vis = 0, c_int = 0, c_open = 0, c_zero = 0, c_self = 0, c_stack = 0;
+    const double* nodes = t->nodes;
+    const double G = p->G, theta = p->theta, deps = p->dist_eps, meps = p->mass_eps;
+    const int cap = t->max_depth;
+    /* key-sorted body list (stable in body index) */
+    uint32_t* keys = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(n > 0 ? n : 1));
+    bho_keyidx* order = (bho_keyidx*)malloc(sizeof(bho_keyidx) * (size_t)(n > 0 ? n : 1));
+    double bounds[4] = {nodes[XMIN], nodes[XMAX], nodes[YMIN], nodes[YMAX]};
+    bho_body_keys(pos, n, bounds, cap, keys);
+    for (int64_t i = 0; i < n; ++i) { order[i].key = keys[i]; order[i].idx = i; }
+    qsort(order, (size_t)n, sizeof(bho_keyidx), bho_keyidx_cmp);
+    int64_t nb = (i1 - i0 + stride - 1) / stride;
+    if (nthreads < 1) nthreads = 1;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads) \
+    reduction(+ : c_vis, c_int, c_open, c_zero, c_self) reduction(max : c_stack)
+#endif
+    for (int64_t k = 0; k < nb; ++k) {
+        int64_t i = i0 + k * stride;
+        int64_t stack[4 * 64 + 8];
+        uint32_t kstack[4 * 64 + 8];
+        int dstack[4 * 64 + 8];
+        int top = 0;
+        double sx = 0.0, sy = 0.0;
+        double pix = pos[2 * i], piy = pos[2 * i + 1];
+        stack[top] = 0; kstack[top] = 0; dstack[top] = 1; ++top;
+        while (top > 0) {
+            if (top > c_stack) c_stack = top;
+            --top;
+            int64_t ni = stack[top];
+            uint32_t code = kstack[top];
+            int depth = dstack[top];
+            const double* node = nodes + ni * QSZ;
+            ++c_vis;
+            double nodeMass = node[MASS];
+            if (nodeMass <= meps) { ++c_zero; continue; }
+            int occ = (int)node[PIDX];
+            int leaf = node[CH0] == -1 && node[CH1] == -1 && node[CH2] == -1 && node[CH3] == -1;
+            double dx = node[COMX] - pix, dy = node[COMY] - piy;
+            double d2 = dx * dx + dy * dy;
+            double d = sqrt(d2) + deps;
+            double w = node[XMAX] - node[XMIN], h = node[YMAX] - node[YMIN];
+            double size = (w > h) ? w : h;
+            if (leaf || (size / d < theta)) {
+                if (leaf && (occ == i || (occ + 2) == -i)) { ++c_self; continue; }
+                if (leaf && depth >= cap && occ == -1) {
+                    /* members: bodies whose cell key == code */
+                    int64_t lo = 0, hi = n;
+                    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (order[mid].key < code) lo = mid + 1; else hi = mid; }
+                    for (int64_t q = lo; q < n && order[q].key == code; ++q) {
+                        int64_t j = order[q].idx;
+                        if (j == i) { ++c_self; continue; }
+                        double ex = pos[2 * j] - pix, ey = pos[2 * j + 1] - piy;
+                        double e2 = ex * ex + ey * ey;
+                        double e = sqrt(e2) + deps;
+                        double fm = (G * mass[i] * mass[j]) / e2;
+                        sx += fm * (ex / e); sy += fm * (ey / e);
+                        ++c_int;
+                    }
+                    continue;
+                }
+                double fm = (G * mass[i] * nodeMass) / d2;
+                double nx = dx / d, ny = dy / d;
+                sx += fm * nx; sy += fm * ny;
+                ++c_int;
+            } else {
+                ++c_open;
+                for (int c = 0; c < 4; ++c) {
+                    int64_t ch = (int64_t)(int)node[CH0 + c];
+                    if (ch != -1) { stack[top] = ch; kstack[top] = (code << 2) | (uint32_t)c; dstack[top] = depth + 1; ++top; }
+                }
+            }
+        }
+        forces[2 * i] = sx; forces[2 * i + 1] = sy;
+    }
+    free(keys); free(order);
+    if (counters) {
+        counters[0] = c_vis; counters[1] = c_int; counters[2] = c_open; counters[3] = c_zero;
+        counters[4] = c_self; counters[5] = c_stack;
+    }
+}
+
 /* project.cu:795-817 updateAccelerations / updateVelocities / updatePositions. */
 void bho_update(const double* forces, const double* mass, double* acc, double* vel, double* pos,
                 int64_t n, double dt) {
