@@ -30,6 +30,7 @@ BH_FLAG_FP64_TRAVERSAL = 1 << 0
 BH_FLAG_COUNTERS = 1 << 1
 BH_FLAG_NO_GRAPH = 1 << 2
 BH_FLAG_EXACT_EPS = 1 << 3
+BH_FLAG_EXACT_LEAVES = 1 << 4   # extension (not reference behaviour), see include/bh.h
 
 # every symbol include/bh.h declares (checked by tests/test_abi.py against the header text)
 ABI_SYMBOLS = (
@@ -199,7 +200,7 @@ class Simulation:
     """Host-side mirror of ``runSimulationGpu`` (project.cu:918-1024) over the C-ABI."""
 
     def __init__(self, n_bodies: int, fp64: bool = False, counters: bool = False, graph: bool = True,
-                 exact_eps: bool = False, **over):
+                 exact_eps: bool = False, exact_leaves: bool = False, **over):
         flags = int(over.pop("flags", 0))
         if fp64:
             flags |= BH_FLAG_FP64_TRAVERSAL
@@ -209,6 +210,8 @@ class Simulation:
             flags |= BH_FLAG_NO_GRAPH
         if exact_eps:
             flags |= BH_FLAG_EXACT_EPS
+        if exact_leaves:
+            flags |= BH_FLAG_EXACT_LEAVES
         bpl = int(over.pop("bodies_per_lane", 0))
         self.params = default_params(n_bodies=n_bodies, flags=flags, **over)
         self.params.reserved[0] = bpl      # traversal tuning knob (include/bh.h)

@@ -526,6 +526,10 @@ int bh_create(const bh_params* p, bh_ctx** out) {
         return BH_ERR_INVALID;
     }
     if (p->n_ranks < 1 || p->rank < 0 || p->rank >= p->n_ranks) { set_error("bad rank / n_ranks"); return BH_ERR_INVALID; }
+    if ((p->flags & BH_FLAG_EXACT_LEAVES) && p->n_ranks > 1) {
+        set_error("BH_FLAG_EXACT_LEAVES needs the leaf's bodies on the device: single-rank contexts only");
+        return BH_ERR_INVALID;
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {

@@ -65,6 +65,10 @@ struct TravArgs {
     unsigned long long* counters;
     int64_t n_slots;            // bodies this launch evaluates
     double G, dt, theta, dist_eps;
+    // BH_FLAG_EXACT_LEAVES only (appended: the layout seen by the other kernels is unchanged)
+    const uint32_t* t_count;    // bodies per pyramid cell
+    const uint32_t* t_first;    // sorted position of a cell's first body
+    uint32_t finest_off;        // pyramid index of the first cap-level cell
 };
 
 __device__ __forceinline__ float approx_sqrt(float x) {
@@ -141,7 +145,12 @@ template <> struct StackEntry<2> {
 #ifndef BH_GENERIC_MIN_BLOCKS
 #define BH_GENERIC_MIN_BLOCKS 4   // 48 registers; 8 (32 regs) is 25 % slower at N = 40k
 #endif
-template <int BPL, bool INTEGRATE, bool COUNT>
+// EXACT (BH_FLAG_EXACT_LEAVES, an extension — SURVEY 8f row f1, specified by
+// oracle/bh_oracle.c:bho_compute_forces_exact_leaves): a multi-body leaf at the depth cap is not applied
+// as one monopole at its centre of mass (which contains the body itself when it lives there)
+// but as the sum over the leaf's bodies j != i of the same pair expression.  The leaf test depends on the
+// node only, so the member loop is warp-uniform; members are fetched through the sorted list.
+template <int BPL, bool INTEGRATE, bool COUNT, bool EXACT = false>
 __global__ void __launch_bounds__(kTravThreads, (BPL == 1 ? BH_GENERIC_MIN_BLOCKS : 4) * (256 / kTravThreads))
 traverse_f32_kernel(const __grid_constant__ TravArgs a) {
     using SE = StackEntry<BPL>;
@@ -155,6 +164,8 @@ traverse_f32_kernel(const __grid_constant__ TravArgs a) {
     float2 nh[BPL], nl[BPL];     // minus the scaled body position, hi and lo floats
     float2 acc2[BPL];            // sum of G M d / (d2 (d + eps)); times m_i at the end
     const float feps = a.consts->feps;
+    [[maybe_unused]] double scale_d = 0.0, Gs = 0.0;   // EXACT: coordinate scale and G * scale^2
+    if constexpr (EXACT) { scale_d = a.consts->scale; Gs = a.G * scale_d * scale_d; }
     {
         const double scale = a.consts->scale;
 #pragma unroll
@@ -211,17 +222,56 @@ traverse_f32_kernel(const __grid_constant__ TravArgs a) {
         return m;
     };
 
+    // EXACT: is cell `idx` (warp-uniform) a multi-body leaf at the depth cap with mass > mass_eps?  If so apply
+    // its bodies one by one to the lanes whose body reached it (act[b]) and return true.
+    [[maybe_unused]] auto exact_leaf = [&](uint32_t idx, const bool (&act)[BPL]) -> bool {
+        if (idx < a.finest_off) return false;
+        const uint32_t cnt = __ldg(a.t_count + idx);
+        if (cnt < 2u || !(__ldg(a.flags + idx) & kNodeNonZero)) return false;
+        const uint32_t first = __ldg(a.t_first + idx);
+        for (uint32_t j = 0; j < cnt; ++j) {
+            const uint32_t bj = __ldg(a.sidx + first + j);
+            const double2 pj = a.pos_in[bj];
+            const double sxj = pj.x * scale_d, syj = pj.y * scale_d;
+            const float xh = (float)sxj, yh = (float)syj;
+            const float2 jl = make_float2((float)(sxj - (double)xh), (float)(syj - (double)yh));
+            const float gmj = (float)(Gs * a.mass[bj]);
+#pragma unroll
+            for (int b = 0; b < BPL; ++b) {
+                const float2 d = __fadd2_rn(__fadd2_rn(make_float2(xh, yh), nh[b]), __fadd2_rn(jl, nl[b]));
+                const float d2 = fmaf(d.x, d.x, d.y * d.y);
+                const float w = d2 * (approx_sqrt(d2) + feps);
+                const bool use = act[b] && (body[b] != bj);
+                const float f = use ? gmj * approx_rcp(w) : 0.f;    // coincident j != i: inf * 0 = NaN, as the pair formula
+                acc2[b] = __ffma2_rn(make_float2(f, f), d, acc2[b]);
+                if constexpr (COUNT) c_int += use;
+            }
+        }
+        if constexpr (COUNT) {
+#pragma unroll
+            for (int b = 0; b < BPL; ++b) c_vis += act[b];
+        }
+        return true;
+    };
+
     int top = 0;
     {   // the root (project.cu:711-715 pushes node 0)
         const float4 A = __ldg(reinterpret_cast<const float4*>(a.rec));
         const float2 B = __ldg(reinterpret_cast<const float2*>(a.rec) + 2);
         uint32_t m[BPL];
         uint32_t any = 0;
+        bool root_done = false;
+        if constexpr (EXACT) {
+            bool live[BPL];
+#pragma unroll
+            for (int b = 0; b < BPL; ++b) live[b] = body[b] != 0xffffffffu;
+            root_done = exact_leaf(0u, live);
+        }
 #pragma unroll
         for (int b = 0; b < BPL; ++b) {
             const bool live = body[b] != 0xffffffffu;
             const float2 mh = live ? nh[b] : make_float2(kFarLane, kFarLane);
-            m[b] = eval(A, B, 0u, b, mh, live);
+            m[b] = root_done ? 0u : eval(A, B, 0u, b, mh, live);
             any |= m[b];
         }
         if (any) {
@@ -251,6 +301,9 @@ traverse_f32_kernel(const __grid_constant__ TravArgs a) {
             const float2 B = __ldg(reinterpret_cast<const float2*>(rp + q) + 2);    // gm thr
             uint32_t m[BPL];
             uint32_t any = 0;
+            if constexpr (EXACT) {
+                if (exact_leaf(base + q, active)) continue;                         // a leaf: nobody opens it
+            }
 #pragma unroll
             for (int b = 0; b < BPL; ++b) {
                 m[b] = eval(A, B, base + q, b, mh[b], active[b]);
@@ -419,7 +472,7 @@ traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
 // ------------------------------------------------------------------------------------------------
 // FP64 verification traversal: the reference's expressions, one body per lane
 // ------------------------------------------------------------------------------------------------
-template <bool INTEGRATE, bool COUNT>
+template <bool INTEGRATE, bool COUNT, bool EXACT = false>
 __global__ void __launch_bounds__(kTravThreads)
 traverse_f64_kernel(const __grid_constant__ TravArgs a) {
     __shared__ uint2 s_stack[kTravWarps][kStackCap];
@@ -443,6 +496,27 @@ traverse_f64_kernel(const __grid_constant__ TravArgs a) {
     auto eval = [&](uint32_t idx, bool active) -> bool {
         const uint32_t fl = a.flags[idx];
         const bool nz = fl & kNodeNonZero, leaf = fl & kNodeLeaf;
+        if constexpr (EXACT) {   // multi-body leaf at the depth cap (warp-uniform test): its bodies one by one
+            if (nz && idx >= a.finest_off && a.t_count[idx] >= 2u) {
+                const uint32_t cnt = a.t_count[idx], first = a.t_first[idx];
+                for (uint32_t j = 0; j < cnt; ++j) {
+                    const uint32_t bj = a.sidx[first + j];
+                    const double2 pj = a.pos_in[bj];
+                    const double ex = pj.x - px, ey = pj.y - py;
+                    const double e2 = ex * ex + ey * ey;
+                    const double e = sqrt(e2) + a.dist_eps;
+                    const bool usej = active && (bj != body);
+                    if (usej) {
+                        const double fm = (a.G * mi * a.mass[bj]) / e2;
+                        sx += fm * (ex / e);
+                        sy += fm * (ey / e);
+                    }
+                    if constexpr (COUNT) c_int += usej;
+                }
+                if constexpr (COUNT) c_vis += active;
+                return false;
+            }
+        }
         const int level = (31 - __clz(3u * idx + 1u)) >> 1;                  // 3 off[l] + 1 == 4^l
         const double M = a.t_mass[idx];
         const double dx = a.t_comx[idx] - px, dy = a.t_comy[idx] - py;
@@ -619,7 +693,7 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
                      const uint32_t* own_list, const uint32_t* own_count_dev, int64_t own_n,
                      const bh_params& p, const Dims& d, const TreeArrays& t, const StepConsts* consts,
                      unsigned long long* counters, bool integrate, cudaStream_t st) {
-    (void)own_lo; (void)own_hi; (void)own_count_dev; (void)n; (void)skeys; (void)d;
+    (void)own_lo; (void)own_hi; (void)own_count_dev; (void)n; (void)skeys;
     TravArgs a;
     a.sidx = sidx; a.own_list = own_list; a.self_node = t.self_node;
     a.pos_in = pos_in; a.vel_in = vel_in;
@@ -628,22 +702,31 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
     a.consts = consts; a.counters = counters;
     a.n_slots = own_n;
     a.G = p.G; a.dt = p.dt; a.theta = p.theta; a.dist_eps = p.dist_eps;
+    a.t_count = t.count; a.t_first = t.first; a.finest_off = (uint32_t)d.level_off[d.finest];
     if (own_n <= 0) return;
     const bool fp64 = p.flags & BH_FLAG_FP64_TRAVERSAL, count = p.flags & BH_FLAG_COUNTERS;
     // two bodies per lane halve the node traffic and the control overhead per body, but need >= ~400k
     // bodies to keep every SM's warp slots full (ncu: profiles/r01_traverse_v4_*)
-    const int bpl = (p.reserved[0] == 1) ? 1 : (p.reserved[0] == 2 || p.reserved[0] == 3) ? 2 : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
+    const bool exact_leaves = p.flags & BH_FLAG_EXACT_LEAVES;   // extension: generic 1-body-per-lane / FP64 kernels only
+    const int bpl = exact_leaves ? 1 : (p.reserved[0] == 1) ? 1 : (p.reserved[0] == 2 || p.reserved[0] == 3) ? 2 : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
     // previous operation on the stream = tree_top_kernel (or a peer-exchange kernel; g_pdl is off there)
 #define BH_GO(K) launch_chain(K, dim3(blocks), dim3(kTravThreads), st, true, a)
     if (fp64) {
         unsigned blocks = (unsigned)((own_n + kTravThreads - 1) / kTravThreads);
+        if (exact_leaves) {
+            if (integrate) { if (count) BH_GO((traverse_f64_kernel<true, true, true>)); else BH_GO((traverse_f64_kernel<true, false, true>)); }
+            else { if (count) BH_GO((traverse_f64_kernel<false, true, true>)); else BH_GO((traverse_f64_kernel<false, false, true>)); }
+        } else
         if (integrate) { if (count) BH_GO((traverse_f64_kernel<true, true>)); else BH_GO((traverse_f64_kernel<true, false>)); }
         else { if (count) BH_GO((traverse_f64_kernel<false, true>)); else BH_GO((traverse_f64_kernel<false, false>)); }
     } else {
         const int64_t per_block = (int64_t)kTravThreads * bpl;
         unsigned blocks = (unsigned)((own_n + per_block - 1) / per_block);
 #define BH_TRAV(B, I, C) BH_GO((traverse_f32_kernel<B, I, C>))
-        if (bpl == 2 && !count && p.reserved[0] != 3) {
+        if (exact_leaves) {
+            if (integrate) { if (count) BH_GO((traverse_f32_kernel<1, true, true, true>)); else BH_GO((traverse_f32_kernel<1, true, false, true>)); }
+            else { if (count) BH_GO((traverse_f32_kernel<1, false, true, true>)); else BH_GO((traverse_f32_kernel<1, false, false, true>)); }
+        } else if (bpl == 2 && !count && p.reserved[0] != 3) {
             const bool exact = p.flags & BH_FLAG_EXACT_EPS;
             if (integrate) { if (exact) BH_GO((traverse_f32_pair_kernel<true, true>)); else BH_GO((traverse_f32_pair_kernel<true, false>)); }
             else { if (exact) BH_GO((traverse_f32_pair_kernel<false, true>)); else BH_GO((traverse_f32_pair_kernel<false, false>)); }

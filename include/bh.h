@@ -39,9 +39,14 @@ enum {
                                          double-float displacement */
     BH_FLAG_COUNTERS = 1u << 1,       /* keep per-step interaction / visit counters (cheap) */
     BH_FLAG_NO_GRAPH = 1u << 2,       /* launch kernels directly instead of replaying a CUDA graph */
-    BH_FLAG_EXACT_EPS = 1u << 3       /* FP32 traversal: evaluate 1/(d + dist_eps) exactly (2 SFU ops per
+    BH_FLAG_EXACT_EPS = 1u << 3,      /* FP32 traversal: evaluate 1/(d + dist_eps) exactly (2 SFU ops per
                                          interaction) instead of to first order in dist_eps/d (1 SFU op;
                                          relative error (dist_eps/d)^2, < 1e-6 for d > 1e-12) */
+    BH_FLAG_EXACT_LEAVES = 1u << 4    /* EXTENSION, not reference behaviour: a multi-body leaf at
+                                         the depth cap acts through its bodies one by one (self excluded) instead
+                                         of through one monopole that contains the body itself (project.cu:360-382,
+                                         :646).  Single GPU only.  Specified by the oracle's
+                                         bho_compute_forces_exact_leaves; default off = reference semantics. */
 };
 
 /* Runtime copy of the reference's compile-time macros and source-level constants.
