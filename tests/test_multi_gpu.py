@@ -76,3 +76,108 @@ def test_gloo_world2_shard_and_allgather_protocol(tmp_path, n):
     for rank in range(world):
         got = np.load(os.path.join(tmp_path, f"pos_rank{rank}.npy"))
         assert np.array_equal(got, p), f"rank {rank}: sharded trajectory differs from the single-rank one"
+
+
+# ------------------------------------------------------------------------------------------------
+# The protocol the CUDA library actually runs: every rank keys and sums ONLY its own slice,
+# two reductions (box: min of 4 doubles; per finest cell: count, m, m x, m y) make the tree global, the
+# level pass runs redundantly on the reduced sums.  Here with gloo and numpy standing in for NVLink and
+# the kernels: the tree every rank ends up with must be the oracle's tree of ALL bodies.
+# ------------------------------------------------------------------------------------------------
+def _pyramid_from_sums(cnt, m, mx, my, finest):
+    """Level pass on reduced finest-cell sums -> per level (count, mass, comx, comy), Morton order."""
+    with np.errstate(invalid="ignore", divide="ignore"):
+        cx = np.where(m > 0, mx / m, 0.0)
+        cy = np.where(m > 0, my / m, 0.0)
+    levels = {finest: (cnt.astype(np.int64), m, cx, cy)}
+    for l in range(finest - 1, -1, -1):
+        c, mm, x, y = levels[l + 1]
+        c4, m4, x4, y4 = (a.reshape(-1, 4) for a in (c, mm, x, y))
+        pc = c4.sum(axis=1)
+        pm = np.zeros(len(pc)); sx = np.zeros(len(pc)); sy = np.zeros(len(pc))
+        for q in range(4):                                   # children 0..3, sums start from 0.0 (project.cu:480-495)
+            pm = pm + m4[:, q]; sx = sx + m4[:, q] * x4[:, q]; sy = sy + m4[:, q] * y4[:, q]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            px = np.where(pm > 0, sx / pm, 0.0); py = np.where(pm > 0, sy / pm, 0.0)
+        single = pc == 1                                     # a lone body's cell copies its only non-empty child
+        which = np.argmax(c4 > 0, axis=1)
+        rows = np.arange(len(pc))
+        pm = np.where(single, m4[rows, which], pm)
+        px = np.where(single, x4[rows, which], px); py = np.where(single, y4[rows, which], py)
+        levels[l] = (pc, pm, px, py)
+    return levels
+
+
+def _canonical_from_pyramid(levels, finest):
+    """DFS pre-order (children 0..3) over { cell : every proper ancestor holds >= 2 bodies } -> rows
+    [depth, mass, comx, comy, internal]."""
+    rows = []
+
+    def rec(l, code):
+        c, m, x, y = (a[code] for a in levels[l])
+        internal = c >= 2 and l < finest
+        rows.append((l, m, x, y, 1.0 if internal else 0.0))
+        if internal:
+            for q in range(4):
+                rec(l + 1, 4 * code + q)
+    rec(0, 0)
+    return np.array(rows)
+
+
+def _sharded_build_worker(rank, world, port, n, max_depth, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import gpu_nbody_simulation_b200 as bh
+    import oracle
+    from gpu_nbody_simulation_b200 import initial_conditions as ic
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pos, vel, mass = ic.plummer_2d(n, seed=7, round6=False)
+    lo, hi = bh.shard_range(n, world, rank)
+    own_p, own_m = pos[lo:hi], mass[lo:hi]
+    finest = max_depth - 1
+    # 1. box: min over ranks of (xmin, -xmax, ymin, -ymax), then the reference's padding rule on every rank
+    raw = torch.tensor([own_p[:, 0].min(), -own_p[:, 0].max(), own_p[:, 1].min(), -own_p[:, 1].max()], dtype=torch.float64)
+    dist.all_reduce(raw, op=dist.ReduceOp.MIN)
+    xmin, nxmax, ymin, nymax = raw.tolist()
+    bounds = oracle.root_bounds(np.array([[xmin, ymin], [-nxmax, -nymax]]))
+    # 2. own keys, own partial sums per finest cell
+    keys = oracle.body_keys(own_p, bounds, max_depth).astype(np.int64)
+    nc = 4 ** finest
+    sums = np.stack([np.bincount(keys, minlength=nc).astype(np.float64),
+                     np.bincount(keys, weights=own_m, minlength=nc),
+                     np.bincount(keys, weights=own_m * own_p[:, 0], minlength=nc),
+                     np.bincount(keys, weights=own_m * own_p[:, 1], minlength=nc)])
+    t = torch.from_numpy(sums)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)               # 3. ONE reduction of 4 doubles per finest cell
+    sums = t.numpy()
+    levels = _pyramid_from_sums(sums[0], sums[1], sums[2], sums[3], finest)   # 4. redundant level pass
+    np.save(os.path.join(out_dir, f"tree_rank{rank}.npy"), _canonical_from_pyramid(levels, finest))
+    np.save(os.path.join(out_dir, f"bounds_rank{rank}.npy"), bounds)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,max_depth", [(3000, 6), (2001, 8)])
+def test_gloo_world2_sharded_build_gives_the_global_tree(tmp_path, n, max_depth):
+    import torch.multiprocessing as mp
+    import oracle
+    from gpu_nbody_simulation_b200 import initial_conditions as ic
+    world = 2
+    mp.spawn(_sharded_build_worker, args=(world, 29650 + max_depth, n, max_depth, str(tmp_path)), nprocs=world, join=True)
+    pos, vel, mass = ic.plummer_2d(n, seed=7, round6=False)
+    par = oracle.default_params(max_depth=max_depth)
+    tree = oracle.Tree(pos, mass, par)
+    want = tree.canonical()            # [depth, xmin, xmax, ymin, ymax, mass, comx, comy, occupant, internal]
+    got0 = np.load(os.path.join(tmp_path, "tree_rank0.npy"))
+    got1 = np.load(os.path.join(tmp_path, "tree_rank1.npy"))
+    assert np.array_equal(got0, got1), "all ranks must hold the identical tree (same reduced sums, same arithmetic)"
+    assert np.array_equal(np.load(os.path.join(tmp_path, "bounds_rank0.npy")), oracle.root_bounds(pos)), "box bit-exact"
+    assert got0.shape[0] == want.shape[0] == tree.size, "topology: same node count"
+    assert np.array_equal(got0[:, 0], want[:, 0]) and np.array_equal(got0[:, 4], want[:, 9]), "same pre-order shape"
+    # values: sums-then-divide instead of the sequential running average -> ~1e-16 relative, not bit-exact
+    assert np.allclose(got0[:, 1], want[:, 5], rtol=1e-13, atol=0)
+    nz = want[:, 5] > 0
+    assert np.allclose(got0[nz, 2], want[nz, 6], rtol=1e-12, atol=1e-18)
+    assert np.allclose(got0[nz, 3], want[nz, 7], rtol=1e-12, atol=1e-18)
