@@ -1,5 +1,6 @@
 // C-ABI of libbh.so: context life cycle, the per-step kernel sequence (optionally replayed as a
-// CUDA graph), multi-GPU position exchange over NCCL, getters in original body order.
+// CUDA graph), the multi-GPU exchange (NVLink peer memory or NCCL), the pipelined host step, getters in
+// original body order.
 // See include/bh.h for the contract and the reference lines each entry point replaces.
 #include <dlfcn.h>
 #include <nccl.h>   // types only; the library is dlopen'ed so that libbh.so has no hard NCCL dependency
@@ -76,23 +77,6 @@ static NcclApi* nccl_api() {
         }                                                                                       \
     } while (0)
 
-// small helper kernels ---------------------------------------------------------------------------
-__global__ void gather2_kernel(const double2* __restrict__ in, const uint32_t* __restrict__ perm, int64_t n,
-                               double2* __restrict__ out) {   // out[j] = in[perm[j]]
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n) out[j] = in[perm[j]];
-}
-__global__ void gather1_kernel(const double* __restrict__ in, const uint32_t* __restrict__ perm, int64_t n,
-                               double* __restrict__ out) {
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n) out[j] = in[perm[j]];
-}
-__global__ void scatter2_kernel(const double2* __restrict__ in, const uint32_t* __restrict__ perm, int64_t n,
-                                double2* __restrict__ out) {  // out[perm[j]] = in[j]
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n) out[perm[j]] = in[j];
-}
-
 }  // namespace bh
 
 using namespace bh;
@@ -104,9 +88,8 @@ struct bh_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     double2 *pos = nullptr, *vel = nullptr, *acc = nullptr, *force = nullptr, *snap_pos = nullptr,
-            *snap_vel = nullptr, *tmp2 = nullptr;
+            *snap_vel = nullptr;
     double* mass = nullptr;
-    double* tmp1 = nullptr;
     uint32_t* keys[2] = {nullptr, nullptr};
     uint32_t* idx[2] = {nullptr, nullptr};
     int sorted = 0;               // which of keys[]/idx[] holds the sorted result
@@ -131,8 +114,6 @@ struct bh_ctx {
     // BH_HOST_TRACE=1: timeline of one bh_step_host call (direct submission), printed to stderr
     bool host_trace = false;
     std::vector<std::pair<const char*, cudaEvent_t>> trace_ev;
-    uint32_t* perm = nullptr;
-    bool renumbered = false;
     double* cell_sums = nullptr;   // [4][finest cells]: count, m, m x, m y — all-reduced every step
     double* bbox_raw = nullptr;    // [4]: xmin, -xmax, ymin, -ymax — all-reduced (min) every step
     SortPlan sp_own;               // sort plan for this rank's slice
@@ -638,11 +619,11 @@ int bh_destroy(bh_ctx* c) {
         for (int r = 0; r < c->p.n_ranks; ++r)
             if (r != c->p.rank && c->pc.peer_base[r]) cudaIpcCloseMemHandle(c->pc.peer_base[r]);
     if (c->comm_buf) cudaFree(c->comm_buf);
-    void* ptrs[] = {c->pos, c->vel, c->acc, c->force, c->snap_pos, c->snap_vel, c->tmp2, c->mass, c->tmp1, c->keys[0],
+    void* ptrs[] = {c->pos, c->vel, c->acc, c->force, c->snap_pos, c->snap_vel, c->mass, c->keys[0],
                     c->keys[1], c->idx[0], c->idx[1], c->consts, c->tree.mass, c->tree.comx, c->tree.comy,
                     c->tree.count /* + scratch + tickets */, c->tree.first, c->tree.flags, c->rec_alloc, c->tree.self_node,
                     c->s.bbox_partial, c->s.heavy_list, c->s.huge_list, c->s.huge_partial, c->s.cell_bnd,
-                    c->packed, c->chunk_lists, c->chunk_counts, c->perm, c->cell_sums, c->bbox_raw};
+                    c->packed, c->chunk_lists, c->chunk_counts, c->cell_sums, c->bbox_raw};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -910,25 +891,13 @@ static int fetch_sorted(bh_ctx* c, std::vector<uint32_t>& keys, std::vector<uint
     return BH_OK;
 }
 
-static int fetch_perm(bh_ctx* c, std::vector<uint32_t>& perm) {
-    perm.clear();
-    if (!c->renumbered) return BH_OK;
-    perm.resize(c->d.n);
-    BH_CUDA_OK(cudaMemcpy(perm.data(), c->perm, 4 * c->d.n, cudaMemcpyDeviceToHost));
-    return BH_OK;
-}
-
 int bh_get_body_keys(bh_ctx* c, uint32_t* out) {
     if (!c || !out || !c->tree_valid) { set_error("bh_get_body_keys: no tree built"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     BH_TRY(ensure_full_tree(c));
-    std::vector<uint32_t> keys, idx, perm;
+    std::vector<uint32_t> keys, idx;
     BH_TRY(fetch_sorted(c, keys, idx));
-    BH_TRY(fetch_perm(c, perm));
-    for (int64_t j = 0; j < c->d.n; ++j) {
-        uint32_t b = idx[j];
-        out[perm.empty() ? b : perm[b]] = keys[j];
-    }
+    for (int64_t j = 0; j < c->d.n; ++j) out[idx[j]] = keys[j];
     return BH_OK;
 }
 
@@ -936,10 +905,9 @@ int bh_get_sorted_order(bh_ctx* c, uint32_t* out) {
     if (!c || !out || !c->tree_valid) { set_error("bh_get_sorted_order: no tree built"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     BH_TRY(ensure_full_tree(c));
-    std::vector<uint32_t> keys, idx, perm;
+    std::vector<uint32_t> keys, idx;
     BH_TRY(fetch_sorted(c, keys, idx));
-    BH_TRY(fetch_perm(c, perm));
-    for (int64_t j = 0; j < c->d.n; ++j) out[j] = perm.empty() ? idx[j] : perm[idx[j]];
+    for (int64_t j = 0; j < c->d.n; ++j) out[j] = idx[j];
     return BH_OK;
 }
 
@@ -971,7 +939,6 @@ static int fetch_host_tree(bh_ctx* c, HostTree& ht) {
     BH_CUDA_OK(cudaMemcpyAsync(&h, c->consts, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
     ht.bounds[0] = h.xmin; ht.bounds[1] = h.xmax; ht.bounds[2] = h.ymin; ht.bounds[3] = h.ymax;
-    BH_TRY(fetch_perm(c, ht.perm));
     return BH_OK;
 }
 
