@@ -43,6 +43,7 @@ BODIES_PER_GPU = 1_000_000
 SEED = 12345
 FLOP_PER_INTERACTION = 20.0
 TRAVERSE_DRAM_BYTES_NCU = 74_801_152 + 37_312_768   # profiles/r01_traverse_v8_pair_ncu_summary.txt
+TRAVERSE_WARP_INSTRUCTIONS_NCU = 298_806_710          # same capture: smsp__inst_executed.sum at N = 1M uniform disk
 METRIC = "body_steps_per_s"
 UNIT = "body·steps/s"
 
@@ -362,6 +363,16 @@ def run_ours(args):
                     "kernel_timing": "cudaEvents around the kernel on the library's stream, averaged over a second pass "
                                      "of the same K steps with direct launches (the timed pass replays a CUDA graph)",
                     "interactions_per_s": inter_per_step / trav_s}
+        if n == 1_000_000 and args.dist == "disk":
+            # issue-slot view of the same kernel: the 20-flop convention counts accepted interactions, the hardware
+            # spends ~18.4 warp instructions per (body, node) EVALUATION; instructions per launch are a
+            # property of kernel + workload, measured once with ncu
+            sms = torch.cuda.get_device_properties(local).multi_processor_count
+            slots_per_s = sms * 4 * mhz * 1e6
+            roofline["issue_view"] = {"warp_instructions_per_launch": TRAVERSE_WARP_INSTRUCTIONS_NCU,
+                                      "source": "smsp__inst_executed.sum, profiles/r01_traverse_v8_pair_ncu_summary.txt",
+                                      "issue_slots_per_s": slots_per_s, "sm_count": sms, "sm_mhz_from_fma_loop": mhz,
+                                      "frac_of_issue_slots": TRAVERSE_WARP_INSTRUCTIONS_NCU / (slots_per_s * trav_s)}
         # whole-step HBM view: mandatory body traffic (72 B/body FP64 state) vs measured copy peak
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
