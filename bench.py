@@ -253,12 +253,12 @@ def run_ours(args):
         # library itself, outside any timed region): a rank's contiguous index slice is then a compact
         # region, so the 64 bodies of a traversal warp stay neighbours.  Body order is arbitrary for a
         # synthetic workload; a multi-GPU application keeps its bodies in this order permanently.
-        with bh.Simulation(n, device=local) as tmp:
+        with bh.Simulation(n, device=local, max_depth=args.max_depth) as tmp:
             tmp.set_bodies(pos, vel, mass)
             tmp.build_tree()
             order = tmp.sorted_order().astype(np.int64)
         pos, vel, mass = np.ascontiguousarray(pos[order]), np.ascontiguousarray(vel[order]), np.ascontiguousarray(mass[order])
-    sim = bh.Simulation(n, device=local, rank=rank, n_ranks=world, graph=not args.no_graph)
+    sim = bh.Simulation(n, device=local, rank=rank, n_ranks=world, graph=not args.no_graph, max_depth=args.max_depth)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -329,7 +329,7 @@ def run_ours(args):
         sim.set_profiling(False)
         phases = {k: t[k] / max(t["steps"], 1) for k in ("bounds_keys_us", "sort_us", "build_us", "traverse_us",
                                                          "exchange_us", "total_us")}
-    simc = bh.Simulation(n, device=local, rank=rank, n_ranks=1, counters=True) if world == 1 else None
+    simc = bh.Simulation(n, device=local, rank=rank, n_ranks=1, counters=True, max_depth=args.max_depth) if world == 1 else None
     if rank == 0 and simc is not None:
         simc.set_bodies(pos, vel, mass)
         simc.snapshot()
@@ -363,7 +363,7 @@ def run_ours(args):
                     "kernel_timing": "cudaEvents around the kernel on the library's stream, averaged over a second pass "
                                      "of the same K steps with direct launches (the timed pass replays a CUDA graph)",
                     "interactions_per_s": inter_per_step / trav_s}
-        if n == 1_000_000 and args.dist == "disk":
+        if n == 1_000_000 and args.dist == "disk" and args.max_depth == 10:
             # issue-slot view of the same kernel: the 20-flop convention counts accepted interactions, the hardware
             # spends ~18.4 warp instructions per (body, node) EVALUATION; instructions per launch are a
             # property of kernel + workload, measured once with ncu
@@ -406,7 +406,7 @@ def run_ours(args):
         cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     gpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_gpu_baseline and not strong and args.dist == "disk":
+    if rank == 0 and world == 1 and not args.no_gpu_baseline and not strong and args.dist == "disk" and args.max_depth == 10:
         gpu_baseline = reference_gpu_run(pos, vel, mass, local)
 
     if rank == 0:
@@ -415,7 +415,7 @@ def run_ours(args):
                 "vs_baseline": None,
                 "dtype": "f32 (double-float displacement; FP64 state, tree and integrator)", "data": "synthetic",
                 "config": {"workload": f"{'uniform disk' if args.dist == 'disk' else args.dist} N={n} ({n // world} per GPU), R=0.1, seed {SEED}, theta=0.5, "
-                                       "G=6.67e-11, dt=1, depth cap 10; every step restarts from the device-resident snapshot of the "
+                                       f"G=6.67e-11, dt=1, depth cap {args.max_depth}; every step restarts from the device-resident snapshot of the "
                                        "initial distribution (out of place: the step reads the snapshot and writes the live "
                                        "state, so every timed step is the full-size work of the reference's step 0)",
                            "l2": "inputs larger than L2: the per-rank working set that every step reads and rewrites is "
@@ -453,6 +453,8 @@ def main():
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference project.cu run on this GPU")
     ap.add_argument("--dist", choices=["disk", "plummer", "square"], default="disk",
                     help="synthetic distribution (BASELINE config 2: disk; config 3: plummer)")
+    ap.add_argument("--max-depth", type=int, default=10,
+                    help="QUADTREE_MAX_DEPTH (reference: 10); BASELINE config 3 (clustered Plummer) raises it, up to 13")
     ap.add_argument("--no-graph", action="store_true", help="direct kernel launches instead of CUDA-graph replay")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-reduces instead of the peer-memory exchange")
     ap.add_argument("--total-bodies", type=int, default=0,
