@@ -19,10 +19,12 @@ ap.add_argument("--counters", action="store_true")
 ap.add_argument("--max-depth", type=int, default=10)
 ap.add_argument("--bpl", type=int, default=0)
 ap.add_argument("--exact-eps", action="store_true")
+ap.add_argument("--exact-leaves", action="store_true", help="BH_FLAG_EXACT_LEAVES (extension)")
 a = ap.parse_args()
 gen = {"disk": ic.uniform_disk, "plummer": ic.plummer_2d, "square": ic.uniform_square}[a.dist]
 pos, vel, mass = gen(a.n, seed=12345, round6=False)
-with bh.Simulation(a.n, graph=False, fp64=a.fp64, counters=a.counters, max_depth=a.max_depth, bodies_per_lane=a.bpl, exact_eps=a.exact_eps) as sim:
+with bh.Simulation(a.n, graph=False, fp64=a.fp64, counters=a.counters, max_depth=a.max_depth, bodies_per_lane=a.bpl, exact_eps=a.exact_eps,
+                   exact_leaves=a.exact_leaves) as sim:
     sim.set_bodies(pos, vel, mass)
     sim.snapshot()
     sim.set_profiling(True)

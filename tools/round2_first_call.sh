@@ -1,0 +1,24 @@
+#!/usr/bin/env bash
+# First GPU call of the next round (one B200): everything round 1 left unmeasured, in one pass.
+#   gpurun --timeout 900 -- 'bash tools/round2_first_call.sh'
+# 1. the exact-leaves kernels (BH_FLAG_EXACT_LEAVES) against the oracle extension — never run on a GPU yet;
+# 2. the regular GPU suite + smoke;
+# 3. bench (default) and the ncu launch list of the SAME command;
+# 4. one ncu --set full capture of the production traversal kernel of the final build;
+# 5. cost of exact leaves at 1M bodies (profile_step with the flag).
+set -u
+mkdir -p gpurun_out
+( BH_TEST_UNVALIDATED=1 timeout 300 python -m pytest tests/test_gpu_exact_leaves.py -m gpu -q -rfs 2>&1 | tail -40 ) > gpurun_out/r2_exact_leaves_pytest.log
+( timeout 600 python -m pytest tests -m gpu -q -rfs 2>&1 | tail -30 ) > gpurun_out/r2_pytest.log
+( timeout 120 python __graft_entry__.py smoke 2>&1 | tail -3 ) > gpurun_out/r2_smoke.log
+timeout 400 python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+    --log-file gpurun_out/r2_launches_bench.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-baseline \
+    > gpurun_out/r2_ncu_bench.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:traverse_f32_pair -s 2 -c 1 \
+    -o gpurun_out/r2_traverse_pair python tools/profile_step.py --steps 4 > gpurun_out/r2_ncu_full.log 2>&1
+timeout 120 python tools/profile_step.py --steps 4 > gpurun_out/r2_profile_default.log 2>&1
+timeout 120 python tools/profile_step.py --steps 4 --exact-leaves > gpurun_out/r2_profile_exact_leaves.log 2>&1
+tail -5 gpurun_out/r2_exact_leaves_pytest.log gpurun_out/r2_pytest.log gpurun_out/r2_smoke.log
+tail -1 gpurun_out/r2_profile_default.log gpurun_out/r2_profile_exact_leaves.log
+cut -c1-300 gpurun_out/r2_bench_default.json
