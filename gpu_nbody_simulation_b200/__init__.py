@@ -41,7 +41,9 @@ ABI_SYMBOLS = (
     "bh_get_bounds", "bh_get_body_keys", "bh_get_sorted_order", "bh_get_tree_size", "bh_get_tree",
     "bh_dump_quadtree", "bh_get_counters", "bh_set_profiling", "bh_get_timers", "bh_reset_timers",
     "bh_last_step_ms", "bh_direct_forces", "bh_load_text", "bh_append_positions_txt", "bh_measure_fp32_peak",
+    "bh_generate", "bh_generate_host", "bh_philox4x32_10", "bh_write_init_files",
 )
+GENERATOR_KINDS = {"uniform_square": 0, "uniform_disk": 1, "plummer_2d": 2}   # BH_GEN_* of include/bh.h
 
 
 class BhError(RuntimeError):
@@ -130,9 +132,15 @@ def lib():
     L.bh_load_text.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, dp, dp, dp]
     L.bh_append_positions_txt.argtypes = [C.c_char_p, dp, C.c_int64, C.c_double, C.c_int]
     L.bh_measure_fp32_peak.argtypes = [C.c_int32, dp, dp]
+    L.bh_generate.argtypes = [vp, C.c_int32, C.c_uint64]
+    L.bh_generate_host.argtypes = [C.c_int32, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, dp, dp, dp]
+    L.bh_philox4x32_10.argtypes = [u32p, u32p, u32p]
+    L.bh_write_init_files.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, dp, dp, dp]
     for name in ABI_SYMBOLS:
         fn = getattr(L, name)
-        if name not in ("bh_last_error", "bh_default_params"):
+        if name in ("bh_default_params", "bh_philox4x32_10"):
+            fn.restype = None
+        elif name != "bh_last_error":
             fn.restype = C.c_int
     _lib = L
     return L
@@ -169,6 +177,34 @@ def measure_fp32_peak(device: int = -1):
     tf, mhz = C.c_double(), C.c_double()
     _check(lib().bh_measure_fp32_peak(device, C.byref(tf), C.byref(mhz)))
     return tf.value, mhz.value
+
+
+def generate_host(kind: str, n_bodies: int, seed: int = 12345, first: int = 0, round6: bool = False):
+    """Seeded bodies [first, first + n_bodies) of the counter-based generators (csrc/generate.cu) on the host —
+    the same values ``Simulation.generate`` writes on the device (up to the last bits of sqrt / sin / cos / pow).
+    Returns (pos, vel, mass)."""
+    pos = np.empty((n_bodies, 2)); vel = np.empty((n_bodies, 2)); mass = np.empty(n_bodies)
+    dp = C.POINTER(C.c_double)
+    _check(lib().bh_generate_host(GENERATOR_KINDS[kind], seed, first, n_bodies, int(round6), pos.ctypes.data_as(dp),
+                                  vel.ctypes.data_as(dp), mass.ctypes.data_as(dp)))
+    return pos, vel, mass
+
+
+def philox4x32_10(counter, key):
+    c = (C.c_uint32 * 4)(*counter); k = (C.c_uint32 * 2)(*key); out = (C.c_uint32 * 4)()
+    lib().bh_philox4x32_10(c, k, out)
+    return list(out)
+
+
+def write_init_files(directory: str, pos, vel, mass):
+    """The reference's three initial-condition files (writers of project.cu:236-246, :268-281) through the C-ABI."""
+    pos, vel, mass = _f64(pos, (-1, 2)), _f64(vel, (-1, 2)), _f64(mass, (-1,))
+    os.makedirs(directory, exist_ok=True)
+    dp = C.POINTER(C.c_double)
+    _check(lib().bh_write_init_files(os.path.join(directory, "masses_init.txt").encode(),
+                                     os.path.join(directory, "positions_init.txt").encode(),
+                                     os.path.join(directory, "velocities_init.txt").encode(), mass.shape[0],
+                                     mass.ctypes.data_as(dp), pos.ctypes.data_as(dp), vel.ctypes.data_as(dp)))
 
 
 def load_text(directory: str, n_bodies: int):
@@ -262,6 +298,11 @@ class Simulation:
         if not hasattr(vel, "data_ptr"):
             vel = _f64(vel, (self.n, 2))
         _check(lib().bh_set_velocities(self._h, _ptr(vel)))
+
+    def generate(self, kind: str, seed: int = 12345):
+        """Fill the context's bodies on the device with a seeded distribution (a rank of a multi-rank context
+        generates only its slice); see generate_host for the host twin."""
+        _check(lib().bh_generate(self._h, GENERATOR_KINDS[kind], seed))
 
     def snapshot(self):
         _check(lib().bh_snapshot(self._h))

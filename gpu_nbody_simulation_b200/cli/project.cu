@@ -16,7 +16,7 @@
 // defaults.  N_THREADS is accepted and ignored (it is the course experiment's grid-stride knob,
 // SURVEY §2.1).  Differences from the reference, all opt-in or documented in DESIGN.md:
 //   * initial conditions come from the three text files (the reference's README toggle); if they
-//     are absent, a SEEDED uniform square (project.cu:30-35 ranges) replaces the time-seeded cuRAND;
+//     are absent, a SEEDED uniform square (bh_generate_host, project.cu:30-35 ranges) replaces the time-seeded cuRAND;
 //   * -DBH_POSITIONS_TXT=1 also writes the trajectory file positions.txt that plot_2d.py reads
 //     (format of savePositions, project.cu:855-863), which the reference's GPU path never writes;
 //   * cap-level single leaves print the occupant's real position (reference: out-of-bounds read).
@@ -55,6 +55,7 @@
 #include "../csrc/traverse.cu"
 #include "../csrc/direct.cu"
 #include "../csrc/peer_comm.cu"
+#include "../csrc/generate.cu"
 #include "../csrc/host_io.cpp"
 
 #include <chrono>
@@ -69,16 +70,6 @@ static void die(const char* what) {
     exit(1);
 }
 
-// splitmix64: seeded stand-in for the reference's time-seeded generators (project.cu:84-101)
-static double uniform01(uint64_t& s) {
-    s += 0x9e3779b97f4a7c15ull;
-    uint64_t z = s;
-    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-    z ^= z >> 31;
-    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
-}
-
 int main() {
     const int64_t n = (int64_t)(N_BODIES);
     const int n_steps = (int)(N_SIMULATIONS);
@@ -88,11 +79,11 @@ int main() {
                      vel.data()) == BH_OK) {
         printf("Loaded %lld bodies from text files.\n", (long long)n);           // project.cu:160
     } else {
-        fprintf(stderr, "note: %s; using a seeded uniform square instead\n", bh_last_error());
-        uint64_t s = 12345;
-        for (int64_t i = 0; i < n; ++i) mass[i] = pow(10.0, -1.0 + uniform01(s) * (log10(0.5) + 1.0));   // project.cu:30-31
-        for (int64_t i = 0; i < 2 * n; ++i) pos[i] = -0.1 + uniform01(s) * 0.2;                            // :32-33
-        for (int64_t i = 0; i < 2 * n; ++i) vel[i] = -1e-4 + uniform01(s) * 2e-4;                          // :34-35
+        // the reference's default: random bodies (initializeGpu, project.cu:1062) — here SEEDED (Philox, seed
+        // 12345), same ranges (project.cu:30-35), rounded like the reference's own text files would be
+        fprintf(stderr, "note: %s; using the seeded uniform square instead\n", bh_last_error());
+        if (bh_generate_host(BH_GEN_UNIFORM_SQUARE, 12345, 0, n, 1, pos.data(), vel.data(), mass.data()) != BH_OK)
+            die("bh_generate_host");
     }
 
     auto t0 = std::chrono::high_resolution_clock::now();                         // project.cu:1083

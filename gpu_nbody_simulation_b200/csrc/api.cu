@@ -1018,6 +1018,38 @@ int bh_direct_forces(bh_ctx* c, double* out, float* device_ms) {
     return BH_OK;
 }
 
+int bh_generate(bh_ctx* c, int32_t kind, uint64_t seed) {
+    if (!c) { set_error("null context"); return BH_ERR_INVALID; }
+    if (kind < BH_GEN_UNIFORM_SQUARE || kind > BH_GEN_PLUMMER_2D) { set_error("unknown generator kind %d", kind); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    launch_generate(kind, seed, c->own_lo, c->own_hi, c->pos, c->vel, c->mass, c->stream);
+    BH_TRY(check_launch());
+    BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->mass_complete = c->p.n_ranks == 1;
+    c->bodies_set = true;
+    c->tree_valid = false;
+    return BH_OK;
+}
+
+void bh_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) { philox_host(counter, key, out); }
+
+int bh_generate_host(int32_t kind, uint64_t seed, int64_t first, int64_t count, int32_t r6, double* pos, double* vel,
+                     double* mass) {
+    if (!pos || !vel || !mass || first < 0 || count < 0) { set_error("bh_generate_host: bad arguments"); return BH_ERR_INVALID; }
+    BH_TRY(generate_host(kind, seed, first, first + count, pos, vel, mass));
+    if (r6) {
+        for (int64_t i = 0; i < 2 * count; ++i) { pos[i] = round6(pos[i]); vel[i] = round6(vel[i]); }
+        for (int64_t i = 0; i < count; ++i) mass[i] = round6(mass[i]);
+    }
+    return BH_OK;
+}
+
+int bh_write_init_files(const char* mf, const char* pf, const char* vf, int64_t n, const double* mass, const double* pos,
+                        const double* vel) {
+    if (!mf || !pf || !vf || !mass || !pos || !vel || n < 0) { set_error("bh_write_init_files: bad arguments"); return BH_ERR_INVALID; }
+    return write_init_files(mf, pf, vf, n, mass, pos, vel);
+}
+
 int bh_load_text(const char* mf, const char* pf, const char* vf, int64_t n, double* mass, double* pos, double* vel) {
     return load_text(mf, pf, vf, n, mass, pos, vel);
 }

@@ -152,6 +152,11 @@ void launch_chunk_lists(const uint32_t* sidx, int64_t n, const ChunkBounds& cb, 
 void launch_direct(const double2* pos, const double* mass, int64_t n, double G, float4* packed,
                    double2* force, cudaStream_t st);
 int measure_fp32_peak(int device, double* tflops, double* mhz);
+// generate.cu: seeded initial conditions; bodies [i0, i1) into host arrays / bodies [lo, hi) into device arrays
+int generate_host(int kind, uint64_t seed, int64_t i0, int64_t i1, double* pos, double* vel, double* mass);
+void philox_host(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
+void launch_generate(int kind, uint64_t seed, int64_t lo, int64_t hi, double2* pos, double2* vel, double* mass,
+                     cudaStream_t st);
 
 int traverse_launch_count();
 extern thread_local uint64_t g_launches;  // kernels launched by this library on this thread

@@ -123,4 +123,29 @@ int append_positions_txt(const char* path, const double* pos, int64_t n, double 
     return BH_OK;
 }
 
+// initializeMasses / initializeVectors with saveToFile (project.cu:236-246, :268-281): `ofs << value` with the
+// default ostream format, i.e. "%g" with 6 significant digits.
+int write_init_files(const char* mf, const char* pf, const char* vf, int64_t n, const double* mass, const double* pos,
+                     const double* vel) {
+    FILE* f = fopen(mf, "w");
+    if (!f) { set_error("Failed to open file for writing masses."); return BH_ERR_IO; }       // project.cu:239
+    for (int64_t i = 0; i < n; ++i) fprintf(f, "%g\n", mass[i]);
+    fclose(f);
+    const char* names[2] = {pf, vf};
+    const double* data[2] = {pos, vel};
+    for (int k = 0; k < 2; ++k) {
+        f = fopen(names[k], "w");
+        if (!f) { set_error("Failed to open file for writing vectors."); return BH_ERR_IO; }  // project.cu:271
+        for (int64_t i = 0; i < n; ++i) fprintf(f, "%g %g\n", data[k][2 * i], data[k][2 * i + 1]);
+        fclose(f);
+    }
+    return BH_OK;
+}
+
+double round6(double v) {
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.6g", v);
+    return strtod(buf, nullptr);
+}
+
 }  // namespace bh

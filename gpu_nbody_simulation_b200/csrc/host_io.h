@@ -23,5 +23,8 @@ int64_t canonical_rows(const HostTree& t, double* out_rows, int64_t cap_rows);
 int dump_quadtree_txt(const HostTree& t, const char* path);
 int load_text(const char* mf, const char* pf, const char* vf, int64_t n, double* mass, double* pos, double* vel);
 int append_positions_txt(const char* path, const double* pos, int64_t n, double time, int truncate);
+int write_init_files(const char* mf, const char* pf, const char* vf, int64_t n, const double* mass, const double* pos,
+                     const double* vel);
+double round6(double v);   // value after a round trip through the "%.6g" text format
 
 }  // namespace bh

@@ -172,8 +172,26 @@ int bh_last_step_ms(bh_ctx* ctx, float* ms);
 /* ---- direct all-pairs kernel (BASELINE config 5; formula of main_approach_1.cpp:53-75) ---- */
 int bh_direct_forces(bh_ctx* ctx, double* out_xy_host /* may be NULL */, float* device_ms);
 
+/* ---- seeded initial conditions (replaces initializeGpu / initializeCpu, project.cu:298-341, whose cuRAND
+ * states are seeded with time(0)): counter-based Philox4x32-10, body i is a pure function of (seed, i);
+ * value ranges of project.cu:30-35; the disk and the projected Plummer sphere are BASELINE configs 2-4. ---- */
+enum { BH_GEN_UNIFORM_SQUARE = 0, BH_GEN_UNIFORM_DISK = 1, BH_GEN_PLUMMER_2D = 2 };
+/* fills the context's bodies on the device (a rank of a multi-rank context generates only its slice) */
+int bh_generate(bh_ctx* ctx, int32_t kind, uint64_t seed);
+/* the same bodies [first, first + count) into host arrays; needs no GPU.  round6 != 0 passes every value
+ * through the reference writers' text format (6 significant digits) so that arrays and files agree. */
+int bh_generate_host(int32_t kind, uint64_t seed, int64_t first, int64_t count, int32_t round6,
+                     double* pos_xy_host, double* vel_xy_host, double* mass_host);
+/* the raw generator (Philox4x32-10, Random123 conventions), for known-answer tests and reproducibility */
+void bh_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
+
 /* ---- text formats of the reference ---- */
 /* loadSimulationDataFromText project.cu:103-161: first n lines of each file */
+/* writers of the three initial-condition files, format of project.cu:236-246, :268-281 (default ostream
+ * formatting = "%g" with 6 significant digits; masses one per line, vectors "x y" per line) */
+int bh_write_init_files(const char* masses_file, const char* positions_file, const char* velocities_file,
+                        int64_t n_bodies, const double* mass_host, const double* pos_xy_host,
+                        const double* vel_xy_host);
 int bh_load_text(const char* masses_file, const char* positions_file, const char* velocities_file,
                  int64_t n, double* mass_out, double* pos_out, double* vel_out);
 /* savePositions project.cu:855-863: appends "time i x y \n" (std::to_string, 6 decimals) */
