@@ -1,0 +1,56 @@
+"""CPU tests of bench.py's host-side helpers (no GPU): clock-sample parsing, NUMA pinning fall-back,
+the reference arm's JSON line."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+class _FakeProc:
+    def terminate(self):
+        pass
+
+
+class _FakeThread:
+    def join(self, timeout=None):
+        pass
+
+
+def test_clock_sampler_parses_only_samples_after_the_mark():
+    s = bench.ClockSampler("0,1")
+    s.proc, s.t = _FakeProc(), _FakeThread()
+    s.lines = ["0, 1200, 1965, 300.1, 0x0, Not Active, Not Active, Not Active, Not Active\n"]   # before the mark
+    s.mark()
+    s.lines += ["0, 1965, 1965, 900.5, 0x4, Not Active, Not Active, Not Active, Active\n",
+                "1, 1950, 1965, 880.0, 0x0, Not Active, Not Active, Not Active, Not Active\n",
+                "garbage line\n",
+                "1, [N/A], 1965, 880.0, 0x0, Not Active, Not Active, Not Active, Not Active\n"]
+    out = s.stop()
+    assert out["samples"] == 2 and out["sm_mhz"] == 1957.5 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"]
+
+
+def test_clock_sampler_without_nvidia_smi():
+    s = bench.ClockSampler("0")
+    assert s.stop()["reasons"] == ["nvidia-smi unavailable"]
+
+
+def test_numa_pinning_is_best_effort():
+    before = os.sched_getaffinity(0)
+    assert bench.pin_to_gpu_numa_node(0) is None or isinstance(bench.pin_to_gpu_numa_node(0), int)
+    os.sched_setaffinity(0, before)
+
+
+def test_reference_arm_prints_the_contract_line():
+    # 65 536-body sample keeps this to a few seconds; under torchrun only rank 0 prints
+    env = dict(os.environ, RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+    line = bench.cpu_reference_run(65_536, 1, 0, budget_s=5.0)[1]
+    assert line["kind"] in ("reference", "port") and line["cores"] == 1 and line["value"] > 0
+    json.dumps(line)
