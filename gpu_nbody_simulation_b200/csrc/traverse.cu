@@ -350,7 +350,11 @@ traverse_f32_kernel(const __grid_constant__ TravArgs a) {
 // (the SFU pipe, 16 lanes/clk/SM on B200, is this kernel's scarcest resource: ncu math_pipe_throttle);
 // relative error (eps/d)^2, i.e. < 1e-6 for separations above 1e-12 (eps = 1e-15).
 // EXACT_EPS = true (BH_FLAG_EXACT_EPS): MUFU.SQRT + MUFU.RCP, exact for any separation.
-template <bool INTEGRATE, bool EXACT_EPS>
+// PREFETCH (experiment, bh_params.reserved[0] == 4; not yet measured): when a child is pushed, lane 0 touches the
+// 128-byte line of THAT child's children (prefetch.global.L1), one iteration or more before the child is
+// popped — ncu shows 37 % of the node fetches missing L1 (~300 cycles to L2) and long-scoreboard stalls.
+// Unlike the v7 experiment the stack discipline is untouched: +1 predicated instruction per child.
+template <bool INTEGRATE, bool EXACT_EPS, bool PREFETCH = false>
 __global__ void __launch_bounds__(kTravThreads, kPairMinBlocks * (256 / kTravThreads))
 traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
     using SE = StackEntry<2>;
@@ -456,6 +460,10 @@ traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
             const bool push = (m[0] | m[1]) != 0u;
             SE::store_if(push & (lane == 0), sp, base + q, m);
             sp += push ? SE::kBytes : 0u;
+            if constexpr (PREFETCH) {
+                asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %0, 0;\n @p prefetch.global.L1 [%1];\n}"
+                             ::"r"((uint32_t)(push & (lane == 0))), "l"(a.rec + (4u * (base + q) + 1u)) : "memory");
+            }
         }
     }
     const float ax[2] = {accx.x, accx.y}, ay[2] = {accy.x, accy.y};
@@ -708,7 +716,7 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
     // two bodies per lane halve the node traffic and the control overhead per body, but need >= ~400k
     // bodies to keep every SM's warp slots full (ncu: profiles/r01_traverse_v4_*)
     const bool exact_leaves = p.flags & BH_FLAG_EXACT_LEAVES;   // extension: generic 1-body-per-lane / FP64 kernels only
-    const int bpl = exact_leaves ? 1 : (p.reserved[0] == 1) ? 1 : (p.reserved[0] == 2 || p.reserved[0] == 3) ? 2 : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
+    const int bpl = exact_leaves ? 1 : (p.reserved[0] == 1) ? 1 : (p.reserved[0] >= 2 && p.reserved[0] <= 4) ? 2 : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
     // previous operation on the stream = tree_top_kernel (or a peer-exchange kernel; g_pdl is off there)
 #define BH_GO(K) launch_chain(K, dim3(blocks), dim3(kTravThreads), st, true, a)
     if (fp64) {
@@ -726,6 +734,8 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
         if (exact_leaves) {
             if (integrate) { if (count) BH_GO((traverse_f32_kernel<1, true, true, true>)); else BH_GO((traverse_f32_kernel<1, true, false, true>)); }
             else { if (count) BH_GO((traverse_f32_kernel<1, false, true, true>)); else BH_GO((traverse_f32_kernel<1, false, false, true>)); }
+        } else if (bpl == 2 && !count && p.reserved[0] == 4 && !(p.flags & BH_FLAG_EXACT_EPS)) {
+            if (integrate) BH_GO((traverse_f32_pair_kernel<true, false, true>)); else BH_GO((traverse_f32_pair_kernel<false, false, true>));
         } else if (bpl == 2 && !count && p.reserved[0] != 3) {
             const bool exact = p.flags & BH_FLAG_EXACT_EPS;
             if (integrate) { if (exact) BH_GO((traverse_f32_pair_kernel<true, true>)); else BH_GO((traverse_f32_pair_kernel<true, false>)); }
