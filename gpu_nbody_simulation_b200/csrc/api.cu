@@ -111,6 +111,7 @@ struct bh_ctx {
     const void* host_graph_key[4] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t host_graph_kernels = 0;
     bool host_graph_failed = false;
+    bool host_pipeline_multi = false;   // env BH_HOST_PIPELINE_MULTI=1 (experiment, see bh_step_host)
     // BH_HOST_TRACE=1: timeline of one bh_step_host call (direct submission), printed to stderr
     bool host_trace = false;
     std::vector<std::pair<const char*, cudaEvent_t>> trace_ev;
@@ -234,7 +235,8 @@ int allreduce_f64(bh_ctx* c, double* buf, size_t count, ncclRedOp_t op) {
 // `src` = the positions the tree is built from: c->pos, or the snapshot when a step restarts from it
 // (out-of-place step: every kernel reads the snapshot, only the fused integrator writes c->pos / c->vel,
 // so no restore copy is needed).
-int enqueue_build(bh_ctx* c, bool full = false, const double2* src = nullptr) {
+// `mass_ready` (optional, pipelined host step): event to wait for before the first kernel that reads masses.
+int enqueue_build(bh_ctx* c, bool full = false, const double2* src = nullptr, cudaEvent_t mass_ready = nullptr) {
     if (!src) src = c->pos;
     g_pdl = c->pdl;
     zero_scratch(c);
@@ -264,6 +266,7 @@ int enqueue_build(bh_ctx* c, bool full = false, const double2* src = nullptr) {
         prof_mark(c, 1);
         launch_sort(c->keys, c->idx, n_own, c->sp_own, c->s, &c->sorted, c->stream);
         prof_mark(c, 2);
+        if (mass_ready) cudaStreamWaitEvent(c->stream, mass_ready, 0);
         launch_tree_runs(c->keys[c->sorted], c->idx[c->sorted], src, c->mass, n_own, c->p, c->d, c->tree, c->s,
                          c->cell_sums, c->stream);
         const double* reduced = c->cell_sums;
@@ -524,6 +527,7 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     { const char* e = getenv("BH_KEYS_TABLE"); c->keys_table = e && e[0] == '1'; }
     { const char* e = getenv("BH_PDL"); c->pdl = e && e[0] == '1' && p->n_ranks == 1; }
     { const char* e = getenv("BH_HOST_TRACE"); c->host_trace = e && e[0] == '1'; }
+    { const char* e = getenv("BH_HOST_PIPELINE_MULTI"); c->host_pipeline_multi = e && e[0] == '1'; }
     { const char* e = getenv("BH_HOST_CHUNKS"); if (e && atoi(e) >= 1) c->host_chunks = std::min(atoi(e), kMaxHostChunks); }
     if (p->device >= 0) c->device = p->device; else BH_CUDA_OK(cudaGetDevice(&c->device));
     if (c->device >= ndev) { set_error("device %d of %d", c->device, ndev); delete c; return BH_ERR_INVALID; }
@@ -765,6 +769,38 @@ int bh_step_from_snapshot(bh_ctx* c, int32_t nsteps) {
 // their uploads overlap the build and the traversal.  out_pos_host receives the new positions.
 int bh_step_host(bh_ctx* c, const double* pos, const double* vel, const double* mass, double* out_pos) {
     if (!c || !pos || !vel || !mass || !out_pos) { set_error("null argument"); return BH_ERR_INVALID; }
+    if (c->p.n_ranks > 1 && c->host_pipeline_multi && c->p2p_ready && !c->profiling) {
+        // EXPERIMENT (env BH_HOST_PIPELINE_MULTI=1, written after round 1's GPU budget was spent, not yet run):
+        // the single-rank pipeline for one rank's slice — positions up, then bounds / keys / sort while masses
+        // and velocities are still in flight; integrator + download on the high-priority stream.
+        DeviceGuard g(c->device);
+        const int64_t lo = c->own_lo, cnt = c->own_hi - c->own_lo;
+        BH_CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+        BH_CUDA_OK(cudaEventRecord(c->ev_fork, c->stream));
+        BH_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_fork, 0));
+        BH_CUDA_OK(cudaMemcpyAsync(c->pos + lo, pos + 2 * lo, sizeof(double2) * cnt, cudaMemcpyHostToDevice, c->copy_stream));
+        BH_CUDA_OK(cudaEventRecord(c->ev_up[0], c->copy_stream));
+        BH_CUDA_OK(cudaMemcpyAsync(c->mass + lo, mass + lo, sizeof(double) * cnt, cudaMemcpyHostToDevice, c->copy_stream));
+        BH_CUDA_OK(cudaEventRecord(c->ev_up[1], c->copy_stream));
+        BH_CUDA_OK(cudaMemcpyAsync(c->vel + lo, vel + 2 * lo, sizeof(double2) * cnt, cudaMemcpyHostToDevice, c->copy_stream));
+        BH_CUDA_OK(cudaEventRecord(c->ev_vel[0], c->copy_stream));
+        c->mass_complete = false;
+        BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[0], 0));
+        BH_TRY(enqueue_build(c, false, nullptr, c->ev_up[1]));
+        BH_TRY(enqueue_forces(c, false));
+        BH_CUDA_OK(cudaEventRecord(c->ev_trav[0], c->stream));
+        BH_CUDA_OK(cudaStreamWaitEvent(c->dl_stream, c->ev_trav[0], 0));
+        BH_CUDA_OK(cudaStreamWaitEvent(c->dl_stream, c->ev_vel[0], 0));
+        launch_integrate(c->pos, c->vel, c->acc, c->force, c->mass, c->own_lo, c->own_hi, c->p.dt, c->dl_stream);
+        BH_TRY(check_launch());
+        BH_CUDA_OK(cudaMemcpyAsync(out_pos + 2 * lo, c->pos + lo, sizeof(double2) * cnt, cudaMemcpyDeviceToHost, c->dl_stream));
+        BH_CUDA_OK(cudaEventRecord(c->ev_dl, c->dl_stream));
+        BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_dl, 0));
+        BH_CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+        BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+        c->bodies_set = true; c->tree_valid = false; c->timed = true;
+        return BH_OK;
+    }
     if (c->p.n_ranks > 1) {
         // multi-rank: every rank moves only its own slice both ways (out_pos gets this rank's slice; the
         // other entries are left untouched — one process per GPU owns one slice of the host arrays)

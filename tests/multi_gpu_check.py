@@ -22,6 +22,9 @@ ap.add_argument("--bodies", dest="n", type=int, default=200_000)
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--fp64", action="store_true")
 ap.add_argument("--no-p2p", action="store_true", help="NCCL all-reduces instead of the peer-memory exchange")
+ap.add_argument("--host-step", action="store_true",
+                help="also check ONE bh_step_host call (own slice up / down) against the single-GPU step; with "
+                     "BH_HOST_PIPELINE_MULTI=1 this exercises the pipelined multi-rank host step")
 a = ap.parse_args()
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -41,11 +44,26 @@ if not a.no_p2p:
     handles = [None] * world
     dist.all_gather_object(handles, sim.comm_handle())
     sim.attach_peers(handles)
+host_slice = None
+if a.host_step:
+    lo_r, hi_r = bh.shard_range(a.n, world, rank)
+    host_slice = sim.step_host(pos, vel, mass)[lo_r:hi_r].copy()      # a rank's call fills only its own slice
 sim.set_bodies(pos, vel, mass)
 sim.step(a.steps)
 p_multi, v_multi, f_multi = sim.positions(), sim.velocities(), sim.forces()
 sim.close()
 ok = True
+if a.host_step:
+    with bh.Simulation(a.n, device=local, **kw) as one:
+        one.set_bodies(pos, vel, mass)
+        one.step(1)
+        want = one.positions()[lo_r:hi_r]
+    e = float(np.sqrt(((host_slice - want) ** 2).sum() / (want ** 2).sum()))
+    print(f"rank {rank}: bh_step_host slice vs single-GPU step: rel-RMS {e:.3e}", flush=True)
+    ok = ok and e <= (1e-8 if a.fp64 else 1e-6)
+    okt = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    ok = bool(int(okt.item()))
 if rank == 0:
     lo, hi = bh.shard_range(a.n, world, 0)
     with bh.Simulation(a.n, device=local, **kw) as one:

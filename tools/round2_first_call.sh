@@ -25,3 +25,7 @@ timeout 120 python tools/profile_step.py --steps 6 --bpl 4 > gpurun_out/r2_profi
 tail -5 gpurun_out/r2_exact_leaves_pytest.log gpurun_out/r2_pytest.log gpurun_out/r2_smoke.log
 tail -3 gpurun_out/r2_prefetch_pytest.log; tail -1 gpurun_out/r2_profile_default.log gpurun_out/r2_profile_exact_leaves.log gpurun_out/r2_profile_prefetch.log
 cut -c1-300 gpurun_out/r2_bench_default.json
+# 7. (needs 2 GPUs: gpurun --gpus 2) the pipelined multi-rank host step, parity then e2e:
+#   BH_HOST_PIPELINE_MULTI=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+#       --master-port 29533 tests/multi_gpu_check.py --bodies 100001 --steps 2 --host-step
+#   BH_HOST_PIPELINE_MULTI=1 python -m torch.distributed.run ... bench.py --gpus 2 --steps 100   (compare e2e with the plain run)
