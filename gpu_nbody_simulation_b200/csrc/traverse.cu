@@ -69,6 +69,8 @@ struct TravArgs {
     const uint32_t* t_count;    // bodies per pyramid cell
     const uint32_t* t_first;    // sorted position of a cell's first body
     uint32_t finest_off;        // pyramid index of the first cap-level cell
+    // pair kernel, REMAP variants only: number of SMs (the grid is padded to a multiple of it)
+    uint32_t remap_cols;
 };
 
 __device__ __forceinline__ float approx_sqrt(float x) {
@@ -354,14 +356,21 @@ traverse_f32_kernel(const __grid_constant__ TravArgs a) {
 // 128-byte line of THAT child's children (prefetch.global.L1), one iteration or more before the child is
 // popped — ncu shows 37 % of the node fetches missing L1 (~300 cycles to L2) and long-scoreboard stalls.
 // Unlike the v7 experiment the stack discipline is untouched: +1 predicated instruction per child.
-template <bool INTEGRATE, bool EXACT_EPS, bool PREFETCH = false>
+// REMAP (experiment, reserved[0] == 5, or 6 together with PREFETCH; not yet measured): blocks that are resident on
+// the same SM at the same time should walk NEIGHBOURING bodies, so that the near-field cells one warp pulls into
+// L1 are hits for the others (ncu: 63 % L1 hit rate).  The hardware hands block b of the first wave to SM b mod
+// #SMs, so the body range is taken from the transposed index (b mod #SMs) * rows + b / #SMs; the grid is padded
+// to #SMs * rows blocks, surplus blocks see no bodies and leave after the root.
+template <bool INTEGRATE, bool EXACT_EPS, bool PREFETCH = false, bool REMAP = false>
 __global__ void __launch_bounds__(kTravThreads, kPairMinBlocks * (256 / kTravThreads))
 traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
     using SE = StackEntry<2>;
     __shared__ __align__(16) uint8_t s_stack[kTravWarps][kStackCap * SE::kBytes];
     pdl_entry();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t warp_slot0 = ((int64_t)blockIdx.x * kTravWarps + warp) * 64;
+    uint32_t bid = blockIdx.x;
+    if constexpr (REMAP) bid = (blockIdx.x % a.remap_cols) * (gridDim.x / a.remap_cols) + blockIdx.x / a.remap_cols;
+    const int64_t warp_slot0 = ((int64_t)bid * kTravWarps + warp) * 64;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&s_stack[warp][0]);
 
     uint32_t body[2], selfn[2];
@@ -711,12 +720,13 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
     a.n_slots = own_n;
     a.G = p.G; a.dt = p.dt; a.theta = p.theta; a.dist_eps = p.dist_eps;
     a.t_count = t.count; a.t_first = t.first; a.finest_off = (uint32_t)d.level_off[d.finest];
+    a.remap_cols = 0;
     if (own_n <= 0) return;
     const bool fp64 = p.flags & BH_FLAG_FP64_TRAVERSAL, count = p.flags & BH_FLAG_COUNTERS;
     // two bodies per lane halve the node traffic and the control overhead per body, but need >= ~400k
     // bodies to keep every SM's warp slots full (ncu: profiles/r01_traverse_v4_*)
     const bool exact_leaves = p.flags & BH_FLAG_EXACT_LEAVES;   // extension: generic 1-body-per-lane / FP64 kernels only
-    const int bpl = exact_leaves ? 1 : (p.reserved[0] == 1) ? 1 : (p.reserved[0] >= 2 && p.reserved[0] <= 4) ? 2 : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
+    const int bpl = exact_leaves ? 1 : (p.reserved[0] == 1) ? 1 : (p.reserved[0] >= 2 && p.reserved[0] <= 6) ? 2 : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
     // previous operation on the stream = tree_top_kernel (or a peer-exchange kernel; g_pdl is off there)
 #define BH_GO(K) launch_chain(K, dim3(blocks), dim3(kTravThreads), st, true, a)
     if (fp64) {
@@ -736,6 +746,17 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
             else { if (count) BH_GO((traverse_f32_kernel<1, false, true, true>)); else BH_GO((traverse_f32_kernel<1, false, false, true>)); }
         } else if (bpl == 2 && !count && p.reserved[0] == 4 && !(p.flags & BH_FLAG_EXACT_EPS)) {
             if (integrate) BH_GO((traverse_f32_pair_kernel<true, false, true>)); else BH_GO((traverse_f32_pair_kernel<false, false, true>));
+        } else if (bpl == 2 && !count && (p.reserved[0] == 5 || p.reserved[0] == 6) && !(p.flags & BH_FLAG_EXACT_EPS)) {
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            a.remap_cols = (uint32_t)sms;
+            blocks = (blocks + a.remap_cols - 1) / a.remap_cols * a.remap_cols;    // padded: surplus blocks find no bodies
+            if (p.reserved[0] == 5) {
+                if (integrate) BH_GO((traverse_f32_pair_kernel<true, false, false, true>)); else BH_GO((traverse_f32_pair_kernel<false, false, false, true>));
+            } else {
+                if (integrate) BH_GO((traverse_f32_pair_kernel<true, false, true, true>)); else BH_GO((traverse_f32_pair_kernel<false, false, true, true>));
+            }
         } else if (bpl == 2 && !count && p.reserved[0] != 3) {
             const bool exact = p.flags & BH_FLAG_EXACT_EPS;
             if (integrate) { if (exact) BH_GO((traverse_f32_pair_kernel<true, true>)); else BH_GO((traverse_f32_pair_kernel<true, false>)); }

@@ -427,6 +427,8 @@ def test_traversal_variants_agree(shipped40k):
     import os
     if os.environ.get("BH_TEST_UNVALIDATED") == "1":       # written after round 1's GPU budget was spent
         variants["pair_prefetch"] = dict(bodies_per_lane=4)
+        variants["pair_sm_local"] = dict(bodies_per_lane=5)
+        variants["pair_sm_local_prefetch"] = dict(bodies_per_lane=6)
     for name, kw in variants.items():
         with build(pos, vel, mass, **kw) as sim:
             sim.compute_forces()
