@@ -171,6 +171,29 @@ def cpu_reference_run(n_bodies, steps, warmup, budget_s=150.0):
                    "ms_per_step": secs * 1e3}
 
 
+def cpu_port_all_cores(pos, mass, budget_s=8.0):
+    """The oracle PORT (oracle/bh_oracle.c, OpenMP over bodies in the force loop — the modification SURVEY 8d allows
+    as a clearly labelled extra; the reference itself has no threading) on all host cores: serial tree build +
+    forces for every `stride`-th body, extrapolated to all bodies.  Bounded to ~budget_s seconds."""
+    import oracle
+    n = mass.shape[0]
+    nt = oracle.max_threads()
+    t0 = time.perf_counter()
+    tree = oracle.Tree(pos, mass)
+    t1 = time.perf_counter()
+    probe_stride = 256
+    tree.forces(stride=probe_stride, nthreads=nt)                 # short probe to size the sample
+    est_full = (time.perf_counter() - t1) * probe_stride
+    stride = max(1, int(est_full / budget_s + 0.999))
+    t2 = time.perf_counter()
+    tree.forces(stride=stride, nthreads=nt)
+    t3 = time.perf_counter()
+    secs = (t1 - t0) + (t3 - t2) * stride
+    return {"value": n / secs, "unit": UNIT, "cores": nt, "kind": "port (OpenMP over bodies, not the reference's code path)",
+            "sample": f"serial tree build {1e3 * (t1 - t0):.0f} ms + forces for every {stride}th of {n} bodies on {nt} threads "
+                      f"({1e3 * (t3 - t2):.0f} ms), extrapolated; integrator not included (bandwidth-trivial)"}
+
+
 def reference_gpu_run(pos, vel, mass, device):
     """The reference's OWN GPU program path on this GPU (north_star's second baseline): unmodified
     project.cu, runSimulationGpu with N_THREADS = N_BODIES, compiled for sm_100a (oracle/_ref/
@@ -404,6 +427,10 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _, cpu_baseline = cpu_reference_run(1_000_000, 1, 0, budget_s=30.0)
         cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        try:
+            cpu_baseline["port_all_cores"] = cpu_port_all_cores(pos, mass)
+        except Exception as e:   # an extra, never worth losing the line for
+            cpu_baseline["port_all_cores"] = {"unavailable": str(e)[:200]}
 
     gpu_baseline = None
     if rank == 0 and world == 1 and not args.no_gpu_baseline and not strong and args.dist == "disk" and args.max_depth == 10:
