@@ -432,6 +432,29 @@ def run_ours(args):
         except Exception as e:   # an extra, never worth losing the line for
             cpu_baseline["port_all_cores"] = {"unavailable": str(e)[:200]}
 
+    # accuracy of the timed configuration (BASELINE.json's metric carries "force rel-RMS error vs ref"): forces of
+    # the default (FP32) traversal against the reference tree forces from the pinned oracle, on a body sample
+    accuracy = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            import oracle
+            with bh.Simulation(n, device=local, max_depth=args.max_depth) as sa:
+                sa.set_bodies(pos, vel, mass)
+                sa.build_tree()
+                sa.compute_forces()
+                f_gpu = sa.forces()
+            stride = max(1, n // 4096)
+            tree = oracle.Tree(pos, mass, oracle.default_params(max_depth=args.max_depth))
+            f_ref, _ = tree.forces(stride=stride, nthreads=oracle.max_threads())
+            a_, b_ = f_gpu[::stride], f_ref[::stride]
+            ok = np.isfinite(b_).all(axis=1)
+            err = float(np.sqrt(((a_[ok] - b_[ok]) ** 2).sum() / max((b_[ok] ** 2).sum(), 1e-300)))
+            accuracy = {"force_rel_rms_vs_reference_tree": err, "bar": 1e-5,
+                        "sample": f"every {stride}th body ({int(ok.sum())} bodies) of the timed workload; reference tree "
+                                  "forces from the C restatement pinned bit-for-bit to the reference (oracle/)"}
+        except Exception as e:   # never worth losing the line for
+            accuracy = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
     gpu_baseline = None
     if rank == 0 and world == 1 and not args.no_gpu_baseline and not strong and args.dist == "disk" and args.max_depth == 10:
         gpu_baseline = reference_gpu_run(pos, vel, mass, local)
@@ -455,7 +478,7 @@ def run_ours(args):
                                            "box + cell-sum exchange by NVLink peer stores fused with the kernels")) if world > 1
                            else "single GPU", "host_numa_node": numa},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "gpu_baseline": gpu_baseline,
+                "roofline": roofline, "accuracy": accuracy, "cpu_baseline": cpu_baseline, "gpu_baseline": gpu_baseline,
                 "phases_us": phases,
                 "value_l2_flushed": n * K / (ms_flushed * 1e-3)}
         print(json.dumps(line), flush=True)
