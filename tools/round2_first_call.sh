@@ -25,6 +25,8 @@ timeout 120 python tools/profile_step.py --steps 4 --exact-leaves > gpurun_out/r
 timeout 120 python tools/profile_step.py --steps 6 --bpl 4 > gpurun_out/r2_profile_prefetch.log 2>&1
 timeout 120 python tools/profile_step.py --steps 6 --bpl 5 > gpurun_out/r2_profile_sm_local.log 2>&1
 timeout 120 python tools/profile_step.py --steps 6 --bpl 6 > gpurun_out/r2_profile_sm_local_prefetch.log 2>&1
+# 8. BASELINE config 1 shape (the reference's own N = 40 000, 10 free-running steps; step 0 is the non-degenerate one)
+timeout 120 python tools/free_run.py 40000 10 square > gpurun_out/r2_free_run_40000.log 2>&1
 tail -5 gpurun_out/r2_exact_leaves_pytest.log gpurun_out/r2_pytest.log gpurun_out/r2_smoke.log
 tail -3 gpurun_out/r2_prefetch_pytest.log; tail -1 gpurun_out/r2_profile_default.log gpurun_out/r2_profile_exact_leaves.log gpurun_out/r2_profile_prefetch.log gpurun_out/r2_profile_sm_local.log gpurun_out/r2_profile_sm_local_prefetch.log
 cut -c1-300 gpurun_out/r2_bench_default.json
