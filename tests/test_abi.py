@@ -97,3 +97,35 @@ def test_initial_condition_generators_are_seeded():
     assert np.all(np.hypot(p2[:, 0], p2[:, 1]) <= 0.1 + 1e-6)
     # %.6g round trip: values survive the reference's text writers unchanged
     assert np.array_equal(np.char.mod("%.6g", pos.ravel()).astype(float), pos.ravel())
+
+
+def test_header_is_plain_c_and_struct_layouts_match_the_python_mirror(tmp_path):
+    """include/bh.h must compile as C (the boundary is a C-ABI, no C++ / torch types) and the ctypes mirrors
+    must have the C compiler's sizes and field offsets."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    fields = {"bh_params": [f[0] for f in bh.Params._fields_], "bh_counters": [f[0] for f in bh.Counters._fields_],
+              "bh_timers": [f[0] for f in bh.Timers._fields_]}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "bh.h"', 'int main(void) {']
+    for st, fl in fields.items():
+        lines.append(f'  printf("{st} %zu\\n", sizeof({st}));')
+        for f in fl:
+            lines.append(f'  printf("{st}.{f} %zu\\n", offsetof({st}, {f}));')
+    lines += ['  printf("flags %u %u %u %u %u\\n", BH_FLAG_FP64_TRAVERSAL, BH_FLAG_COUNTERS, BH_FLAG_NO_GRAPH, BH_FLAG_EXACT_EPS, BH_FLAG_EXACT_LEAVES);',
+              '  printf("gen %d %d %d\\n", BH_GEN_UNIFORM_SQUARE, BH_GEN_UNIFORM_DISK, BH_GEN_PLUMMER_2D);',
+              '  return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = dict(l.split(" ", 1) for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for st, cls in (("bh_params", bh.Params), ("bh_counters", bh.Counters), ("bh_timers", bh.Timers)):
+        assert int(out[st]) == C.sizeof(cls), st
+        for f in fields[st]:
+            assert int(out[f"{st}.{f}"]) == getattr(cls, f).offset, f"{st}.{f}"
+    assert out["flags"].split() == [str(v) for v in (bh.BH_FLAG_FP64_TRAVERSAL, bh.BH_FLAG_COUNTERS, bh.BH_FLAG_NO_GRAPH,
+                                                      bh.BH_FLAG_EXACT_EPS, bh.BH_FLAG_EXACT_LEAVES)]
+    assert out["gen"].split() == [str(bh.GENERATOR_KINDS[k]) for k in ("uniform_square", "uniform_disk", "plummer_2d")]
