@@ -129,3 +129,25 @@ def test_header_is_plain_c_and_struct_layouts_match_the_python_mirror(tmp_path):
     assert out["flags"].split() == [str(v) for v in (bh.BH_FLAG_FP64_TRAVERSAL, bh.BH_FLAG_COUNTERS, bh.BH_FLAG_NO_GRAPH,
                                                       bh.BH_FLAG_EXACT_EPS, bh.BH_FLAG_EXACT_LEAVES)]
     assert out["gen"].split() == [str(bh.GENERATOR_KINDS[k]) for k in ("uniform_square", "uniform_disk", "plummer_2d")]
+
+
+def test_integration_stub_compiles_and_links(tmp_path):
+    """The reference-side binding shown in INTEGRATION.md (the replacement body of runSimulationGpu) must stay
+    valid: compile it with the reference's own typedefs (project.cu:38-43) and link it against libbh.so."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no C++ compiler")
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stub = re.search(r"```cpp\n(.*?)```", md, flags=re.S).group(1)
+    assert "runSimulationGpu" in stub and "bh_step" in stub
+    src = tmp_path / "stub.cpp"
+    src.write_text("#include <array>\n#include <cstdlib>\n#include <iostream>\n#define N_BODIES 1000\n#define N_SIMULATIONS 3\n"
+                   "using Vector = std::array<double, 2>;\nusing Positions = std::array<Vector, N_BODIES>;\n"
+                   "using Velocities = Positions;\nusing Masses = std::array<double, N_BODIES>;\n"
+                   "long long gpu_parallel_duration = 0;\n" + stub +
+                   "\nint main() { static Masses m; static Positions p; static Velocities v; if (m[0] > 1) runSimulationGpu(m, p, v); return 0; }\n")
+    pkg = os.path.join(ROOT, "gpu_nbody_simulation_b200")
+    subprocess.check_call([cxx, "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), str(src), "-L", pkg, "-lbh",
+                           "-Wl,--unresolved-symbols=ignore-in-shared-libs", "-o", str(tmp_path / "stub")])
