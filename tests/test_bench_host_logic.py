@@ -54,3 +54,12 @@ def test_reference_arm_prints_the_contract_line():
     line = bench.cpu_reference_run(65_536, 1, 0, budget_s=5.0)[1]
     assert line["kind"] in ("reference", "port") and line["cores"] == 1 and line["value"] > 0
     json.dumps(line)
+
+
+def test_shell_scripts_parse():
+    import glob
+    scripts = glob.glob(os.path.join(ROOT, "scripts", "*.sh")) + glob.glob(os.path.join(ROOT, "tools", "*.sh")) + \
+        [os.path.join(ROOT, "oracle", "build_ref.sh")]
+    assert len(scripts) >= 6
+    for s in scripts:
+        assert subprocess.run(["bash", "-n", s]).returncode == 0, s
