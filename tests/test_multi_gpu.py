@@ -16,13 +16,20 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 @pytest.mark.gpu
 def test_two_gpus_match_single_gpu_and_oracle():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_check.py"), "--bodies", "100001",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "multi_gpu_check.py"), "--bodies", "100001",
            "--steps", "2"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "MULTI_GPU_CHECK PASS" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
@@ -65,7 +72,7 @@ def test_gloo_world2_shard_and_allgather_protocol(tmp_path, n):
     import oracle
     from gpu_nbody_simulation_b200 import initial_conditions as ic
     steps, world = 3, 2
-    port = 29600 + (n % 50)
+    port = _free_port()
     mp.spawn(_gloo_worker, args=(world, port, n, steps, str(tmp_path)), nprocs=world, join=True)
     pos, vel, mass = ic.uniform_disk(n, seed=99, round6=False)
     par = oracle.default_params(G=6.67e-17)
@@ -165,7 +172,7 @@ def test_gloo_world2_sharded_build_gives_the_global_tree(tmp_path, n, max_depth)
     import oracle
     from gpu_nbody_simulation_b200 import initial_conditions as ic
     world = 2
-    mp.spawn(_sharded_build_worker, args=(world, 29650 + max_depth, n, max_depth, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_sharded_build_worker, args=(world, _free_port(), n, max_depth, str(tmp_path)), nprocs=world, join=True)
     pos, vel, mass = ic.plummer_2d(n, seed=7, round6=False)
     par = oracle.default_params(max_depth=max_depth)
     tree = oracle.Tree(pos, mass, par)
