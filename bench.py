@@ -22,7 +22,13 @@ per-cell sums over NVLink peer memory, not the bodies).
 `e2e`    : same step through the C-ABI with HOST buffers: pinned H2D of positions, velocities and
            masses + step + D2H of positions every step, wall clock around the synchronous calls.
 `roofline`: traversal kernel, 20 flop per accepted interaction against the FP32
-           FMA peak measured by a register-resident FMA loop on the same device.
+           FMA peak measured by a register-resident FMA loop on the same device; `issue_view` = the same
+           kernel against the SM's issue slots (what actually binds it).
+`cpu_baseline`: the reference's OWN CPU functions (oracle/_ref, 1 thread: it has no threading) on the same
+           bodies (+ `port_all_cores`: the oracle port with OpenMP over bodies, labelled as a port).
+`gpu_baseline`: the reference's OWN GPU program (unmodified project.cu, sm_100a) on the same GPU, its two timers.
+`accuracy`: force rel-RMS of the timed configuration against the reference tree forces (sampled bodies).
+`--impl reference`: the CPU reference arm alone, same JSON line shape.
 """
 import argparse
 import json
