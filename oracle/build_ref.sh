@@ -14,6 +14,15 @@ if [ ! -f "$ref" ]; then
     exit 0
 fi
 mkdir -p "$here/_ref"
+if [ "${1:-}" = "direct" ]; then
+    # the reference's direct-sum force function (main_approach_1.cpp:53-75; n = 2 is hard-coded there)
+    src="${BH_REFERENCE_ROOT:-/root/reference}/implementation/main_approach_1.cpp"
+    out="$here/_ref/ref_direct"
+    if [ -x "$out" ] && [ "$out" -nt "$here/ref_direct_harness.cpp" ] && [ "$out" -nt "$src" ]; then exit 0; fi
+    g++ -O2 -w -std=c++17 -ffp-contract=off -DREF_DIRECT_SOURCE="\"$src\"" -o "$out" "$here/ref_direct_harness.cpp"
+    echo "built $out"
+    exit 0
+fi
 if [ "${1:-}" = "gpu" ]; then
     # the reference's GPU program path (runSimulationGpu) for the B200 baseline: oracle/build_ref.sh gpu <N> <steps>
     # unmodified project.cu, -O2, sm_100a, N_THREADS = N_BODIES.

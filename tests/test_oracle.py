@@ -162,3 +162,21 @@ def test_oracle_equals_the_live_reference_on_fresh_inputs(n, kind, seed):
         assert np.array_equal(a.ravel(), recs[("acc", s)], equal_nan=True)
         assert np.array_equal(v.ravel(), recs[("vel", s)], equal_nan=True)
         assert np.array_equal(p.ravel(), recs[("pos", s)], equal_nan=True)
+
+
+def test_direct_sum_pair_expression_equals_the_reference_function():
+    """oracle.direct_forces against the reference's own computeForces of main_approach_1.cpp:53-75 (compiled where it
+    lies into oracle/_ref/ref_direct; the reference hard-codes n = 2), bit for bit on random pairs."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(oracle.__file__), "_ref", "ref_direct")
+    if not os.access(exe, os.X_OK):
+        pytest.skip("oracle/_ref/ref_direct not built here")
+    rng = np.random.default_rng(77)
+    for _ in range(40):
+        pos = rng.uniform(-0.1, 0.1, size=(2, 2)) * 10.0 ** rng.integers(-6, 3)
+        mass = 10.0 ** rng.uniform(-6, 6, size=2)                # main_approach_1.cpp:16-17 mass range
+        out = subprocess.run([exe] + [repr(float(v)) for v in (pos[0, 0], pos[0, 1], mass[0], pos[1, 0], pos[1, 1], mass[1])],
+                             capture_output=True, text=True, check=True).stdout.split()
+        want = np.array([float.fromhex(x) for x in out]).reshape(2, 2)
+        got = oracle.direct_forces(pos, mass, G=6.67e-11)
+        assert np.array_equal(got, want), (pos, mass, got, want)
