@@ -23,6 +23,15 @@ if [ "${1:-}" = "direct" ]; then
     echo "built $out"
     exit 0
 fi
+if [ "${1:-}" = "approach2" ]; then
+    # the reference's stand-alone CPU Barnes-Hut program (main_approach_2.cpp; N_BODIES = 1000 is hard-coded there)
+    src="${BH_REFERENCE_ROOT:-/root/reference}/implementation/main_approach_2.cpp"
+    out="$here/_ref/ref_approach2"
+    if [ -x "$out" ] && [ "$out" -nt "$here/ref_approach2_harness.cpp" ] && [ "$out" -nt "$src" ]; then exit 0; fi
+    g++ -O2 -w -std=c++17 -ffp-contract=off -DREF_APPROACH2_SOURCE="\"$src\"" -o "$out" "$here/ref_approach2_harness.cpp"
+    echo "built $out"
+    exit 0
+fi
 if [ "${1:-}" = "gpu" ]; then
     # the reference's GPU program path (runSimulationGpu) for the B200 baseline: oracle/build_ref.sh gpu <N> <steps>
     # unmodified project.cu, -O2, sm_100a, N_THREADS = N_BODIES.

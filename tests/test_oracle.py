@@ -180,3 +180,30 @@ def test_direct_sum_pair_expression_equals_the_reference_function():
         want = np.array([float.fromhex(x) for x in out]).reshape(2, 2)
         got = oracle.direct_forces(pos, mass, G=6.67e-11)
         assert np.array_equal(got, want), (pos, mass, got, want)
+
+
+def test_oracle_equals_the_references_standalone_cpu_program_when_the_cap_is_not_reached(tmp_path):
+    """BASELINE config 1 names the main_approach CPU programs: main_approach_2.cpp is the same PR quadtree + ComputeMass +
+    theta-traversal as project.cu's CPU path without the depth cap (N_BODIES = 1000 hard-coded).  Its OWN buildTree and
+    computeForces (oracle/_ref/ref_approach2, compiled where the file lies) against the oracle with a cap that is never
+    reached: node table and forces bit for bit."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(oracle.__file__), "_ref", "ref_approach2")
+    if not os.access(exe, os.X_OK):
+        pytest.skip("oracle/_ref/ref_approach2 not built here")
+    n = 1000
+    for seed in (5, 6):
+        rng = np.random.default_rng(seed)
+        pos = rng.uniform(-0.1, 0.1, size=(n, 2))
+        mass = 10.0 ** rng.uniform(-6, 6, size=n)                 # main_approach_2.cpp:18-19 mass range
+        oracle.write_bodies_bin(str(tmp_path / "b.bin"), pos, np.zeros((n, 2)), mass)
+        subprocess.run([exe, str(tmp_path / "b.bin"), str(tmp_path / "o.bin")], check=True)
+        raw = open(tmp_path / "o.bin", "rb").read()
+        nn = int(np.frombuffer(raw[:8], dtype=np.uint64)[0])
+        nodes = np.frombuffer(raw[8:8 + nn * 96], dtype=np.float64).reshape(nn, 12)
+        forces = np.frombuffer(raw[8 + nn * 96:], dtype=np.float64).reshape(n, 2)
+        tree = oracle.Tree(pos, mass, oracle.default_params(max_depth=16))
+        got = tree.nodes()
+        assert not np.any((got[:, 11] == -1) & (got[:, 6] > 0) & (got[:, 0] == -1)), "cap reached: pick another seed"
+        assert np.array_equal(got, nodes)
+        assert np.array_equal(tree.forces()[0], forces)
