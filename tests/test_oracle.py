@@ -207,3 +207,36 @@ def test_oracle_equals_the_references_standalone_cpu_program_when_the_cap_is_not
         assert not np.any((got[:, 11] == -1) & (got[:, 6] > 0) & (got[:, 0] == -1)), "cap reached: pick another seed"
         assert np.array_equal(got, nodes)
         assert np.array_equal(tree.forces()[0], forces)
+
+
+def test_oracle_dump_text_equals_the_live_references_dump(tmp_path):
+    """quadtree_*.txt (TraverseTreeToFile, project.cu:504-534; read by plot_quadtree.py): the oracle's dump against the
+    reference's own writer run live, line by line.  Only the occupantPos of cap-level single leaves may differ: the
+    reference indexes positions[] with the negative encoded occupant there (out-of-bounds read), the oracle
+    and the product print the occupant's real position."""
+    n = 2048
+    if not oracle.ref_available(n):
+        pytest.skip(f"oracle/_ref/ref_harness_N{n} not built here")
+    import re
+    rng = np.random.default_rng(31)
+    pos = rng.normal(0.0, 0.03, size=(n, 2))
+    pos[:300] = pos[:300] * 1e-3                                   # dense core: cap-level leaves of both kinds
+    vel = np.zeros((n, 2))
+    mass = np.power(10.0, rng.uniform(-1.0, np.log10(0.5), size=n))
+    prefix = str(tmp_path / "ref_quadtree")
+    oracle.run_ref(pos, vel, mass, steps=1, quadtree_txt=prefix, keep_dump=False, dump="")
+    ref_lines = open(prefix + "_init.txt").read().splitlines()
+    tree = oracle.Tree(pos, mass)
+    tree.dump(str(tmp_path / "oracle_quadtree.txt"))
+    got_lines = open(tmp_path / "oracle_quadtree.txt").read().splitlines()
+    assert len(ref_lines) == len(got_lines) == tree.size
+    cap_single = re.compile(r"occupantIndex=(-\d+) ")
+    masked = 0
+    for a, b in zip(ref_lines, got_lines):
+        m = cap_single.search(a)
+        if m and int(m.group(1)) <= -2:
+            assert a.split("occupantPos=")[0] == b.split("occupantPos=")[0]
+            masked += 1
+        else:
+            assert a == b
+    assert 0 < masked < len(ref_lines) // 2
