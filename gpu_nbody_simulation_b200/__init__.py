@@ -199,6 +199,8 @@ def philox4x32_10(counter, key):
 def write_init_files(directory: str, pos, vel, mass):
     """The reference's three initial-condition files (writers of project.cu:236-246, :268-281) through the C-ABI."""
     pos, vel, mass = _f64(pos, (-1, 2)), _f64(vel, (-1, 2)), _f64(mass, (-1,))
+    if not (pos.shape[0] == vel.shape[0] == mass.shape[0]):
+        raise ValueError("pos, vel and mass must describe the same number of bodies")
     os.makedirs(directory, exist_ok=True)
     dp = C.POINTER(C.c_double)
     _check(lib().bh_write_init_files(os.path.join(directory, "masses_init.txt").encode(),

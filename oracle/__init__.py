@@ -244,7 +244,7 @@ def read_dump(path):
 
 
 def run_ref(pos, vel, mass, steps=1, dump="tree,forces,state", dump_steps="all", quadtree_txt=None,
-            reset_each_step=False, keep_dump=True):
+            reset_each_step=False, keep_dump=True, positions_txt=None):
     """Run the reference's own CPU functions (unmodified project.cu) on these bodies.
     Returns (records, timings) where timings is the list of per-step JSON dicts."""
     mass = _f64(mass, (-1,))
@@ -263,6 +263,8 @@ def run_ref(pos, vel, mass, steps=1, dump="tree,forces,state", dump_steps="all",
             cmd += ["--quadtree-txt", quadtree_txt]
         if reset_each_step:
             cmd += ["--reset-each-step"]
+        if positions_txt:
+            cmd += ["--positions-txt", positions_txt]
         res = subprocess.run(cmd, check=True, capture_output=True, text=True)
         timings = [json.loads(l) for l in res.stdout.splitlines() if l.startswith("{")]
         recs = read_dump(outp) if keep_dump else {}
@@ -305,3 +307,20 @@ def run_ref_gpu(pos, vel, mass, steps=1, calls=2, want_positions=False, device=N
         calls_out = [json.loads(l) for l in res.stdout.splitlines() if l.startswith("{")]
         p = np.fromfile(outp, dtype=np.float64).reshape(n, 2) if want_positions else None
     return calls_out, p
+
+
+def run_ref_loader(directory: str, n: int):
+    """The reference's own loadSimulationDataFromText (project.cu:103-161) on DIR/masses_init.txt, positions_init.txt,
+    velocities_init.txt (first n lines).  Returns (pos, vel, mass); raises RuntimeError with the reference's exception
+    text when it throws."""
+    exe = ref_harness_path(n)
+    if not os.access(exe, os.X_OK):
+        raise FileNotFoundError(f"{exe} not built (oracle/build_ref.sh {n})")
+    with tempfile.TemporaryDirectory() as td:
+        outp = os.path.join(td, "dump.bin")
+        res = subprocess.run([exe, "--load-text", directory, "--steps", "0", "--out", outp, "--dump", ""],
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(res.stderr.strip())
+        recs = read_dump(outp)
+    return recs[("loaded_pos", 0)].reshape(n, 2), recs[("loaded_vel", 0)].reshape(n, 2), recs[("loaded_mass", 0)]

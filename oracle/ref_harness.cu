@@ -21,7 +21,11 @@
 //
 // usage: ref_harness_N<N> --in bodies.bin --steps K [--out dump.bin]
 //                         [--dump tree,forces,state] [--dump-steps all|first|last]
-//                         [--quadtree-txt prefix] [--reset-each-step]
+//                         [--quadtree-txt prefix] [--reset-each-step] [--positions-txt file]
+//   --load-text DIR: instead of --in, read the bodies with the reference's own loadSimulationDataFromText
+//                    (project.cu:103-161) from DIR/masses_init.txt, positions_init.txt, velocities_init.txt
+//   --positions-txt: the reference's trajectory file (savePositions at t = 0 and after every step,
+//                    project.cu:855-863, :879, :907, :912), what plot_2d.py reads
 //   bodies.bin : u64 N | mass[N] | pos[2N] | vel[2N]      (all FP64, host endian)
 //   dump.bin   : records { char name[16]; u64 step; u64 ndoubles; double data[] }
 // stdout: one JSON line per step with wall-clock microseconds per phase.
@@ -48,7 +52,7 @@ static void put(FILE* f, const char* name, uint64_t step, const double* d, uint6
 }
 
 int main(int argc, char** argv) {
-    const char* in = nullptr; const char* out = nullptr; const char* qtxt = nullptr;
+    const char* in = nullptr; const char* out = nullptr; const char* qtxt = nullptr; const char* ptxt = nullptr; const char* ldir = nullptr;
     const char* what = "tree,forces,state"; const char* which = "all";
     int steps = 1; bool reset = false;
     for (int i = 1; i < argc; ++i) {
@@ -59,9 +63,11 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--dump-steps") && i + 1 < argc) which = argv[++i];
         else if (!strcmp(argv[i], "--quadtree-txt") && i + 1 < argc) qtxt = argv[++i];
         else if (!strcmp(argv[i], "--reset-each-step")) reset = true;
+        else if (!strcmp(argv[i], "--positions-txt") && i + 1 < argc) ptxt = argv[++i];
+        else if (!strcmp(argv[i], "--load-text") && i + 1 < argc) ldir = argv[++i];
         else { fprintf(stderr, "bad arg %s\n", argv[i]); return 2; }
     }
-    if (!in) { fprintf(stderr, "--in required\n"); return 2; }
+    if (!in && !ldir) { fprintf(stderr, "--in or --load-text required\n"); return 2; }
     const size_t N = N_BODIES;
     // heap, not stack: the reference keeps these in main's frame (project.cu:1055-1057)
     auto masses = std::make_unique<Masses>();
@@ -76,6 +82,13 @@ int main(int argc, char** argv) {
     auto forces = std::make_unique<Forces>();
     auto pos0 = std::make_unique<Positions>();
     auto vel0 = std::make_unique<Velocities>();
+    if (ldir) {
+        const std::string d(ldir);
+        try {                                                                         // project.cu:1065-1066
+            loadSimulationDataFromText(d + "/masses_init.txt", d + "/positions_init.txt", d + "/velocities_init.txt",
+                                       N_BODIES, *masses, *positions, *velocities);
+        } catch (const std::exception& e) { fprintf(stderr, "reference loader: %s\n", e.what()); return 5; }
+    } else {
     FILE* fi = fopen(in, "rb");
     if (!fi) { perror(in); return 1; }
     uint64_t n_in = 0;
@@ -86,11 +99,21 @@ int main(int argc, char** argv) {
     if (fread(masses->data(), 8, N, fi) != N || fread(positions->data(), 8, 2 * N, fi) != 2 * N ||
         fread(velocities->data(), 8, 2 * N, fi) != 2 * N) { fprintf(stderr, "short input\n"); return 1; }
     fclose(fi);
+    }
     *pos0 = *positions; *vel0 = *velocities;
     FILE* fo = out ? fopen(out, "wb") : nullptr;
     const bool d_tree = strstr(what, "tree"), d_forces = strstr(what, "forces"), d_state = strstr(what, "state");
 
+    if (fo && ldir) {   // what the reference's loader produced
+        put(fo, "loaded_mass", 0, masses->data(), N);
+        put(fo, "loaded_pos", 0, (*positions)[0].data(), 2 * N);
+        put(fo, "loaded_vel", 0, (*velocities)[0].data(), 2 * N);
+    }
+    std::string output_str;
+    double absolute_t = 0.0;
+    if (ptxt) savePositions(output_str, *positions, absolute_t);                      // project.cu:879
     for (int step = 0; step < steps; ++step) {
+        absolute_t += DELTA_T;                                                       // project.cu:884
         if (reset) { *positions = *pos0; *velocities = *vel0; }
         const bool dump = !strcmp(which, "all") || (!strcmp(which, "first") && step == 0) ||
                           (!strcmp(which, "last") && step == steps - 1);
@@ -118,11 +141,13 @@ int main(int argc, char** argv) {
             put(fo, "vel", step, (*velocities)[0].data(), 2 * N);
             put(fo, "pos", step, (*positions)[0].data(), 2 * N);
         }
+        if (ptxt) savePositions(output_str, *positions, absolute_t);                  // project.cu:907
         auto us = [](auto a, auto b) { return (long long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
         printf("{\"step\": %d, \"n_bodies\": %zu, \"nodes\": %zu, \"build_us\": %lld, \"force_us\": %lld, \"update_us\": %lld}\n",
                step, N, quadtree.size(), us(t0, t1), us(t2, t3), us(t3, t4));
         fflush(stdout);
     }
     if (fo) fclose(fo);
+    if (ptxt) { std::ofstream pf(ptxt); pf << output_str; }                           // project.cu:912
     return 0;
 }

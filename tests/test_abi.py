@@ -151,3 +151,54 @@ def test_integration_stub_compiles_and_links(tmp_path):
     pkg = os.path.join(ROOT, "gpu_nbody_simulation_b200")
     subprocess.check_call([cxx, "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), str(src), "-L", pkg, "-lbh",
                            "-Wl,--unresolved-symbols=ignore-in-shared-libs", "-o", str(tmp_path / "stub")])
+
+
+def test_positions_txt_equals_the_live_references_savePositions(tmp_path):
+    """bh_append_positions_txt (host code of libbh.so, no GPU needed) against the reference's own savePositions
+    (project.cu:855-863) run live through oracle/_ref: the trajectory file plot_2d.py reads, byte for byte, for the
+    positions of a 2-step reference run (t = 0, 1, 2)."""
+    import oracle
+    n = 2048
+    if not oracle.ref_available(n):
+        pytest.skip(f"oracle/_ref/ref_harness_N{n} not built here")
+    rng = np.random.default_rng(12)
+    pos = rng.uniform(-0.1, 0.1, size=(n, 2))
+    vel = rng.uniform(-1e-4, 1e-4, size=(n, 2))
+    mass = np.power(10.0, rng.uniform(-1.0, np.log10(0.5), size=n))
+    ref_file = str(tmp_path / "positions_ref.txt")
+    recs, _ = oracle.run_ref(pos, vel, mass, steps=2, positions_txt=ref_file)
+    mine = str(tmp_path / "positions.txt").encode()
+    dp = C.POINTER(C.c_double)
+    L = bh.lib()
+    assert L.bh_append_positions_txt(mine, np.ascontiguousarray(pos).ctypes.data_as(dp), n, 0.0, 1) == 0
+    for s in range(2):
+        p = np.ascontiguousarray(recs[("pos", s)])
+        assert L.bh_append_positions_txt(mine, p.ctypes.data_as(dp), n, float(s + 1), 0) == 0
+    assert open(mine.decode(), "rb").read() == open(ref_file, "rb").read()
+
+
+def test_load_text_equals_the_live_references_loader(tmp_path):
+    """bh_load_text against the reference's own loadSimulationDataFromText (project.cu:103-161) run live: same doubles
+    from the same three files (written by bh_write_init_files), extra lines ignored, and the same refusal when a
+    file is too short."""
+    import oracle
+    n = 2048
+    if not oracle.ref_available(n):
+        pytest.skip(f"oracle/_ref/ref_harness_N{n} not built here")
+    pos, vel, mass = bh.generate_host("plummer_2d", n + 7, seed=21)            # 7 lines more than N: first N are used
+    d = str(tmp_path / "ic")
+    bh.write_init_files(d, pos, vel, mass)
+    p_ref, v_ref, m_ref = oracle.run_ref_loader(d, n)
+    p, v, m = bh.load_text(d, n)
+    assert np.array_equal(p, p_ref) and np.array_equal(v, v_ref) and np.array_equal(m, m_ref)
+    with pytest.raises(ValueError):
+        bh.write_init_files(str(tmp_path / "bad"), pos[:n - 1], vel, mass)
+    short = str(tmp_path / "short")
+    bh.write_init_files(short, pos, vel, mass)
+    lines = open(os.path.join(short, "positions_init.txt")).read().splitlines()
+    open(os.path.join(short, "positions_init.txt"), "w").write("\n".join(lines[:n - 1]) + "\n")   # one line short
+    with pytest.raises(RuntimeError) as ref_err:
+        oracle.run_ref_loader(short, n)
+    with pytest.raises(bh.BhError) as my_err:
+        bh.load_text(short, n)
+    assert "Not enough" in str(ref_err.value) and "Not enough" in str(my_err.value)
