@@ -487,6 +487,164 @@ traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// EXPERIMENT (reserved[0] == 7; written after round 1's GPU budget was spent, not yet run): the pair kernel with
+// the stack pop and the node fetch of the NEXT iteration issued in the middle of the current one.
+//
+// ncu (profiles/r01_traverse_v8_pair_stall_hotspots.txt): 18 % of the stall samples are memory dependencies — the
+// first consumer of the node record behind the LDG.128 (10.6 %) and the pop's address chain LDS -> IMAD (8 %).
+// An iteration is therefore split into phase A (displacements, d2, acceptance tests, ballots, pushes — after it the
+// stack is final, so the next cell can be popped and its four records requested) and phase B (the force arithmetic of
+// the current children: 8 MUFU + 24 packed instructions that need nothing from memory), which runs while the next
+// records are in flight.  Same instruction count and the same per-body arithmetic as the pair kernel except that the
+// "no force" select acts on d2 (d2 := +inf  =>  rsqrt = 0  =>  exactly 0, also for a body's own leaf where d2 == 0)
+// instead of on the finished factor.  Costs registers: two record groups + the saved (dx, dy, d2, gm) of four children.
+// ------------------------------------------------------------------------------------------------
+#ifndef BH_PIPE_MIN_BLOCKS
+#define BH_PIPE_MIN_BLOCKS 5    // per 128 threads: <= 102 registers
+#endif
+template <bool INTEGRATE>
+__global__ void __launch_bounds__(kTravThreads, BH_PIPE_MIN_BLOCKS)
+traverse_f32_pair_pipe_kernel(const __grid_constant__ TravArgs a) {
+    using SE = StackEntry<2>;
+    __shared__ __align__(16) uint8_t s_stack[kTravWarps][kStackCap * SE::kBytes];
+    pdl_entry();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warp_slot0 = ((int64_t)blockIdx.x * kTravWarps + warp) * 64;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&s_stack[warp][0]);
+
+    uint32_t body[2], selfn[2];
+    float2 nxh, nyh, nxl, nyl;   // minus the scaled positions of body 0 (.x) and body 1 (.y), hi / lo floats
+    float2 accx = make_float2(0.f, 0.f), accy = make_float2(0.f, 0.f);
+    const float feps = a.consts->feps;
+    {
+        const double scale = a.consts->scale;
+        float t[2][4];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int64_t slot = warp_slot0 + b * 32 + lane;
+            body[b] = 0xffffffffu; selfn[b] = 0xffffffffu;
+            double px = 0.0, py = 0.0;
+            if (slot < a.n_slots) {
+                uint32_t sp = a.own_list ? a.own_list[slot] : (uint32_t)slot;
+                body[b] = a.sidx[sp];
+                selfn[b] = a.self_node[body[b]];
+                double2 p = a.pos_in[body[b]];
+                px = p.x; py = p.y;
+            }
+            const double sx = px * scale, sy = py * scale;
+            const float xh = (float)sx, yh = (float)sy;
+            t[b][0] = -xh; t[b][1] = -yh;
+            t[b][2] = -(float)(sx - (double)xh); t[b][3] = -(float)(sy - (double)yh);
+        }
+        nxh = make_float2(t[0][0], t[1][0]); nyh = make_float2(t[0][1], t[1][1]);
+        nxl = make_float2(t[0][2], t[1][2]); nyl = make_float2(t[0][3], t[1][3]);
+    }
+    const float2 neg_eps2 = make_float2(-feps, -feps);
+    const float kInf = __int_as_float(0x7f800000);
+
+    struct Group {              // the four children of one popped cell
+        float4 A[4];            // chx chy clx cly
+        float2 B[4];            // gm thr
+        uint32_t base;          // pyramid index of child 0
+        float2 mxh, myh;        // minus the bodies' hi coordinates, or the far-away stand-in outside the cell's mask
+    };
+    struct Saved { float2 dx, dy, d2; float gm; };
+
+    // phase A for one child: displacement, d2, tests; returns the ballots of "opens"; d2 := +inf where no force is due
+    auto phase_a = [&](const float4 A, const float2 B, uint32_t idx, const float2 mxh, const float2 myh, Saved& s,
+                       uint32_t& m0, uint32_t& m1) {
+        s.dx = __fadd2_rn(__fadd2_rn(make_float2(A.x, A.x), mxh), __fadd2_rn(make_float2(A.z, A.z), nxl));
+        s.dy = __fadd2_rn(__fadd2_rn(make_float2(A.y, A.y), myh), __fadd2_rn(make_float2(A.w, A.w), nyl));
+        const float2 d2 = __ffma2_rn(s.dx, s.dx, __fmul2_rn(s.dy, s.dy));
+        s.gm = B.x;
+        // per body: accept = !(d2 <= thr); use = accept && not the body's own leaf; d2s = use ? d2 : +inf; ballot(!accept)
+        asm volatile("{\n .reg .pred pa, pu;\n setp.gtu.f32 pa, %2, %3;\n setp.ne.and.u32 pu, %4, %5, pa;\n"
+                     " selp.f32 %0, %2, %6, pu;\n vote.sync.ballot.b32 %1, !pa, 0xffffffff;\n}"
+                     : "=f"(s.d2.x), "=r"(m0) : "f"(d2.x), "f"(B.y), "r"(selfn[0]), "r"(idx), "f"(kInf));
+        asm volatile("{\n .reg .pred pa, pu;\n setp.gtu.f32 pa, %2, %3;\n setp.ne.and.u32 pu, %4, %5, pa;\n"
+                     " selp.f32 %0, %2, %6, pu;\n vote.sync.ballot.b32 %1, !pa, 0xffffffff;\n}"
+                     : "=f"(s.d2.y), "=r"(m1) : "f"(d2.y), "f"(B.y), "r"(selfn[1]), "r"(idx), "f"(kInf));
+    };
+    // phase B for one child: G M / (d2 (d + eps)) to first order in eps / d, accumulation (project.cu:765-772)
+    auto phase_b = [&](const Saved& s) {
+        const float2 inv = make_float2(approx_rsqrt(s.d2.x), approx_rsqrt(s.d2.y));
+        const float2 t = __fmul2_rn(inv, inv);
+        const float2 u = __ffma2_rn(neg_eps2, t, inv);
+        const float2 g = __fmul2_rn(make_float2(s.gm, s.gm), __fmul2_rn(t, u));
+        accx = __ffma2_rn(g, s.dx, accx);
+        accy = __ffma2_rn(g, s.dy, accy);
+    };
+    // pop the top of the stack into `g` and request its four records
+    uint32_t sp = sbase;
+    auto pop_and_fetch = [&](Group& g) {
+        sp -= SE::kBytes;
+        uint32_t node, pm[2];
+        __syncwarp();             // lane 0's stores of earlier steps are visible to the whole warp
+        SE::load(sp, node, pm);
+        __syncwarp();             // nobody overwrites the slot before everybody has read it
+        g.base = 4u * node + 1u;
+        const NodeRec* __restrict__ rp = a.rec + g.base;
+        const bool a0 = (pm[0] >> lane) & 1u, a1 = (pm[1] >> lane) & 1u;
+        g.mxh = make_float2(a0 ? nxh.x : kFarLane, a1 ? nxh.y : kFarLane);
+        g.myh = make_float2(a0 ? nyh.x : kFarLane, a1 ? nyh.y : kFarLane);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            g.A[q] = __ldg(reinterpret_cast<const float4*>(rp + q));
+            g.B[q] = __ldg(reinterpret_cast<const float2*>(rp + q) + 2);
+        }
+    };
+    // one iteration on `cur`; fetches the next cell into `nxt` between the phases; returns whether there is one
+    auto iterate = [&](const Group& cur, Group& nxt) -> bool {
+        Saved s[4];
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) {
+            uint32_t m[2];
+            phase_a(cur.A[q], cur.B[q], cur.base + q, cur.mxh, cur.myh, s[q], m[0], m[1]);
+            const bool push = (m[0] | m[1]) != 0u;
+            SE::store_if(push & (lane == 0), sp, cur.base + q, m);
+            sp += push ? SE::kBytes : 0u;
+        }
+        const bool more = sp != sbase;       // warp-uniform
+        if (more) pop_and_fetch(nxt);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) phase_b(s[q]);
+        return more;
+    };
+
+    {   // the root (project.cu:711-715 pushes node 0)
+        const float4 A = __ldg(reinterpret_cast<const float4*>(a.rec));
+        const float2 B = __ldg(reinterpret_cast<const float2*>(a.rec) + 2);
+        const bool l0 = body[0] != 0xffffffffu, l1 = body[1] != 0xffffffffu;
+        const float2 mxh = make_float2(l0 ? nxh.x : kFarLane, l1 ? nxh.y : kFarLane);
+        const float2 myh = make_float2(l0 ? nyh.x : kFarLane, l1 ? nyh.y : kFarLane);
+        Saved s;
+        uint32_t m[2];
+        phase_a(A, B, 0u, mxh, myh, s, m[0], m[1]);
+        const bool push = (m[0] | m[1]) != 0u;
+        SE::store_if(push & (lane == 0), sp, 0u, m);
+        sp += push ? SE::kBytes : 0u;
+        phase_b(s);
+    }
+    if (sp != sbase) {
+        Group g0, g1;
+        pop_and_fetch(g0);
+        while (true) {                        // ping-pong between the two record groups: no register copies
+            if (!iterate(g0, g1)) break;
+            if (!iterate(g1, g0)) break;
+        }
+    }
+    const float ax[2] = {accx.x, accx.y}, ay[2] = {accy.x, accy.y};
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        if (body[b] != 0xffffffffu) {
+            const double2 p = a.pos_in[body[b]];
+            const double mi = a.mass[body[b]];
+            finish_body<INTEGRATE>(a, body[b], p.x, p.y, mi, mi * (double)ax[b], mi * (double)ay[b]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP64 verification traversal: the reference's expressions, one body per lane
 // ------------------------------------------------------------------------------------------------
 template <bool INTEGRATE, bool COUNT, bool EXACT = false>
@@ -726,7 +884,7 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
     // two bodies per lane halve the node traffic and the control overhead per body, but need >= ~400k
     // bodies to keep every SM's warp slots full (ncu: profiles/r01_traverse_v4_*)
     const bool exact_leaves = p.flags & BH_FLAG_EXACT_LEAVES;   // extension: generic 1-body-per-lane / FP64 kernels only
-    const int bpl = exact_leaves ? 1 : (p.reserved[0] == 1) ? 1 : (p.reserved[0] >= 2 && p.reserved[0] <= 6) ? 2 : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
+    const int bpl = exact_leaves ? 1 : (p.reserved[0] == 1) ? 1 : (p.reserved[0] >= 2 && p.reserved[0] <= 7) ? 2 : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
     // previous operation on the stream = tree_top_kernel (or a peer-exchange kernel; g_pdl is off there)
 #define BH_GO(K) launch_chain(K, dim3(blocks), dim3(kTravThreads), st, true, a)
     if (fp64) {
@@ -746,6 +904,8 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
             else { if (count) BH_GO((traverse_f32_kernel<1, false, true, true>)); else BH_GO((traverse_f32_kernel<1, false, false, true>)); }
         } else if (bpl == 2 && !count && p.reserved[0] == 4 && !(p.flags & BH_FLAG_EXACT_EPS)) {
             if (integrate) BH_GO((traverse_f32_pair_kernel<true, false, true>)); else BH_GO((traverse_f32_pair_kernel<false, false, true>));
+        } else if (bpl == 2 && !count && p.reserved[0] == 7 && !(p.flags & BH_FLAG_EXACT_EPS)) {
+            if (integrate) BH_GO((traverse_f32_pair_pipe_kernel<true>)); else BH_GO((traverse_f32_pair_pipe_kernel<false>));
         } else if (bpl == 2 && !count && (p.reserved[0] == 5 || p.reserved[0] == 6) && !(p.flags & BH_FLAG_EXACT_EPS)) {
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);

@@ -73,7 +73,8 @@ typedef struct bh_params {
     int32_t n_ranks;      /* 1 = single GPU */
     int32_t reserved[4];  /* reserved[0]: traversal tuning knob: 0 = default, 1 / 2 = bodies per lane (2 = packed pair
                              kernel), 3 = generic kernel with 2 bodies per lane; experiments, not yet measured: 4 = pair kernel + L1
-                             prefetch, 5 = pair kernel + SM-local block order, 6 = both */
+                             prefetch, 5 = pair kernel + SM-local block order, 6 = both, 7 = pair kernel with the next cell's
+                             pop + fetch issued between the test phase and the force phase */
 } bh_params;
 
 typedef struct bh_ctx bh_ctx; /* opaque; owns device memory, stream, CUDA graph, NCCL comm */

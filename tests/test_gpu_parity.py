@@ -429,6 +429,7 @@ def test_traversal_variants_agree(shipped40k):
         variants["pair_prefetch"] = dict(bodies_per_lane=4)
         variants["pair_sm_local"] = dict(bodies_per_lane=5)
         variants["pair_sm_local_prefetch"] = dict(bodies_per_lane=6)
+        variants["pair_pipelined"] = dict(bodies_per_lane=7)
     for name, kw in variants.items():
         with build(pos, vel, mass, **kw) as sim:
             sim.compute_forces()
