@@ -240,3 +240,52 @@ def test_oracle_dump_text_equals_the_live_references_dump(tmp_path):
         else:
             assert a == b
     assert 0 < masked < len(ref_lines) // 2
+
+
+def _edge_case(kind, n, rng):
+    if kind == "collinear":                       # zero-height box: padding comes from the other axis (project.cu:553-570)
+        pos = np.stack([rng.uniform(-1, 1, n), np.full(n, 0.25)], axis=1)
+    elif kind == "all_coincident":                # extent 0: the 1e-6 fallback pad, one cap-level leaf with every body
+        pos = np.full((n, 2), -3.5)
+    elif kind == "two_far_clusters":              # 12 decades of dynamic range in the coordinates
+        pos = np.concatenate([rng.normal(0, 1e-6, (n // 2, 2)), 1e6 + rng.normal(0, 1e-6, (n - n // 2, 2))])
+    elif kind == "tiny_separations":              # pairs 1e-13 apart: deep splits, cap-level leaves, near-zero distances
+        base = rng.uniform(-0.1, 0.1, (n // 2, 2))
+        pos = np.concatenate([base, base + 1e-13])
+        if len(pos) < n:
+            pos = np.concatenate([pos, rng.uniform(-0.1, 0.1, (n - len(pos), 2))])
+    elif kind == "lattice":                       # bodies exactly on cell boundaries of a power-of-two lattice
+        g = np.arange(32) / 32.0
+        pos = np.stack(np.meshgrid(g, g), axis=-1).reshape(-1, 2)[:n]
+        if len(pos) < n:
+            pos = np.concatenate([pos, pos[: n - len(pos)] + 0.5 / 32])
+    elif kind == "zero_and_tiny_masses":
+        pos = rng.uniform(-0.1, 0.1, (n, 2))
+    else:
+        raise KeyError(kind)
+    mass = np.power(10.0, rng.uniform(-1.0, np.log10(0.5), size=n))
+    if kind == "zero_and_tiny_masses":            # nodes with mass <= 1e-15 are skipped (project.cu:617)
+        mass[::3] = 0.0
+        mass[1::3] = 1e-16
+    return np.ascontiguousarray(pos, dtype=np.float64), mass
+
+
+@pytest.mark.parametrize("kind", ["collinear", "all_coincident", "two_far_clusters", "tiny_separations", "lattice",
+                                  "zero_and_tiny_masses"])
+def test_oracle_equals_the_live_reference_on_edge_cases(kind):
+    n = 1000
+    if not oracle.ref_available(n):
+        pytest.skip(f"oracle/_ref/ref_harness_N{n} not built here")
+    rng = np.random.default_rng(1000 + len(kind))
+    pos, mass = _edge_case(kind, n, np.random.default_rng(len(kind)))
+    vel = rng.uniform(-1e-4, 1e-4, size=(n, 2))
+    recs, _ = oracle.run_ref(pos, vel, mass, steps=2)
+    p, v = pos.copy(), vel.copy()
+    for s in range(2):
+        tree = oracle.Tree(p, mass)
+        assert np.array_equal(tree.nodes().ravel(), recs[("tree", s)], equal_nan=True), f"{kind}: node table, step {s}"
+        f, _ = tree.forces()
+        assert np.array_equal(f.ravel(), recs[("forces", s)], equal_nan=True), f"{kind}: forces, step {s}"
+        with np.errstate(all="ignore"):
+            a, v, p = oracle.update(f, mass, v, p, 1.0)
+        assert np.array_equal(p.ravel(), recs[("pos", s)], equal_nan=True), f"{kind}: positions, step {s}"
