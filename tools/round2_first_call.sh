@@ -8,7 +8,7 @@
 # 5. cost of exact leaves at 1M bodies (profile_step with the flag).
 set -u
 mkdir -p gpurun_out
-( BH_TEST_UNVALIDATED=1 timeout 300 python -m pytest tests/test_gpu_exact_leaves.py tests/test_gpu_generate.py -m gpu -q -rfs 2>&1 | tail -40 ) > gpurun_out/r2_exact_leaves_pytest.log
+( BH_TEST_UNVALIDATED=1 timeout 300 python -m pytest tests/test_gpu_exact_leaves.py tests/test_gpu_generate.py tests/test_gpu_edge_cases.py -m gpu -q -rfs 2>&1 | tail -40 ) > gpurun_out/r2_exact_leaves_pytest.log
 ( timeout 600 python -m pytest tests -m gpu -q -rfs 2>&1 | tail -30 ) > gpurun_out/r2_pytest.log
 ( timeout 120 python __graft_entry__.py smoke 2>&1 | tail -3 ) > gpurun_out/r2_smoke.log
 timeout 400 python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
