@@ -361,7 +361,9 @@ traverse_f32_kernel(const __grid_constant__ TravArgs a) {
 // L1 are hits for the others (ncu: 63 % L1 hit rate).  The hardware hands block b of the first wave to SM b mod
 // #SMs, so the body range is taken from the transposed index (b mod #SMs) * rows + b / #SMs; the grid is padded
 // to #SMs * rows blocks, surplus blocks see no bodies and leave after the root.
-template <bool INTEGRATE, bool EXACT_EPS, bool PREFETCH = false, bool REMAP = false>
+// LEAVES (BH_FLAG_EXACT_LEAVES together with reserved[0] == 2; not yet run): the exact-leaves extension (see
+// traverse_f32_kernel) in the pair kernel — the member loop is packed across the lane's two bodies as well.
+template <bool INTEGRATE, bool EXACT_EPS, bool PREFETCH = false, bool REMAP = false, bool LEAVES = false>
 __global__ void __launch_bounds__(kTravThreads, kPairMinBlocks * (256 / kTravThreads))
 traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
     using SE = StackEntry<2>;
@@ -402,6 +404,43 @@ traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
     }
     const float2 eps2 = make_float2(feps, feps), neg_eps2 = make_float2(-feps, -feps);
     (void)eps2; (void)neg_eps2;
+    [[maybe_unused]] double scale_d = 0.0, Gs = 0.0;   // LEAVES: coordinate scale and G * scale^2
+    if constexpr (LEAVES) { scale_d = a.consts->scale; Gs = a.G * scale_d * scale_d; }
+
+    // LEAVES: if cell `idx` (warp-uniform) is a multi-body leaf at the depth cap with mass > mass_eps, apply its bodies
+    // one by one to the lane's bodies that reached it (act0 / act1), self excluded, and return true.
+    [[maybe_unused]] auto exact_leaf = [&](uint32_t idx, bool act0, bool act1) -> bool {
+        if (idx < a.finest_off) return false;
+        const uint32_t cnt = __ldg(a.t_count + idx);
+        if (cnt < 2u || !(__ldg(a.flags + idx) & kNodeNonZero)) return false;
+        const uint32_t first = __ldg(a.t_first + idx);
+        for (uint32_t j = 0; j < cnt; ++j) {
+            const uint32_t bj = __ldg(a.sidx + first + j);
+            const double2 pj = a.pos_in[bj];
+            const double sxj = pj.x * scale_d, syj = pj.y * scale_d;
+            const float xh = (float)sxj, yh = (float)syj;
+            const float xl = (float)(sxj - (double)xh), yl = (float)(syj - (double)yh);
+            const float gmj = (float)(Gs * a.mass[bj]);
+            const float2 dx = __fadd2_rn(__fadd2_rn(make_float2(xh, xh), nxh), __fadd2_rn(make_float2(xl, xl), nxl));
+            const float2 dy = __fadd2_rn(__fadd2_rn(make_float2(yh, yh), nyh), __fadd2_rn(make_float2(yl, yl), nyl));
+            const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+            float2 g;
+            if constexpr (EXACT_EPS) {
+                const float2 w = __fmul2_rn(d2, __fadd2_rn(make_float2(approx_sqrt(d2.x), approx_sqrt(d2.y)), eps2));
+                g = __fmul2_rn(make_float2(gmj, gmj), make_float2(approx_rcp(w.x), approx_rcp(w.y)));
+            } else {
+                const float2 inv = make_float2(approx_rsqrt(d2.x), approx_rsqrt(d2.y));
+                const float2 t = __fmul2_rn(inv, inv);
+                const float2 u = __ffma2_rn(neg_eps2, t, inv);
+                g = __fmul2_rn(make_float2(gmj, gmj), __fmul2_rn(t, u));
+            }
+            // the select comes last: a body's own entry has d2 == 0 (g is NaN there) and must contribute exactly 0
+            const float2 f = make_float2((act0 && body[0] != bj) ? g.x : 0.f, (act1 && body[1] != bj) ? g.y : 0.f);
+            accx = __ffma2_rn(f, dx, accx);
+            accy = __ffma2_rn(f, dy, accy);
+        }
+        return true;
+    };
 
     // Evaluate one node for both bodies of this lane; returns the two ballots of "opens".
     auto eval = [&](const float4 A, const float2 B, uint32_t idx, const float2 mxh, const float2 myh, uint32_t& m0,
@@ -442,8 +481,10 @@ traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
         const bool l0 = body[0] != 0xffffffffu, l1 = body[1] != 0xffffffffu;
         const float2 mxh = make_float2(l0 ? nxh.x : kFarLane, l1 ? nxh.y : kFarLane);
         const float2 myh = make_float2(l0 ? nyh.x : kFarLane, l1 ? nyh.y : kFarLane);
-        uint32_t m[2];
-        eval(A, B, 0u, mxh, myh, m[0], m[1]);
+        uint32_t m[2] = {0u, 0u};
+        bool root_done = false;
+        if constexpr (LEAVES) root_done = exact_leaf(0u, l0, l1);
+        if (!root_done) eval(A, B, 0u, mxh, myh, m[0], m[1]);
         const bool push = (m[0] | m[1]) != 0u;
         SE::store_if(push & (lane == 0), sp, 0u, m);
         sp += push ? SE::kBytes : 0u;
@@ -464,6 +505,9 @@ traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
             const float4 A = __ldg(reinterpret_cast<const float4*>(rp + q));        // chx chy clx cly
             const float2 B = __ldg(reinterpret_cast<const float2*>(rp + q) + 2);    // gm thr
             uint32_t m[2];
+            if constexpr (LEAVES) {
+                if (exact_leaf(base + q, a0, a1)) continue;                          // a leaf: nobody opens it
+            }
             eval(A, B, base + q, mxh, myh, m[0], m[1]);
             // branch-free push: one straight-line block per step keeps four independent chains in flight
             const bool push = (m[0] | m[1]) != 0u;
@@ -884,7 +928,8 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
     // two bodies per lane halve the node traffic and the control overhead per body, but need >= ~400k
     // bodies to keep every SM's warp slots full (ncu: profiles/r01_traverse_v4_*)
     const bool exact_leaves = p.flags & BH_FLAG_EXACT_LEAVES;   // extension: generic 1-body-per-lane / FP64 kernels only
-    const int bpl = exact_leaves ? 1 : (p.reserved[0] == 1) ? 1 : (p.reserved[0] >= 2 && p.reserved[0] <= 7) ? 2 : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
+    const bool leaves_pair = exact_leaves && p.reserved[0] == 2 && !(p.flags & (BH_FLAG_COUNTERS | BH_FLAG_FP64_TRAVERSAL));
+    const int bpl = leaves_pair ? 2 : exact_leaves ? 1 : (p.reserved[0] == 1) ? 1 : (p.reserved[0] >= 2 && p.reserved[0] <= 7) ? 2 : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
     // previous operation on the stream = tree_top_kernel (or a peer-exchange kernel; g_pdl is off there)
 #define BH_GO(K) launch_chain(K, dim3(blocks), dim3(kTravThreads), st, true, a)
     if (fp64) {
@@ -899,7 +944,11 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
         const int64_t per_block = (int64_t)kTravThreads * bpl;
         unsigned blocks = (unsigned)((own_n + per_block - 1) / per_block);
 #define BH_TRAV(B, I, C) BH_GO((traverse_f32_kernel<B, I, C>))
-        if (exact_leaves) {
+        if (leaves_pair) {
+            const bool exact = p.flags & BH_FLAG_EXACT_EPS;
+            if (integrate) { if (exact) BH_GO((traverse_f32_pair_kernel<true, true, false, false, true>)); else BH_GO((traverse_f32_pair_kernel<true, false, false, false, true>)); }
+            else { if (exact) BH_GO((traverse_f32_pair_kernel<false, true, false, false, true>)); else BH_GO((traverse_f32_pair_kernel<false, false, false, false, true>)); }
+        } else if (exact_leaves) {
             if (integrate) { if (count) BH_GO((traverse_f32_kernel<1, true, true, true>)); else BH_GO((traverse_f32_kernel<1, true, false, true>)); }
             else { if (count) BH_GO((traverse_f32_kernel<1, false, true, true>)); else BH_GO((traverse_f32_kernel<1, false, false, true>)); }
         } else if (bpl == 2 && !count && p.reserved[0] == 4 && !(p.flags & BH_FLAG_EXACT_EPS)) {

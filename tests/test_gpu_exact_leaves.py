@@ -47,6 +47,14 @@ def test_forces_match_the_oracle_extension(name):
         assert rel_rms(f[ok], want[ok]) <= 1e-5        # FP32 traversal, same bar as the reference-semantics mode
         per = np.linalg.norm(f[ok] - want[ok], axis=1) / np.maximum(np.linalg.norm(want[ok], axis=1), 1e-300)
         assert np.median(per) <= 1e-5
+    for exact_eps in (False, True):             # the pair kernel's exact-leaves path (two bodies per lane, packed)
+        with Simulation(len(mass), exact_leaves=True, bodies_per_lane=2, exact_eps=exact_eps) as sim:
+            sim.set_bodies(pos, vel, mass)
+            sim.build_tree()
+            sim.compute_forces()
+            f = sim.forces()
+            ok = np.isfinite(want).all(axis=1)
+            assert rel_rms(f[ok], want[ok]) <= 1e-5, exact_eps
 
 
 def test_against_the_direct_sum(shipped40k):

@@ -19,6 +19,7 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:trav
     -o gpurun_out/r2_traverse_pair python tools/profile_step.py --steps 4 > gpurun_out/r2_ncu_full.log 2>&1
 timeout 120 python tools/profile_step.py --steps 4 > gpurun_out/r2_profile_default.log 2>&1
 timeout 120 python tools/profile_step.py --steps 4 --exact-leaves > gpurun_out/r2_profile_exact_leaves.log 2>&1
+timeout 120 python tools/profile_step.py --steps 4 --exact-leaves --bpl 2 > gpurun_out/r2_profile_exact_leaves_pair.log 2>&1
 # 6. the experimental variants of the pair kernel (bodies_per_lane knob 4 = L1 prefetch, 5 = SM-local block order,
 #    6 = both, 7 = pop + fetch of the next cell between test and force phase): parity, then time (traverse_us of each log vs r2_profile_default.log)
 ( BH_TEST_UNVALIDATED=1 timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -q -k traversal_variants 2>&1 | tail -5 ) > gpurun_out/r2_prefetch_pytest.log
@@ -29,7 +30,7 @@ timeout 120 python tools/profile_step.py --steps 6 --bpl 7 > gpurun_out/r2_profi
 # 8. BASELINE config 1 shape (the reference's own N = 40 000, 10 free-running steps; step 0 is the non-degenerate one)
 timeout 120 python tools/free_run.py 40000 10 square > gpurun_out/r2_free_run_40000.log 2>&1
 tail -5 gpurun_out/r2_exact_leaves_pytest.log gpurun_out/r2_pytest.log gpurun_out/r2_smoke.log
-tail -3 gpurun_out/r2_prefetch_pytest.log; tail -1 gpurun_out/r2_profile_default.log gpurun_out/r2_profile_exact_leaves.log gpurun_out/r2_profile_prefetch.log gpurun_out/r2_profile_sm_local.log gpurun_out/r2_profile_sm_local_prefetch.log gpurun_out/r2_profile_pipelined.log
+tail -3 gpurun_out/r2_prefetch_pytest.log; tail -1 gpurun_out/r2_profile_default.log gpurun_out/r2_profile_exact_leaves.log gpurun_out/r2_profile_exact_leaves_pair.log gpurun_out/r2_profile_prefetch.log gpurun_out/r2_profile_sm_local.log gpurun_out/r2_profile_sm_local_prefetch.log gpurun_out/r2_profile_pipelined.log
 cut -c1-300 gpurun_out/r2_bench_default.json
 # 7. (needs 2 GPUs: gpurun --gpus 2) the pipelined multi-rank host step, parity then e2e:
 #   BH_HOST_PIPELINE_MULTI=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
