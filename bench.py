@@ -5,30 +5,34 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (config.workload): BASELINE.json configs[1] — 1 000 000 bodies, uniform disk R = 0.1, seed
-12345, the reference's constants (G, dt = 1, theta = 0.5, depth cap 10).  A *step* is one pass of
-the whole hot path: bounds -> cell keys -> radix sort -> tree + COM -> traversal -> integrate.
-Because the reference's own physics flings bodies away after ONE step and the tree collapses to
-a few hundred nodes, every step starts from the initial distribution (a device
-snapshot that the step reads out of place; nothing is skipped: bounds, keys, sort, tree, traversal
-and integrator all run every step) — i.e. every timed step does the full-size, non-degenerate work
-of the reference's step 0.  At N > 1 GPUs the body count grows with N (weak scaling, 1M bodies per
-GPU, contiguous Morton slices, sharded tree build; the ranks exchange the bounding box and the
-per-cell sums over NVLink peer memory, not the bodies).
+12345, the reference's constants (G, dt = 1, theta = 0.5, depth cap 10), drawn by the library's own
+counter-based generator (bh_generate_host: the same bodies for every arm and every N; no text round
+trip).  A *step* is one pass of the whole hot path: bounds -> cell keys -> radix sort -> tree + COM ->
+traversal -> integrate.  Because the reference's own physics flings bodies away after ONE step and
+the tree collapses to a few hundred nodes, every step starts from the initial
+distribution (a device snapshot that the step reads out of place; nothing is skipped: bounds, keys,
+sort, tree, traversal and integrator all run every step) — i.e. every timed step does the full-size,
+non-degenerate work of the reference's step 0.  At N > 1 GPUs the body count grows with N (weak
+scaling, 1M bodies per GPU, contiguous Morton slices, sharded tree build; the ranks exchange the
+bounding box and the per-cell sums over NVLink peer memory, not the bodies).
 
-`value`  : device-resident throughput, inputs in HBM: W warm-up steps, then EXACTLY K steps between two
-           barrier + torch.cuda.synchronize() brackets, device time from CUDA events on the library's
-           stream, max over ranks.  The per-rank working set (~150 MB) exceeds the 126 MB L2;
-           `value_l2_flushed` repeats the K steps with an explicit L2 flush before each one.
+`value`  : device-resident throughput, inputs in HBM: W warm-up steps, then brackets of EXACTLY K steps
+           between two barrier + torch.cuda.synchronize() fences, device time from CUDA events on the
+           library's stream, max over ranks; the bracket is repeated (`brackets`) and the MEDIAN is
+           reported, so a short K is not an 11 ms sample.  The per-rank working set (~150 MB) exceeds
+           the 126 MB L2; `value_l2_flushed` repeats K steps with an explicit L2 flush before each.
 `e2e`    : same step through the C-ABI with HOST buffers: pinned H2D of positions, velocities and
            masses + step + D2H of positions every step, wall clock around the synchronous calls.
 `roofline`: traversal kernel, 20 flop per accepted interaction against the FP32
-           FMA peak measured by a register-resident FMA loop on the same device; `issue_view` = the same
-           kernel against the SM's issue slots (what actually binds it).
+           FMA peak measured by a register-resident FMA loop on the same device.
+`strong` : (N > 1) BASELINE config 4 / north_star's target: 16M bodies TOTAL on the N GPUs, against the
+           same 16M bodies on ONE GPU (rank 0) measured in the same job.
+`direct` : (N = 1) BASELINE config 5: the tiled all-pairs kernel at 262 144 bodies.
 `cpu_baseline`: the reference's OWN CPU functions (oracle/_ref, 1 thread: it has no threading) on the same
            bodies (+ `port_all_cores`: the oracle port with OpenMP over bodies, labelled as a port).
 `gpu_baseline`: the reference's OWN GPU program (unmodified project.cu, sm_100a) on the same GPU, its two timers.
 `accuracy`: force rel-RMS of the timed configuration against the reference tree forces (sampled bodies).
-`--impl reference`: the CPU reference arm alone, same JSON line shape.
+`--impl reference`: the CPU reference arm alone, same JSON line shape, same workload.
 """
 import argparse
 import json
@@ -46,20 +50,32 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 BODIES_PER_GPU = 1_000_000
+STRONG_TOTAL = 16_000_000
+DIRECT_N = 262_144
 SEED = 12345
 FLOP_PER_INTERACTION = 20.0
-TRAVERSE_DRAM_BYTES_NCU = 74_801_152 + 37_312_768   # profiles/r01_traverse_v8_pair_ncu_summary.txt
-TRAVERSE_WARP_INSTRUCTIONS_NCU = 298_806_710          # same capture: smsp__inst_executed.sum at N = 1M uniform disk
 METRIC = "body_steps_per_s"
 UNIT = "body·steps/s"
+GEN_KIND = {"disk": "uniform_disk", "plummer": "plummer_2d", "square": "uniform_square"}
+# dram__bytes_read.sum + dram__bytes_write.sum and smsp__inst_executed.sum of the production traversal kernel, one
+# `ncu --set full` capture at N = 1M uniform disk; see profiles/ (file named in NCU_SOURCE)
+NCU_SOURCE = "profiles/r01_traverse_v8_pair_ncu_summary.txt"
+TRAVERSE_DRAM_BYTES_NCU = 74_801_152 + 37_312_768
+TRAVERSE_WARP_INSTRUCTIONS_NCU = 298_806_710
 
 
 def make_workload(n, dist="disk"):
-    from gpu_nbody_simulation_b200 import initial_conditions as ic
-    # values pass through the reference writers' "%.6g" text format (round6) up to 2M bodies; above that
-    # the string round trip alone takes minutes per rank, so the raw FP64 draws are used
-    gen = {"disk": ic.uniform_disk, "plummer": ic.plummer_2d, "square": ic.uniform_square}[dist]
-    return gen(n, seed=SEED, round6=n <= 2_000_000)
+    """The timed bodies: the library's seeded counter-based generator on the host (csrc/generate.cu, needs no
+    GPU), raw FP64 draws — ONE generator and ONE family of workloads for every N, both arms and the CLI."""
+    import gpu_nbody_simulation_b200 as bh
+    return bh.generate_host(GEN_KIND[dist], n, seed=SEED)
+
+
+def workload_string(n, world, dist="disk", max_depth=10):
+    name = {"disk": "uniform disk", "plummer": "Plummer sphere projected to 2-D (a=0.02, r<=0.1)", "square": "uniform square"}[dist]
+    return (f"{name} N={n} ({n // world} per GPU), R=0.1, seed {SEED} (bh_generate_host), theta=0.5, G=6.67e-11, dt=1, "
+            f"depth cap {max_depth}; every step restarts from the initial distribution (the full-size work of the "
+            "reference's step 0)")
 
 
 class ClockSampler:
@@ -76,10 +92,10 @@ class ClockSampler:
         arrived: nvidia-smi's start-up attaches to every GPU of the box and takes 1-2 s on an 8-GPU
         node, during which kernel launches of all ranks stall for milliseconds — started right before
         the timed bracket (as an earlier version did, once per rank) it cost the 4- and 8-GPU runs
-        30-60 % (gpurun_out/final_weak_g8.json vs bench_weak_g8.log).  Polling afterwards is cheap."""
+        30-60 %.  Polling afterwards is cheap."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
             t0 = time.perf_counter()
@@ -113,54 +129,82 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def pin_to_gpu_numa_node(dev):
-    """Binds this process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that the pinned
-    host buffers of the e2e leg are allocated next to the GPU's PCIe root.  Best effort: returns the
-    node number or None (no sysfs entry, single node, restricted cpuset)."""
+def numa_node_of_gpu(dev):
+    """(node, reason): the NUMA node the GPU hangs off according to sysfs, or (None, why not)."""
     try:
         import torch
         p = torch.cuda.get_device_properties(dev)
         bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
-        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
-        if node < 0:
-            return None
+    except Exception as e:
+        return None, f"no PCI address for device {dev}: {type(e).__name__}"
+    path = f"/sys/bus/pci/devices/{bdf}/numa_node"
+    try:
+        node = int(open(path).read())
+    except OSError:
+        return None, f"{path} not readable (container without the PCI sysfs tree)"
+    if node < 0:
+        return None, f"{path} = {node}: the platform exposes no NUMA affinity for this GPU (single node or virtualised)"
+    return node, "sysfs"
+
+
+def pin_to_gpu_numa_node(dev):
+    """Binds this process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that the pinned
+    host buffers of the e2e leg are allocated next to the GPU's PCIe root.  Best effort: returns the
+    node number or None (no sysfs entry, single node, restricted cpuset)."""
+    return pin_to_gpu_numa_node_why(dev)[0]
+
+
+def pin_to_gpu_numa_node_why(dev):
+    node, why = numa_node_of_gpu(dev)
+    if node is None:
+        return None, why
+    try:
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
             cpus.update(range(int(lo), int(hi or lo) + 1))
         cpus &= os.sched_getaffinity(0)
         if not cpus:
-            return None
+            return None, f"node {node}: none of its CPUs is in this process's cpuset"
         os.sched_setaffinity(0, cpus)
-        return node
-    except Exception:
-        return None
+        return node, f"bound to the {len(cpus)} CPUs of node {node}"
+    except Exception as e:
+        return None, f"node {node}: {type(e).__name__}: {e}"
 
 
 def cpu_reference_run(n_bodies, steps, warmup, budget_s=150.0):
-    """Times the reference's OWN CPU path (oracle/_ref, unmodified project.cu functions, 1 thread —
-    the reference has no threading) or, if it was not built, the oracle port.  Every step restarts
-    from the initial distribution, like the GPU arm.  Returns (value, info)."""
+    """Times the reference's OWN CPU path (oracle/_ref, unmodified project.cu functions, 1 thread — the
+    reference has no threading) on the first `n_bodies` bodies of the bench workload (the whole 1M workload
+    when n_bodies = 1M), every step restarted from the initial distribution like the GPU arm.  The body count is
+    NEVER reduced silently: if the binary for n_bodies is missing the oracle port is timed instead (kind "port").
+    A step of the 1M workload takes ~4 s, so when `steps + warmup` full steps do not fit into `budget_s` fewer
+    steps are executed (each still the full workload; the rate is per step) and `steps_executed` says so.
+    Returns (value, info)."""
     import oracle
-    est_per_step = {1_000_000: 10.5, 262_144: 2.6, 65_536: 0.6}
-    total = steps + warmup
-    choice = None
-    for n in (1_000_000, 262_144, 65_536):
-        if n <= n_bodies and oracle.ref_available(n) and est_per_step[n] * total <= budget_s:
-            choice = n
-            break
-    pos, vel, mass = make_workload(1_000_000)
-    if choice is not None:
-        p, v, m = pos[:choice], vel[:choice], mass[:choice]
-        _, tim = oracle.run_ref(p, v, m, steps=total, dump="", keep_dump=False, reset_each_step=True)
-        timed = tim[warmup:]
+    pos, vel, mass = make_workload(BODIES_PER_GPU)
+    pos, vel, mass = pos[:n_bodies], vel[:n_bodies], mass[:n_bodies]
+    if oracle.ref_available(n_bodies):
+        t0 = time.perf_counter()
+        _, first = oracle.run_ref(pos, vel, mass, steps=1, dump="", keep_dump=False, reset_each_step=True)
+        probe_wall = time.perf_counter() - t0                       # includes writing / reading the 40 MB input
+        per_step = sum(first[0][k] for k in ("build_us", "force_us", "update_us")) * 1e-6
+        afford = int(max(0.0, budget_s - probe_wall) / max(per_step, 1e-9))
+        want = steps + max(0, warmup - 1)                            # the probe step was the first warm-up step
+        run = max(1, min(want, afford))
+        _, tim = oracle.run_ref(pos, vel, mass, steps=run, dump="", keep_dump=False, reset_each_step=True)
+        timed = tim[min(max(0, warmup - 1), run - 1):] if run > steps else tim
+        timed = timed[-steps:]
         secs = sum(t["build_us"] + t["force_us"] + t["update_us"] for t in timed) * 1e-6
-        value = choice * len(timed) / secs
-        info = {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
+        value = n_bodies * len(timed) / secs
+        info = {"value": value, "unit": UNIT, "cores": 1, "kind": "reference", "n_bodies": n_bodies,
+                "steps_executed": len(timed),
                 "sample": (f"{len(timed)} full steps (buildTree + computeForces + update*) of the reference's own CPU "
-                           f"functions on the first {choice} bodies of the 1M uniform disk, restarted from the initial "
-                           f"distribution every step; build {sum(t['build_us'] for t in timed) / len(timed) / 1e3:.0f} ms, "
-                           f"force {sum(t['force_us'] for t in timed) / len(timed) / 1e3:.0f} ms per step"),
+                           f"functions (oracle/_ref/ref_harness_N{n_bodies}: unmodified project.cu, -O2, 1 thread) on "
+                           f"{'all' if n_bodies == BODIES_PER_GPU else 'the first'} {n_bodies} bodies of the bench workload, "
+                           f"restarted from the initial distribution every step; build "
+                           f"{sum(t['build_us'] for t in timed) / len(timed) / 1e3:.0f} ms, force "
+                           f"{sum(t['force_us'] for t in timed) / len(timed) / 1e3:.0f} ms per step"
+                           + ("" if len(timed) == steps else f"; {steps} steps asked, {len(timed)} fit the {budget_s:.0f} s budget")),
                 "ms_per_step": secs / len(timed) * 1e3}
         return value, info
     # oracle port: full tree build, forces on a strided subset, single thread
@@ -171,9 +215,10 @@ def cpu_reference_run(n_bodies, steps, warmup, budget_s=150.0):
     tree.forces(stride=stride, nthreads=1)
     t2 = time.perf_counter()
     secs = (t1 - t0) + (t2 - t1) * stride
-    value = 1_000_000 / secs
-    return value, {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": f"oracle port: full 1M tree build + forces for every {stride}th body, extrapolated",
+    value = n_bodies / secs
+    return value, {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "n_bodies": n_bodies, "steps_executed": 1,
+                   "sample": f"oracle port (oracle/_ref/ref_harness_N{n_bodies} not built): full {n_bodies}-body tree build + "
+                             f"forces for every {stride}th body, extrapolated",
                    "ms_per_step": secs * 1e3}
 
 
@@ -231,16 +276,38 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, info = cpu_reference_run(1_000_000, args.steps, args.warmup)
+    n = BODIES_PER_GPU
+    value, info = cpu_reference_run(n, args.steps, args.warmup)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "steps_executed": info["steps_executed"],
             "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "uniform disk N=1M, theta=0.5, reference constants, every step from the initial "
-                                   "distribution (CPU reference path, see cpu_baseline.sample)"},
+            "config": {"workload": workload_string(n, 1), "n_bodies": info["n_bodies"],
+                       "note": "CPU reference arm: always the N = 1M single-GPU workload, whatever --gpus says (a step of "
+                               "the N-GPU weak workload would take N x 4 s); see cpu_baseline.sample"},
             "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def bracket_plan(K, target_steps=1000, lo=5, hi=50):
+    """Number of K-step brackets: enough for ~target_steps timed steps in total, between lo and hi."""
+    return int(max(lo, min(hi, -(-target_steps // max(K, 1)))))
+
+
+def sampled_accuracy(bh, oracle, f_gpu, pos, mass, max_depth, lo, hi, nsample=4096, exact_leaves=False):
+    """Force rel-RMS of f_gpu[lo:hi] against the reference tree forces (pinned oracle) on ~nsample bodies of [lo, hi)."""
+    stride = max(1, (hi - lo) // nsample)
+    tree = oracle.Tree(pos, mass, oracle.default_params(max_depth=max_depth))
+    fn = tree.forces_exact_leaves if exact_leaves else tree.forces
+    f_ref, _ = fn(i0=lo, i1=hi, stride=stride, nthreads=oracle.max_threads())
+    a_, b_ = f_gpu[lo:hi:stride], f_ref[lo:hi:stride]
+    ok = np.isfinite(b_).all(axis=1)
+    err = float(np.sqrt(((a_[ok] - b_[ok]) ** 2).sum() / max((b_[ok] ** 2).sum(), 1e-300)))
+    return {"force_rel_rms_vs_reference_tree": err, "bar": 1e-5,
+            "sample": f"every {stride}th body of [{lo}, {hi}) ({int(ok.sum())} bodies) of the timed workload; reference tree "
+                      "forces from the C restatement pinned bit-for-bit to the reference (oracle/)"}
 
 
 def run_ours(args):
@@ -254,16 +321,16 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
-    numa = pin_to_gpu_numa_node(local)
+    numa, numa_why = pin_to_gpu_numa_node_why(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    strong = args.total_bodies > 0
-    n = args.total_bodies if strong else BODIES_PER_GPU * world
-    pos, vel, mass = make_workload(n, args.dist)
+    strong_only = args.total_bodies > 0
+    n = args.total_bodies if strong_only else BODIES_PER_GPU * world
     K, W = args.steps, args.warmup
+    R = args.brackets if args.brackets > 0 else bracket_plan(K)
 
     def barrier():
         if dist is not None:
@@ -277,50 +344,72 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    if world > 1:
+    def morton_order(pos, vel, mass, n_):
         # Hand the bodies over in Morton order of the initial distribution (computed once with the
         # library itself, outside any timed region): a rank's contiguous index slice is then a compact
         # region, so the 64 bodies of a traversal warp stay neighbours.  Body order is arbitrary for a
         # synthetic workload; a multi-GPU application keeps its bodies in this order permanently.
-        with bh.Simulation(n, device=local, max_depth=args.max_depth) as tmp:
+        with bh.Simulation(n_, device=local, max_depth=args.max_depth) as tmp:
             tmp.set_bodies(pos, vel, mass)
             tmp.build_tree()
             order = tmp.sorted_order().astype(np.int64)
-        pos, vel, mass = np.ascontiguousarray(pos[order]), np.ascontiguousarray(vel[order]), np.ascontiguousarray(mass[order])
-    sim = bh.Simulation(n, device=local, rank=rank, n_ranks=world, graph=not args.no_graph, max_depth=args.max_depth)
+        return np.ascontiguousarray(pos[order]), np.ascontiguousarray(vel[order]), np.ascontiguousarray(mass[order])
+
+    def make_sim(n_, n_ranks, counters=False, p2p=True):
+        s = bh.Simulation(n_, device=local, rank=rank if n_ranks > 1 else 0, n_ranks=n_ranks, graph=not args.no_graph,
+                          max_depth=args.max_depth, counters=counters, exact_leaves=args.exact_leaves and n_ranks == 1)
+        if n_ranks > 1:
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(bh.nccl_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            s.attach_nccl(bytes(idt.cpu().numpy().tobytes()))   # NCCL: getters (ragged all-gather of slices)
+            if p2p and not args.no_p2p:
+                # per-step exchange over NVLink peer memory, fused with the kernels (csrc/peer_comm.cu)
+                handles = [None] * n_ranks
+                dist.all_gather_object(handles, s.comm_handle())
+                s.attach_peers(handles)
+                dist.barrier()      # nobody stores into a peer before every rank has opened every handle
+        return s
+
+    def timed_brackets(s, k, w, r):
+        """w warm-up steps, then r brackets of EXACTLY k steps, each between barrier + synchronize fences; per bracket
+        the device time from CUDA events on the library's stream, max over ranks.  Returns the list of ms."""
+        barrier()
+        s.step_from_snapshot(w)
+        s.synchronize()
+        out = []
+        for _ in range(r):
+            barrier()
+            s.step_from_snapshot(k)
+            barrier()
+            out.append(max_over_ranks(s.last_step_ms()))
+        return out
+
+    pos, vel, mass = make_workload(n, args.dist)
     if world > 1:
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(bh.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        sim.attach_nccl(bytes(idt.cpu().numpy().tobytes()))   # NCCL: getters (ragged all-gather of slices)
-        if not args.no_p2p:
-            # per-step exchange over NVLink peer memory, fused with the kernels (csrc/peer_comm.cu)
-            handles = [None] * world
-            dist.all_gather_object(handles, sim.comm_handle())
-            sim.attach_peers(handles)
+        pos, vel, mass = morton_order(pos, vel, mass, n)
+    sim = make_sim(n, world)
     sim.set_bodies(pos, vel, mass)
     sim.snapshot()
 
     # ---- device-resident timing -------------------------------------------------------------------
-    # L2 is flushed (512 MB written) before every timed step; each step is timed on its own with
-    # CUDA events on the library's stream and the K durations are summed.
     flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 
     def flush_l2(i):
         flush_buf.fill_(i & 0xFF)
         torch.cuda.synchronize()
 
-    def timed_steps(k):
+    def timed_steps_flushed(s, k):
         tot = 0.0
         for i in range(k):
             flush_l2(i)
-            sim.step_from_snapshot(1)
-            tot += sim.last_step_ms()
+            s.step_from_snapshot(1)
+            tot += s.last_step_ms()
         return tot
 
     # clocks: ONE nvidia-smi for the whole job (rank 0 samples every GPU of the job), started and
-    # producing samples BEFORE the warm-up so that its start-up cannot disturb the timed bracket
+    # producing samples BEFORE the warm-up so that its start-up cannot disturb the timed brackets
     vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
     smi_ids = [vis[i] if i < len(vis) else str(i) for i in range(world)]   # nvidia-smi ignores CUDA_VISIBLE_DEVICES
     sampler = ClockSampler(",".join(smi_ids)) if rank == 0 else None
@@ -332,85 +421,86 @@ def run_ours(args):
     barrier()
     if sampler:
         sampler.mark()
-    # headline: EXACTLY K steps between two barrier + synchronize brackets, device time from CUDA events on
-    # the library's stream (recorded around the K steps), max over ranks
     sim.reset_timers()
-    sim.step_from_snapshot(K)
-    barrier()
-    ms = max_over_ranks(sim.last_step_ms())
-    launches = sim.timers()["kernel_launches"]
+    bracket_ms = timed_brackets(sim, K, 0, R)
+    launches = sim.timers()["kernel_launches"] // R        # kernels of this library per K-step bracket
+    ms = statistics.median(bracket_ms)
     # variant with an explicit L2 flush before every step (steps timed one by one and summed); with several
     # ranks this one also charges every host-side skew between the ranks to the waiting rank
-    ms_flushed = max_over_ranks(timed_steps(K))
+    ms_flushed = max_over_ranks(timed_steps_flushed(sim, K))
     barrier()
     clocks = sampler.stop() if sampler else None
     value = n * K / (ms * 1e-3)
 
     # ---- per-phase events + interaction count (second pass, direct launches, same work) -----------
-    phases, inter_per_step, roofline = None, None, None
-    if world > 1:      # collective: every rank runs the profiled pass, rank 0 reports its phases
-        sim.set_profiling(True)
-        sim.step_from_snapshot(2)
-        sim.reset_timers()
-        timed_steps(K)
-        sim.synchronize()
-        t = sim.timers()
-        sim.set_profiling(False)
-        phases = {k: t[k] / max(t["steps"], 1) for k in ("bounds_keys_us", "sort_us", "build_us", "traverse_us",
-                                                         "exchange_us", "total_us")}
-    simc = bh.Simulation(n, device=local, rank=rank, n_ranks=1, counters=True, max_depth=args.max_depth) if world == 1 else None
-    if rank == 0 and simc is not None:
-        simc.set_bodies(pos, vel, mass)
-        simc.snapshot()
-        simc.step_from_snapshot(1)
-        simc.synchronize()
-        cnt = simc.counters()
-        inter_per_step = cnt["interactions"]
-        simc.close()
-        sim.set_profiling(True)
-        sim.step_from_snapshot(2)
-        sim.reset_timers()
-        timed_steps(K)
-        sim.synchronize()
-        t = sim.timers()
-        sim.set_profiling(False)
-        phases = {k: t[k] / max(t["steps"], 1) for k in ("bounds_keys_us", "sort_us", "build_us", "traverse_us",
-                                                         "exchange_us", "total_us")}
+    sim.set_profiling(True)
+    sim.step_from_snapshot(2)
+    sim.reset_timers()
+    timed_steps_flushed(sim, min(K, 50))
+    sim.synchronize()
+    t = sim.timers()
+    sim.set_profiling(False)
+    phases = {k: t[k] / max(t["steps"], 1) for k in ("bounds_keys_us", "sort_us", "build_us", "traverse_us",
+                                                     "exchange_us", "total_us")}
+    # interactions of THIS rank's bodies: counting variant of the traversal kernel on a second context (multi-rank:
+    # NCCL exchange, one step)
+    simc = make_sim(n, world, counters=True, p2p=False)
+    simc.set_bodies(pos, vel, mass)
+    simc.snapshot()
+    simc.step_from_snapshot(1)
+    simc.synchronize()
+    inter_rank = simc.counters()["interactions"]
+    simc.close()
+    roofline = None
+    own_lo, own_hi = bh.shard_range(n, world, rank)
+    if rank == 0:
         peak_tf, mhz = bh.measure_fp32_peak(local)
         trav_s = phases["traverse_us"] * 1e-6
-        achieved = inter_per_step * FLOP_PER_INTERACTION / trav_s / 1e12
+        achieved = inter_rank * FLOP_PER_INTERACTION / trav_s / 1e12
         roofline = {"bound": "fp32", "kernel": "traverse_kernel<fp32,integrate>", "achieved": achieved,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "traffic": TRAVERSE_DRAM_BYTES_NCU,
-                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full "
-                                      "capture at N=1M (profiles/r01_traverse_v8_pair_ncu_summary.txt); algorithmic "
-                                      "bytes = 72 B/body state + 11 MB tree = 83 MB",
+                    "traffic": TRAVERSE_DRAM_BYTES_NCU if (world == 1 and n == BODIES_PER_GPU) else None,
+                    "traffic_source": f"dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full "
+                                      f"capture at N=1M ({NCU_SOURCE}); algorithmic bytes = 72 B/body state + 11 MB tree = 83 MB",
                     "peak_source": f"measured here: FFMA loop, {peak_tf:.1f} TFLOP/s (implies {mhz:.0f} MHz at 128 FMA/clk/SM); "
                                    "FP32 peak is not in MEASURED_PEAKS.json (SURVEY 8d)",
-                    "interactions_per_step": inter_per_step, "flop_per_interaction": FLOP_PER_INTERACTION,
-                    "kernel_us": phases["traverse_us"],
+                    "interactions_per_step": inter_rank, "bodies": own_hi - own_lo,
+                    "flop_per_interaction": FLOP_PER_INTERACTION, "kernel_us": phases["traverse_us"],
                     "kernel_timing": "cudaEvents around the kernel on the library's stream, averaged over a second pass "
-                                     "of the same K steps with direct launches (the timed pass replays a CUDA graph)",
-                    "interactions_per_s": inter_per_step / trav_s}
-        if n == 1_000_000 and args.dist == "disk" and args.max_depth == 10:
-            # issue-slot view of the same kernel: the 20-flop convention counts accepted interactions, the hardware
-            # spends ~18.4 warp instructions per (body, node) EVALUATION; instructions per launch are a
-            # property of kernel + workload, measured once with ncu
+                                     "of steps with direct launches (the timed pass replays a CUDA graph); rank 0's kernel "
+                                     "and rank 0's bodies",
+                    "interactions_per_s": inter_rank / trav_s}
+        if world == 1 and n == BODIES_PER_GPU and args.dist == "disk" and args.max_depth == 10 and not args.exact_leaves:
             sms = torch.cuda.get_device_properties(local).multi_processor_count
             slots_per_s = sms * 4 * mhz * 1e6
             roofline["issue_view"] = {"warp_instructions_per_launch": TRAVERSE_WARP_INSTRUCTIONS_NCU,
-                                      "source": "smsp__inst_executed.sum, profiles/r01_traverse_v8_pair_ncu_summary.txt",
+                                      "source": f"smsp__inst_executed.sum, {NCU_SOURCE}",
                                       "issue_slots_per_s": slots_per_s, "sm_count": sms, "sm_mhz_from_fma_loop": mhz,
                                       "frac_of_issue_slots": TRAVERSE_WARP_INSTRUCTIONS_NCU / (slots_per_s * trav_s)}
-        # whole-step HBM view: mandatory body traffic (72 B/body FP64 state) vs measured copy peak
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
             src = "MEASURED_PEAKS.json"
         except Exception:
             hbm_peak, src = 6650.0, "fallback"
-        roofline["hbm_view"] = {"bytes_per_body_step": 72, "achieved_gbs": 72.0 * n / (ms / K * 1e-3) / 1e9,
+        roofline["hbm_view"] = {"bytes_per_body_step": 72, "achieved_gbs": 72.0 * (n // world) / (ms / K * 1e-3) / 1e9,
                                 "peak_gbs": hbm_peak, "peak_source": src,
-                                "note": "the step is FP32-issue bound, not HBM bound (SURVEY 8d)"}
+                                "note": "per GPU; the step is FP32-issue bound, not HBM bound (SURVEY 8d)"}
+
+    # ---- accuracy of the timed configuration (BASELINE.json's metric carries "force rel-RMS error vs ref") ---------
+    # forces of the default (FP32) traversal; multi-rank: the getter gathers every rank's slice, rank 0 checks ITS slice
+    accuracy = None
+    sim.restore()
+    sim.build_tree()
+    sim.compute_forces()
+    f_gpu = sim.forces()              # collective on a multi-rank context
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            import oracle
+            accuracy = sampled_accuracy(bh, oracle, f_gpu, pos, mass, args.max_depth, own_lo, own_hi,
+                                        exact_leaves=args.exact_leaves and world == 1)
+        except Exception as e:   # never worth losing the line for
+            accuracy = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    del f_gpu
 
     # ---- end to end through the C-ABI with host buffers --------------------------------------------
     hp = torch.from_numpy(pos).pin_memory()
@@ -419,73 +509,146 @@ def run_ours(args):
     hout = torch.empty((n, 2), dtype=torch.float64).pin_memory()
     for _ in range(max(1, min(W, 3))):
         sim.step_host(hp, hv, hm, hout)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        # bh_step_host: H2D of this step's inputs (pinned), one step, D2H of its result; synchronous
-        sim.step_host(hp, hv, hm, hout)
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_runs = []
+    for _ in range(max(3, min(R, 10))):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            # bh_step_host: H2D of this step's inputs (pinned), one step, D2H of its result; synchronous
+            sim.step_host(hp, hv, hm, hout)
+        barrier()
+        e2e_runs.append(max_over_ranks(time.perf_counter() - t0))
+    e2e_s = statistics.median(e2e_runs)
+    per_rank = own_hi - own_lo
     e2e = {"value": n * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(40 * n), "d2h_bytes_per_step": int(16 * n),
-           "ms_per_step": e2e_s / K * 1e3}
+           "ms_per_step": e2e_s / K * 1e3, "brackets": len(e2e_runs),
+           "note": f"each rank moves its own slice ({per_rank} bodies: {40 * per_rank} B up, {16 * per_rank} B down) over its own PCIe link"}
+    del hp, hv, hm, hout
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        _, cpu_baseline = cpu_reference_run(1_000_000, 1, 0, budget_s=30.0)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not strong_only:
+        _, cpu_baseline = cpu_reference_run(BODIES_PER_GPU, 3, 1, budget_s=30.0)
         cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
         try:
             cpu_baseline["port_all_cores"] = cpu_port_all_cores(pos, mass)
         except Exception as e:   # an extra, never worth losing the line for
             cpu_baseline["port_all_cores"] = {"unavailable": str(e)[:200]}
 
-    # accuracy of the timed configuration (BASELINE.json's metric carries "force rel-RMS error vs ref"): forces of
-    # the default (FP32) traversal against the reference tree forces from the pinned oracle, on a body sample
-    accuracy = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            import oracle
-            with bh.Simulation(n, device=local, max_depth=args.max_depth) as sa:
-                sa.set_bodies(pos, vel, mass)
-                sa.build_tree()
-                sa.compute_forces()
-                f_gpu = sa.forces()
-            stride = max(1, n // 4096)
-            tree = oracle.Tree(pos, mass, oracle.default_params(max_depth=args.max_depth))
-            f_ref, _ = tree.forces(stride=stride, nthreads=oracle.max_threads())
-            a_, b_ = f_gpu[::stride], f_ref[::stride]
-            ok = np.isfinite(b_).all(axis=1)
-            err = float(np.sqrt(((a_[ok] - b_[ok]) ** 2).sum() / max((b_[ok] ** 2).sum(), 1e-300)))
-            accuracy = {"force_rel_rms_vs_reference_tree": err, "bar": 1e-5,
-                        "sample": f"every {stride}th body ({int(ok.sum())} bodies) of the timed workload; reference tree "
-                                  "forces from the C restatement pinned bit-for-bit to the reference (oracle/)"}
-        except Exception as e:   # never worth losing the line for
-            accuracy = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
-
     gpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_gpu_baseline and not strong and args.dist == "disk" and args.max_depth == 10:
+    if rank == 0 and world == 1 and not args.no_gpu_baseline and not strong_only and args.dist == "disk" and args.max_depth == 10:
         gpu_baseline = reference_gpu_run(pos, vel, mass, local)
+
+    # ---- config 5: direct all-pairs kernel at 262 144 bodies (single GPU) -------------------------------------
+    direct = None
+    if rank == 0 and world == 1 and not args.no_direct and not strong_only:
+        try:
+            dn = DIRECT_N
+            with bh.Simulation(dn, device=local) as sd:
+                sd.set_bodies(pos[:dn], vel[:dn], mass[:dn])
+                sd.direct_forces(want_output=False)
+                times = [sd.direct_forces(want_output=False)[1] for _ in range(5)]
+                f_d, _ = sd.direct_forces()
+            dms = statistics.median(times)
+            pairs = float(dn) * dn
+            peak_tf = roofline["peak"] if roofline else None
+            direct = {"n_bodies": dn, "ms": dms, "pairs_per_s": pairs / (dms * 1e-3),
+                      "tflops_at_20_flop_per_pair": pairs * 20.0 / (dms * 1e-3) / 1e12,
+                      "frac_of_fp32_peak": (pairs * 20.0 / (dms * 1e-3) / 1e12 / peak_tf) if peak_tf else None,
+                      "formula": "main_approach_1.cpp:53-75 (G m_i m_j d / (d^2 d), i != j), FP32 arithmetic on a "
+                                 "double-float displacement, shared-memory tiles"}
+            if not args.no_cpu_baseline:
+                import oracle
+                sel = np.linspace(0, dn - 1, 64).astype(np.int64)
+                ref = np.stack([oracle.direct_forces(pos[:dn], mass[:dn], i0=int(i), i1=int(i) + 1,
+                                                     nthreads=oracle.max_threads())[int(i)] for i in sel])
+                direct["force_rel_rms_vs_oracle_direct_sum"] = float(
+                    np.sqrt(((f_d[sel] - ref) ** 2).sum() / (ref ** 2).sum()))
+                direct["sample"] = "64 bodies x all 262 144 partners, FP64 direct sum of the pinned oracle"
+        except Exception as e:
+            direct = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    sim.close()
+    del flush_buf
+    torch.cuda.empty_cache()
+
+    # ---- strong scaling at 16M bodies (north_star's multi-GPU target; BASELINE config 4) ------------------------
+    strong = None
+    if world > 1 and not strong_only and not args.no_strong:
+        ns = STRONG_TOTAL
+        Ks = max(3, min(K, 20))
+        Rs = 5
+        sp, sv, sm_ = make_workload(ns, "disk")
+        sp, sv, sm_ = morton_order(sp, sv, sm_, ns)
+        ss = make_sim(ns, world)
+        ss.set_bodies(sp, sv, sm_)
+        ss.snapshot()
+        s_ms = statistics.median(timed_brackets(ss, Ks, 3, Rs)) / Ks
+        ss.set_profiling(True)
+        ss.step_from_snapshot(2)
+        ss.reset_timers()
+        ss.step_from_snapshot(Ks)
+        ss.synchronize()
+        ts = ss.timers()
+        ss.set_profiling(False)
+        s_phases = {k: ts[k] / max(ts["steps"], 1) for k in ("bounds_keys_us", "sort_us", "build_us", "traverse_us",
+                                                             "exchange_us", "total_us")}
+        ss.restore()
+        ss.build_tree()
+        ss.compute_forces()
+        fs = ss.forces()
+        ss.close()
+        barrier()
+        one_ms, s_acc = None, None
+        if rank == 0:
+            lo0, hi0 = bh.shard_range(ns, world, 0)
+            if not args.no_cpu_baseline:
+                try:
+                    import oracle
+                    s_acc = sampled_accuracy(bh, oracle, fs, sp, sm_, args.max_depth, lo0, hi0, nsample=2048)
+                except Exception as e:
+                    s_acc = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+            with bh.Simulation(ns, device=local, max_depth=args.max_depth, graph=not args.no_graph) as s1:
+                s1.set_bodies(sp, sv, sm_)
+                s1.snapshot()
+                s1.step_from_snapshot(3)
+                s1.synchronize()
+                runs = []
+                for _ in range(Rs):
+                    torch.cuda.synchronize()
+                    s1.step_from_snapshot(Ks)
+                    runs.append(s1.last_step_ms())
+                one_ms = statistics.median(runs) / Ks
+        barrier()
+        if rank == 0:
+            strong = {"total_bodies": ns, "n_gpus": world, "steps_per_bracket": Ks, "brackets": Rs,
+                      "ms_per_step": s_ms, "value": ns / (s_ms * 1e-3), "unit": UNIT,
+                      "ms_per_step_1gpu_same_job": one_ms, "speedup_vs_1gpu": one_ms / s_ms,
+                      "target": "north_star: >= 6x at 16M bodies on 8 GPUs",
+                      "phases_us_rank0": s_phases, "accuracy": s_acc,
+                      "workload": workload_string(ns, world)}
+        del sp, sv, sm_, fs
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if strong_only else "weak",
                 "vs_baseline": None,
                 "dtype": "f32 (double-float displacement; FP64 state, tree and integrator)", "data": "synthetic",
-                "config": {"workload": f"{'uniform disk' if args.dist == 'disk' else args.dist} N={n} ({n // world} per GPU), R=0.1, seed {SEED}, theta=0.5, "
-                                       f"G=6.67e-11, dt=1, depth cap {args.max_depth}; every step restarts from the device-resident snapshot of the "
-                                       "initial distribution (out of place: the step reads the snapshot and writes the live "
-                                       "state, so every timed step is the full-size work of the reference's step 0)",
+                "brackets": {"count": R, "steps_each": K, "ms_median": ms, "ms_min": min(bracket_ms), "ms_max": max(bracket_ms),
+                             "note": "value = N K / median over the brackets; every bracket is EXACTLY K steps between "
+                                     "barrier + synchronize fences, device time, max over ranks"},
+                "config": {"workload": workload_string(n, world, args.dist, args.max_depth), "n_bodies": n,
+                           "exact_leaves": bool(args.exact_leaves),
                            "l2": "inputs larger than L2: the per-rank working set that every step reads and rewrites is "
                                  "~150 MB at 1M bodies per GPU (FP64 state + snapshot 116 MB, sort buffers 16 MB, tree 23 MB) "
-                                 "vs 126 MB of L2; value_l2_flushed repeats the K steps with 512 MB written before each "
+                                 "vs 126 MB of L2; value_l2_flushed repeats K steps with 512 MB written before each "
                                  "step (steps timed one by one and summed; with several ranks the un-timed flush also "
                                  "absorbs rank skew, so the bracketed value is the one to quote)",
                            "parallelism": (f"morton-shard x{world}: bodies handed over in Morton order, contiguous index "
                                            f"slice per rank, sharded build, " + ("2 NCCL all-reduces per step" if args.no_p2p else
                                            "box + cell-sum exchange by NVLink peer stores fused with the kernels")) if world > 1
-                           else "single GPU", "host_numa_node": numa},
+                           else "single GPU", "host_numa_node": numa, "host_numa_note": numa_why},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "accuracy": accuracy, "cpu_baseline": cpu_baseline, "gpu_baseline": gpu_baseline,
-                "phases_us": phases,
+                "phases_us": phases, "strong": strong, "direct": direct,
                 "value_l2_flushed": n * K / (ms_flushed * 1e-3)}
         print(json.dumps(line), flush=True)
         if args.reference_lines:
@@ -494,7 +657,6 @@ def run_ours(args):
             par_us = (phases["traverse_us"] if phases else ms / K * 1e3) * K
             print(f"GPU total computation took {int(round(ms))} milliseconds. "
                   f"GPU parallel computation took {int(round(par_us))} microseconds.", flush=True)
-    sim.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -505,12 +667,16 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--brackets", type=int, default=0, help="number of K-step brackets (default: ~1000 steps in total, 5..50)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference project.cu run on this GPU")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the 16M-body strong-scaling object")
+    ap.add_argument("--no-direct", action="store_true", help="N = 1: skip the direct all-pairs object (config 5)")
     ap.add_argument("--dist", choices=["disk", "plummer", "square"], default="disk",
                     help="synthetic distribution (BASELINE config 2: disk; config 3: plummer)")
     ap.add_argument("--max-depth", type=int, default=10,
                     help="QUADTREE_MAX_DEPTH (reference: 10); BASELINE config 3 (clustered Plummer) raises it, up to 13")
+    ap.add_argument("--exact-leaves", action="store_true", help="BH_FLAG_EXACT_LEAVES (extension; single GPU)")
     ap.add_argument("--no-graph", action="store_true", help="direct kernel launches instead of CUDA-graph replay")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-reduces instead of the peer-memory exchange")
     ap.add_argument("--total-bodies", type=int, default=0,

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -42,19 +43,24 @@ struct NcclApi {
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
+static NcclApi g_nccl;
+static std::once_flag g_nccl_once;
+static void nccl_load();
 static NcclApi* nccl_api() {
-    static NcclApi api;
-    static bool tried = false;
-    if (tried) return api.handle ? &api : nullptr;
-    tried = true;
+    std::call_once(g_nccl_once, nccl_load);     // contexts may live on several threads
+    if (!g_nccl.handle) { set_error("libnccl not loadable or incomplete"); return nullptr; }
+    return &g_nccl;
+}
+static void nccl_load() {
+    NcclApi& api = g_nccl;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     void* h = nullptr;
     for (const char* nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_NOLOAD); if (h) break; }   // torch's copy if loaded
     if (!h) for (const char* nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
-    if (!h) { set_error("libnccl not loadable: %s", dlerror()); return nullptr; }
+    if (!h) return;
 #define BH_SYM(field, name)                                                        \
     api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name));            \
-    if (!api.field) { set_error("libnccl lacks %s", name); return nullptr; }
+    if (!api.field) return;
     BH_SYM(GetUniqueId, "ncclGetUniqueId");
     BH_SYM(CommInitRank, "ncclCommInitRank");
     BH_SYM(CommDestroy, "ncclCommDestroy");
@@ -65,7 +71,6 @@ static NcclApi* nccl_api() {
     BH_SYM(GetErrorString, "ncclGetErrorString");
 #undef BH_SYM
     api.handle = h;
-    return &api;
 }
 
 #define BH_NCCL_OK(api, expr)                                                                   \
@@ -137,6 +142,8 @@ struct bh_ctx {
     bh_timers timers{};
     uint64_t launches_base = 0;
     bool bodies_set = false, tree_valid = false, have_snapshot = false, timed = false;
+    bool tree_built = false;         // some tree has been built (node count / root box of the last build stay readable after a step)
+    uint64_t zero_mass_bodies = 0;   // counted on the host by bh_set_bodies (see bh_counters)
     size_t step_zero_bytes = 0;      // see zero_scratch
     bool pdl = false;                // env BH_PDL=1: programmatic dependent launch along the single-GPU chain
     bool keys_table = false;         // env BH_KEYS_TABLE=1: cell keys from the boundary table instead of per-body bisection
@@ -189,6 +196,19 @@ struct DeviceGuard {
 int check_launch() {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("kernel launch: %s", cudaGetErrorString(e)); return BH_ERR_CUDA; }
+    return BH_OK;
+}
+
+// Peer-memory exchange: the device-side timeout word is sticky and fatal (peer_comm.cuh: wait_flag).  Called by every
+// entry point that has just synchronised the stream; the context stays in error until bh_attach_peers is called again.
+int peer_error(bh_ctx* c) {
+    if (!c->p2p_ready) return BH_OK;
+    uint32_t err = 0;
+    BH_CUDA_OK(cudaMemcpy(&err, c->comm_buf + c->pc.off_err, sizeof err, cudaMemcpyDeviceToHost));
+    if (err) {
+        set_error("peer-memory exchange timed out (a rank did not reach the step); results are invalid — re-attach the peers");
+        return BH_ERR_NCCL;
+    }
     return BH_OK;
 }
 
@@ -292,10 +312,15 @@ int enqueue_forces(bh_ctx* c, bool integrate, const double2* src_pos = nullptr, 
     g_pdl = c->pdl;
     bh_params p = c->p;
     if (list && p.reserved[0] == 0) p.reserved[0] = n_all >= kTwoBodiesPerLaneMin ? 2 : 1;
+    // Exact leaves read OTHER bodies' positions (the members of a shared cap leaf) during the walk; a fused in-place
+    // integrator in a warp that finished earlier would already have moved them.  Forces first, then one integrator
+    // launch over the same bodies — unless the step is out of place (reads the snapshot, writes pos / vel).
+    const bool split = integrate && (c->p.flags & BH_FLAG_EXACT_LEAVES) && !src_pos;
     launch_traverse(c->keys[c->sorted], c->idx[c->sorted], src_pos ? src_pos : c->pos, src_vel ? src_vel : c->vel,
                     c->pos, c->vel, c->acc, c->force, c->mass, c->d.n,
                     c->own_lo, c->own_hi, list, nullptr, list ? list_n : n_all, p, c->d, c->tree, c->consts, c->s.counters,
-                    integrate, c->stream);
+                    integrate && !split, c->stream);
+    if (split) launch_integrate(c->pos, c->vel, c->acc, c->force, c->mass, c->own_lo, c->own_hi, c->p.dt, c->stream);
     prof_mark(c, 4);
     return check_launch();
 }
@@ -366,7 +391,9 @@ int run_steps(bh_ctx* c, int nsteps, bool from_snapshot) {
     }
     BH_CUDA_OK(cudaEventRecord(c->ev1, c->stream));
     c->timed = true;
-    if (nsteps > 0) c->tree_valid = true;
+    // the fused integrator has moved the bodies: the tree on the device describes the positions BEFORE the last step
+    // (or the snapshot), so bh_compute_forces and the diagnostic getters must not pair it with the new positions
+    if (nsteps > 0) { c->tree_valid = false; c->tree_built = true; }
     return BH_OK;
 }
 
@@ -377,7 +404,7 @@ int copy_out2(bh_ctx* c, const double2* dev, double* host, bool gather_ranks) {
     if (gather_ranks && c->p.n_ranks > 1) BH_TRY(exchange_slices(c, (void*)dev, sizeof(double2)));
     BH_CUDA_OK(cudaMemcpyAsync(host, dev, sizeof(double2) * c->d.n, cudaMemcpyDeviceToHost, c->stream));
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
-    return BH_OK;
+    return peer_error(c);
 }
 
 // Diagnostic getters (keys, order, node table, dump) of a multi-rank context need the tree over
@@ -529,7 +556,8 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     { const char* e = getenv("BH_HOST_TRACE"); c->host_trace = e && e[0] == '1'; }
     { const char* e = getenv("BH_HOST_PIPELINE_MULTI"); c->host_pipeline_multi = e && e[0] == '1'; }
     { const char* e = getenv("BH_HOST_CHUNKS"); if (e && atoi(e) >= 1) c->host_chunks = std::min(atoi(e), kMaxHostChunks); }
-    if (p->device >= 0) c->device = p->device; else BH_CUDA_OK(cudaGetDevice(&c->device));
+    if (p->device >= 0) c->device = p->device;
+    else if ((e = cudaGetDevice(&c->device)) != cudaSuccess) { set_error("cudaGetDevice: %s", cudaGetErrorString(e)); delete c; return BH_ERR_CUDA; }
     if (c->device >= ndev) { set_error("device %d of %d", c->device, ndev); delete c; return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     compute_dims(c->p, c->d, c->sp);
@@ -671,6 +699,9 @@ int bh_comm_handle(bh_ctx* c, void* handle64) {
     DeviceGuard g(c->device);
     if (!c->comm_buf) {
         peer_comm_layout(c->pc, c->p.rank, c->p.n_ranks, c->d.ncells_finest, &c->comm_bytes);
+        {   const char* e = getenv("BH_PEER_TIMEOUT_MS");
+            const double ms = e && atof(e) > 0 ? atof(e) : 4000.0;
+            c->pc.timeout_ns = (unsigned long long)(ms * 1e6); }
         BH_CUDA_OK(cudaMalloc((void**)&c->comm_buf, c->comm_bytes));
         BH_CUDA_OK(cudaMemset(c->comm_buf, 0, c->comm_bytes));
         for (int r = 0; r < kMaxPeers; ++r) c->pc.peer_base[r] = nullptr;
@@ -687,6 +718,14 @@ int bh_attach_peers(bh_ctx* c, const void* handles, int32_t n_handles) {
     if (!c || !handles) { set_error("null argument"); return BH_ERR_INVALID; }
     if (n_handles != c->p.n_ranks || !c->comm_buf) { set_error("bh_attach_peers: call bh_comm_handle on every rank first and pass n_ranks handles"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
+    BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (c->p2p_ready) {                      // re-attach: drop the old mappings and graphs, clear the sticky error + flags
+        for (int r = 0; r < c->p.n_ranks; ++r)
+            if (r != c->p.rank && c->pc.peer_base[r]) { cudaIpcCloseMemHandle(c->pc.peer_base[r]); c->pc.peer_base[r] = nullptr; }
+        for (auto& gr : c->graph) if (gr) { cudaGraphExecDestroy(gr); gr = nullptr; }
+        c->p2p_ready = false;
+    }
+    BH_CUDA_OK(cudaMemset(c->comm_buf, 0, c->pc.off_rs));   // box slots, flags, error word, sequence number, tickets
     for (int r = 0; r < c->p.n_ranks; ++r) {
         if (r == c->p.rank) continue;
         cudaIpcMemHandle_t h;
@@ -711,6 +750,9 @@ int bh_set_bodies(bh_ctx* c, const double* pos, const double* vel, const double*
     BH_CUDA_OK(cudaMemcpyAsync(c->vel + lo, vel + 2 * lo, sizeof(double2) * cnt, cudaMemcpyHostToDevice, c->stream));
     BH_CUDA_OK(cudaMemcpyAsync(c->mass + lo, mass + lo, sizeof(double) * cnt, cudaMemcpyHostToDevice, c->stream));
     c->mass_complete = c->p.n_ranks == 1;
+    uint64_t zeros = 0;                      // overlaps the copies
+    for (int64_t i = lo; i < lo + cnt; ++i) zeros += mass[i] == 0.0;
+    c->zero_mass_bodies = zeros;
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
     BH_TRY(check_launch());
     c->bodies_set = true;
@@ -798,8 +840,8 @@ int bh_step_host(bh_ctx* c, const double* pos, const double* vel, const double* 
         BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_dl, 0));
         BH_CUDA_OK(cudaEventRecord(c->ev1, c->stream));
         BH_CUDA_OK(cudaStreamSynchronize(c->stream));
-        c->bodies_set = true; c->tree_valid = false; c->timed = true;
-        return BH_OK;
+        c->bodies_set = true; c->tree_valid = false; c->tree_built = true; c->timed = true;
+        return peer_error(c);
     }
     if (c->p.n_ranks > 1) {
         // multi-rank: every rank moves only its own slice both ways (out_pos gets this rank's slice; the
@@ -810,7 +852,7 @@ int bh_step_host(bh_ctx* c, const double* pos, const double* vel, const double* 
         const int64_t lo = c->own_lo, cnt = c->own_hi - c->own_lo;
         BH_CUDA_OK(cudaMemcpyAsync(out_pos + 2 * lo, c->pos + lo, sizeof(double2) * cnt, cudaMemcpyDeviceToHost, c->stream));
         BH_CUDA_OK(cudaStreamSynchronize(c->stream));
-        return BH_OK;
+        return peer_error(c);
     }
     if (c->profiling) {
         BH_TRY(bh_set_bodies(c, pos, vel, mass));
@@ -819,7 +861,8 @@ int bh_step_host(bh_ctx* c, const double* pos, const double* vel, const double* 
     }
     DeviceGuard g(c->device);
     const int64_t n = c->d.n;
-    const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(c->host_chunks, n / 4096));
+    // exact leaves read other bodies' positions during the walk: chunk k's integrator must not overlap chunk k+1's walk
+    const int nch = (c->p.flags & BH_FLAG_EXACT_LEAVES) ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(c->host_chunks, n / 4096));
     if (nch > 1 && !c->chunk_lists) {
         BH_TRY(dev_alloc(&c->chunk_lists, (size_t)n));
         BH_TRY(dev_alloc(&c->chunk_counts, (size_t)kMaxHostChunks * ((n + 255) / 256)));
@@ -862,7 +905,7 @@ int bh_step_host(bh_ctx* c, const double* pos, const double* vel, const double* 
     BH_CUDA_OK(cudaEventRecord(c->ev1, c->stream));
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
     trace_dump(c);
-    c->bodies_set = true; c->tree_valid = false; c->timed = true; c->tree_full = true;
+    c->bodies_set = true; c->tree_valid = false; c->tree_built = true; c->timed = true; c->tree_full = true;
     return BH_OK;
 }
 
@@ -870,12 +913,12 @@ int bh_build_tree(bh_ctx* c) {
     if (!c || !c->bodies_set) { set_error("bh_build_tree: no bodies"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     BH_TRY(enqueue_build(c));
-    c->tree_valid = true;
+    c->tree_valid = true; c->tree_built = true;
     return BH_OK;
 }
 
 int bh_compute_forces(bh_ctx* c) {
-    if (!c || !c->tree_valid) { set_error("bh_compute_forces: build the tree first"); return BH_ERR_INVALID; }
+    if (!c || !c->tree_valid) { set_error("bh_compute_forces: no tree for the current positions (call bh_build_tree; a step moves the bodies)"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     if (c->p.n_ranks > 1 && c->tree_full) BH_TRY(enqueue_build(c));   // diagnostic getters left a full tree behind
     cudaMemsetAsync(c->s.counters, 0, 4 * sizeof(unsigned long long), c->stream);
@@ -895,12 +938,7 @@ int bh_synchronize(bh_ctx* c) {
     if (!c) { set_error("null context"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
-    if (c->p2p_ready) {
-        uint32_t err = 0;
-        BH_CUDA_OK(cudaMemcpy(&err, c->comm_buf + c->pc.off_err, sizeof err, cudaMemcpyDeviceToHost));
-        if (err) { set_error("peer-memory exchange timed out (a rank did not reach the step)"); return BH_ERR_NCCL; }
-    }
-    return BH_OK;
+    return peer_error(c);
 }
 
 int bh_get_positions(bh_ctx* c, double* out) { if (!c) return BH_ERR_INVALID; return copy_out2(c, c->pos, out, true); }
@@ -909,7 +947,7 @@ int bh_get_accelerations(bh_ctx* c, double* out) { if (!c) return BH_ERR_INVALID
 int bh_get_forces(bh_ctx* c, double* out) { if (!c) return BH_ERR_INVALID; return copy_out2(c, c->force, out, true); }
 
 int bh_get_bounds(bh_ctx* c, double out4[4]) {
-    if (!c || !c->tree_valid) { set_error("bh_get_bounds: no tree built"); return BH_ERR_INVALID; }
+    if (!c || !c->tree_built) { set_error("bh_get_bounds: no tree built"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     StepConsts h;
     BH_CUDA_OK(cudaMemcpyAsync(&h, c->consts, sizeof h, cudaMemcpyDeviceToHost, c->stream));
@@ -928,7 +966,7 @@ static int fetch_sorted(bh_ctx* c, std::vector<uint32_t>& keys, std::vector<uint
 }
 
 int bh_get_body_keys(bh_ctx* c, uint32_t* out) {
-    if (!c || !out || !c->tree_valid) { set_error("bh_get_body_keys: no tree built"); return BH_ERR_INVALID; }
+    if (!c || !out || !c->tree_valid) { set_error("bh_get_body_keys: no tree for the current positions (call bh_build_tree; a step moves the bodies)"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     BH_TRY(ensure_full_tree(c));
     std::vector<uint32_t> keys, idx;
@@ -938,7 +976,7 @@ int bh_get_body_keys(bh_ctx* c, uint32_t* out) {
 }
 
 int bh_get_sorted_order(bh_ctx* c, uint32_t* out) {
-    if (!c || !out || !c->tree_valid) { set_error("bh_get_sorted_order: no tree built"); return BH_ERR_INVALID; }
+    if (!c || !out || !c->tree_valid) { set_error("bh_get_sorted_order: no tree for the current positions (call bh_build_tree; a step moves the bodies)"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     BH_TRY(ensure_full_tree(c));
     std::vector<uint32_t> keys, idx;
@@ -948,7 +986,7 @@ int bh_get_sorted_order(bh_ctx* c, uint32_t* out) {
 }
 
 int bh_get_tree_size(bh_ctx* c, int64_t* n_nodes) {
-    if (!c || !n_nodes || !c->tree_valid) { set_error("bh_get_tree_size: no tree built"); return BH_ERR_INVALID; }
+    if (!c || !n_nodes || !c->tree_built) { set_error("bh_get_tree_size: no tree built"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     unsigned long long v = 0;
     BH_CUDA_OK(cudaMemcpyAsync(&v, c->s.counters + 4, sizeof v, cudaMemcpyDeviceToHost, c->stream));
@@ -979,7 +1017,7 @@ static int fetch_host_tree(bh_ctx* c, HostTree& ht) {
 }
 
 int bh_get_tree(bh_ctx* c, double* out_rows, int64_t cap_rows, int64_t* n_rows) {
-    if (!c || !n_rows || !c->tree_valid) { set_error("bh_get_tree: no tree built"); return BH_ERR_INVALID; }
+    if (!c || !n_rows || !c->tree_valid) { set_error("bh_get_tree: no tree for the current positions (call bh_build_tree; a step moves the bodies)"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     BH_TRY(ensure_full_tree(c));
     HostTree ht;
@@ -989,7 +1027,7 @@ int bh_get_tree(bh_ctx* c, double* out_rows, int64_t cap_rows, int64_t* n_rows) 
 }
 
 int bh_dump_quadtree(bh_ctx* c, const char* path) {
-    if (!c || !path || !c->tree_valid) { set_error("bh_dump_quadtree: no tree built"); return BH_ERR_INVALID; }
+    if (!c || !path || !c->tree_valid) { set_error("bh_dump_quadtree: no tree for the current positions (call bh_build_tree; a step moves the bodies)"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     BH_TRY(ensure_full_tree(c));
     HostTree ht;
@@ -1008,6 +1046,7 @@ int bh_get_counters(bh_ctx* c, bh_counters* out) {
     memset(out, 0, sizeof *out);
     out->interactions = v[0]; out->visits = v[1]; out->opens = v[2]; out->warp_steps = v[3]; out->nodes = v[4];
     out->heavy_cells = heavy;
+    out->zero_mass_bodies = c->zero_mass_bodies;
     return BH_OK;
 }
 
@@ -1036,11 +1075,12 @@ int bh_last_step_ms(bh_ctx* c, float* ms) {
     DeviceGuard g(c->device);
     BH_CUDA_OK(cudaEventSynchronize(c->ev1));
     BH_CUDA_OK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
-    return BH_OK;
+    return peer_error(c);
 }
 
 int bh_direct_forces(bh_ctx* c, double* out, float* device_ms) {
     if (!c || !c->bodies_set) { set_error("bh_direct_forces: no bodies"); return BH_ERR_INVALID; }
+    if (c->p.n_ranks > 1) { set_error("bh_direct_forces: single-rank contexts only (a rank holds only its slice)"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     if (!c->packed) BH_TRY(dev_alloc(&c->packed, (size_t)c->d.n));
     BH_CUDA_OK(cudaEventRecord(c->ev0, c->stream));
@@ -1062,6 +1102,7 @@ int bh_generate(bh_ctx* c, int32_t kind, uint64_t seed) {
     BH_TRY(check_launch());
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
     c->mass_complete = c->p.n_ranks == 1;
+    c->zero_mass_bodies = 0;                 // log-uniform in [0.1, 0.5]
     c->bodies_set = true;
     c->tree_valid = false;
     return BH_OK;

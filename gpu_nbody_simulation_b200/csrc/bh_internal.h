@@ -99,6 +99,7 @@ struct PeerComm {
     uint8_t* peer_base[kMaxPeers];   // peer_base[rank] is this rank's own buffer
     size_t off_bbox, off_bbox_flag, off_rs_flag, off_ag_flag, off_err, off_rs, off_sums;
     uint64_t ncells, slice;          // finest cells, cells per rank slice
+    unsigned long long timeout_ns;   // wall-clock bound of every flag wait (env BH_PEER_TIMEOUT_MS, default 4000)
 };
 
 struct SortPlan {

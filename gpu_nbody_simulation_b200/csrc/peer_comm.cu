@@ -16,8 +16,8 @@
 //
 // Buffer reuse across steps is safe without double buffering: a rank can only run ahead of a peer
 // by the distance the data dependencies allow (it needs the peer's contribution of step s to finish
-// step s), see DESIGN.md §7.  Every spin has a clock64 timeout (~4 s) that raises an error flag
-// instead of hanging the GPU.
+// step s), see DESIGN.md §7.  Every spin has a wall-clock timeout (default 4 s, env BH_PEER_TIMEOUT_MS) that
+// raises a sticky error word instead of hanging the GPU (peer_comm.cuh: wait_flag).
 #include "peer_comm.cuh"
 
 namespace bh {
@@ -56,7 +56,7 @@ rs_reduce_ag_kernel(PeerComm pc, const uint32_t* __restrict__ seq_dev, uint32_t*
     const uint32_t seq = *seq_dev;
     if ((int)threadIdx.x < pc.n_ranks)
         wait_flag(reinterpret_cast<const uint32_t*>(own + pc.off_rs_flag) + threadIdx.x, seq,
-                  reinterpret_cast<uint32_t*>(own + pc.off_err));
+                  reinterpret_cast<uint32_t*>(own + pc.off_err), pc.timeout_ns);
     __syncthreads();
     const uint64_t c0 = (uint64_t)pc.rank * pc.slice;
     const uint64_t len = c0 >= pc.ncells ? 0 : (pc.ncells - c0 < pc.slice ? pc.ncells - c0 : pc.slice);
@@ -85,7 +85,7 @@ __global__ void wait_ag_kernel(PeerComm pc, const uint32_t* __restrict__ seq_dev
     uint8_t* own = pc.peer_base[pc.rank];
     if ((int)threadIdx.x < pc.n_ranks)
         wait_flag(reinterpret_cast<const uint32_t*>(own + pc.off_ag_flag) + threadIdx.x, *seq_dev,
-                  reinterpret_cast<uint32_t*>(own + pc.off_err));
+                  reinterpret_cast<uint32_t*>(own + pc.off_err), pc.timeout_ns);
 }
 
 }  // namespace

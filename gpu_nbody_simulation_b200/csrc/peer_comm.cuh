@@ -4,7 +4,11 @@
 
 namespace bh {
 
-constexpr long long kSpinTimeoutCycles = 8000000000ll;
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -14,11 +18,15 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// spin until *flag == seq; a clock64 timeout raises the error flag instead of hanging the GPU
-__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t seq, uint32_t* err) {
-    const long long t0 = clock64();
+// Spin until *flag == seq.  A wall-clock timeout (PeerComm::timeout_ns, env BH_PEER_TIMEOUT_MS, default 4 s) raises
+// the error word instead of hanging the GPU.  The error is STICKY: once set, later waits return at once (the
+// sequence protocol is desynchronised for good), and every host entry point that synchronises returns BH_ERR_NCCL
+// until the peers are re-attached (api.cu: peer_error).
+__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t seq, uint32_t* err, unsigned long long timeout_ns) {
+    if (*reinterpret_cast<volatile uint32_t*>(err)) return;
+    const unsigned long long t0 = global_timer_ns();
     while (ld_acquire_sys(flag) != seq) {
-        if (clock64() - t0 > kSpinTimeoutCycles) { atomicExch(err, 1u); break; }
+        if (global_timer_ns() - t0 > timeout_ns) { atomicExch(err, 1u); break; }
     }
 }
 
@@ -37,7 +45,7 @@ __device__ __forceinline__ void peer_bbox_exchange(const PeerComm& pc, uint32_t 
         st_release_sys(reinterpret_cast<uint32_t*>(pc.peer_base[tid] + pc.off_bbox_flag) + pc.rank, seq);
         uint8_t* own = pc.peer_base[pc.rank];
         wait_flag(reinterpret_cast<const uint32_t*>(own + pc.off_bbox_flag) + tid, seq,
-                  reinterpret_cast<uint32_t*>(own + pc.off_err));
+                  reinterpret_cast<uint32_t*>(own + pc.off_err), pc.timeout_ns);
     }
     __syncthreads();
     if (tid == 0) {

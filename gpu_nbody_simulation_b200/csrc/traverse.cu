@@ -69,8 +69,6 @@ struct TravArgs {
     const uint32_t* t_count;    // bodies per pyramid cell
     const uint32_t* t_first;    // sorted position of a cell's first body
     uint32_t finest_off;        // pyramid index of the first cap-level cell
-    // pair kernel, REMAP variants only: number of SMs (the grid is padded to a multiple of it)
-    uint32_t remap_cols;
 };
 
 __device__ __forceinline__ float approx_sqrt(float x) {
@@ -352,27 +350,19 @@ traverse_f32_kernel(const __grid_constant__ TravArgs a) {
 // (the SFU pipe, 16 lanes/clk/SM on B200, is this kernel's scarcest resource: ncu math_pipe_throttle);
 // relative error (eps/d)^2, i.e. < 1e-6 for separations above 1e-12 (eps = 1e-15).
 // EXACT_EPS = true (BH_FLAG_EXACT_EPS): MUFU.SQRT + MUFU.RCP, exact for any separation.
-// PREFETCH (experiment, bh_params.reserved[0] == 4; not yet measured): when a child is pushed, lane 0 touches the
-// 128-byte line of THAT child's children (prefetch.global.L1), one iteration or more before the child is
-// popped — ncu shows 37 % of the node fetches missing L1 (~300 cycles to L2) and long-scoreboard stalls.
-// Unlike the v7 experiment the stack discipline is untouched: +1 predicated instruction per child.
-// REMAP (experiment, reserved[0] == 5, or 6 together with PREFETCH; not yet measured): blocks that are resident on
-// the same SM at the same time should walk NEIGHBOURING bodies, so that the near-field cells one warp pulls into
-// L1 are hits for the others (ncu: 63 % L1 hit rate).  The hardware hands block b of the first wave to SM b mod
-// #SMs, so the body range is taken from the transposed index (b mod #SMs) * rows + b / #SMs; the grid is padded
-// to #SMs * rows blocks, surplus blocks see no bodies and leave after the root.
-// LEAVES (BH_FLAG_EXACT_LEAVES together with reserved[0] == 2; not yet run): the exact-leaves extension (see
+// LEAVES (BH_FLAG_EXACT_LEAVES together with reserved[0] == 2): the exact-leaves extension (see
 // traverse_f32_kernel) in the pair kernel — the member loop is packed across the lane's two bodies as well.
-template <bool INTEGRATE, bool EXACT_EPS, bool PREFETCH = false, bool REMAP = false, bool LEAVES = false>
+// Measured and removed in round 2 (warm A/B at N = 1M, 407 us baseline, profiles/r02_traverse_variants_ab.txt): an L1
+// prefetch of a pushed child's children (433 us), an SM-local block order (417 us), both (438 us), and a
+// software-pipelined pop + fetch of the next cell between the test and the force phase (608 us, 121 registers).
+template <bool INTEGRATE, bool EXACT_EPS, bool LEAVES = false>
 __global__ void __launch_bounds__(kTravThreads, kPairMinBlocks * (256 / kTravThreads))
 traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
     using SE = StackEntry<2>;
     __shared__ __align__(16) uint8_t s_stack[kTravWarps][kStackCap * SE::kBytes];
     pdl_entry();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t bid = blockIdx.x;
-    if constexpr (REMAP) bid = (blockIdx.x % a.remap_cols) * (gridDim.x / a.remap_cols) + blockIdx.x / a.remap_cols;
-    const int64_t warp_slot0 = ((int64_t)bid * kTravWarps + warp) * 64;
+    const int64_t warp_slot0 = ((int64_t)blockIdx.x * kTravWarps + warp) * 64;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&s_stack[warp][0]);
 
     uint32_t body[2], selfn[2];
@@ -513,168 +503,6 @@ traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
             const bool push = (m[0] | m[1]) != 0u;
             SE::store_if(push & (lane == 0), sp, base + q, m);
             sp += push ? SE::kBytes : 0u;
-            if constexpr (PREFETCH) {
-                asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %0, 0;\n @p prefetch.global.L1 [%1];\n}"
-                             ::"r"((uint32_t)(push & (lane == 0))), "l"(a.rec + (4u * (base + q) + 1u)) : "memory");
-            }
-        }
-    }
-    const float ax[2] = {accx.x, accx.y}, ay[2] = {accy.x, accy.y};
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        if (body[b] != 0xffffffffu) {
-            const double2 p = a.pos_in[body[b]];
-            const double mi = a.mass[body[b]];
-            finish_body<INTEGRATE>(a, body[b], p.x, p.y, mi, mi * (double)ax[b], mi * (double)ay[b]);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// EXPERIMENT (reserved[0] == 7; written after round 1's GPU budget was spent, not yet run): the pair kernel with
-// the stack pop and the node fetch of the NEXT iteration issued in the middle of the current one.
-//
-// ncu (profiles/r01_traverse_v8_pair_stall_hotspots.txt): 18 % of the stall samples are memory dependencies — the
-// first consumer of the node record behind the LDG.128 (10.6 %) and the pop's address chain LDS -> IMAD (8 %).
-// An iteration is therefore split into phase A (displacements, d2, acceptance tests, ballots, pushes — after it the
-// stack is final, so the next cell can be popped and its four records requested) and phase B (the force arithmetic of
-// the current children: 8 MUFU + 24 packed instructions that need nothing from memory), which runs while the next
-// records are in flight.  Same instruction count and the same per-body arithmetic as the pair kernel except that the
-// "no force" select acts on d2 (d2 := +inf  =>  rsqrt = 0  =>  exactly 0, also for a body's own leaf where d2 == 0)
-// instead of on the finished factor.  Costs registers: two record groups + the saved (dx, dy, d2, gm) of four children.
-// ------------------------------------------------------------------------------------------------
-#ifndef BH_PIPE_MIN_BLOCKS
-#define BH_PIPE_MIN_BLOCKS 5    // per 128 threads: <= 102 registers
-#endif
-template <bool INTEGRATE>
-__global__ void __launch_bounds__(kTravThreads, BH_PIPE_MIN_BLOCKS)
-traverse_f32_pair_pipe_kernel(const __grid_constant__ TravArgs a) {
-    using SE = StackEntry<2>;
-    __shared__ __align__(16) uint8_t s_stack[kTravWarps][kStackCap * SE::kBytes];
-    pdl_entry();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t warp_slot0 = ((int64_t)blockIdx.x * kTravWarps + warp) * 64;
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&s_stack[warp][0]);
-
-    uint32_t body[2], selfn[2];
-    float2 nxh, nyh, nxl, nyl;   // minus the scaled positions of body 0 (.x) and body 1 (.y), hi / lo floats
-    float2 accx = make_float2(0.f, 0.f), accy = make_float2(0.f, 0.f);
-    const float feps = a.consts->feps;
-    {
-        const double scale = a.consts->scale;
-        float t[2][4];
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            const int64_t slot = warp_slot0 + b * 32 + lane;
-            body[b] = 0xffffffffu; selfn[b] = 0xffffffffu;
-            double px = 0.0, py = 0.0;
-            if (slot < a.n_slots) {
-                uint32_t sp = a.own_list ? a.own_list[slot] : (uint32_t)slot;
-                body[b] = a.sidx[sp];
-                selfn[b] = a.self_node[body[b]];
-                double2 p = a.pos_in[body[b]];
-                px = p.x; py = p.y;
-            }
-            const double sx = px * scale, sy = py * scale;
-            const float xh = (float)sx, yh = (float)sy;
-            t[b][0] = -xh; t[b][1] = -yh;
-            t[b][2] = -(float)(sx - (double)xh); t[b][3] = -(float)(sy - (double)yh);
-        }
-        nxh = make_float2(t[0][0], t[1][0]); nyh = make_float2(t[0][1], t[1][1]);
-        nxl = make_float2(t[0][2], t[1][2]); nyl = make_float2(t[0][3], t[1][3]);
-    }
-    const float2 neg_eps2 = make_float2(-feps, -feps);
-    const float kInf = __int_as_float(0x7f800000);
-
-    struct Group {              // the four children of one popped cell
-        float4 A[4];            // chx chy clx cly
-        float2 B[4];            // gm thr
-        uint32_t base;          // pyramid index of child 0
-        float2 mxh, myh;        // minus the bodies' hi coordinates, or the far-away stand-in outside the cell's mask
-    };
-    struct Saved { float2 dx, dy, d2; float gm; };
-
-    // phase A for one child: displacement, d2, tests; returns the ballots of "opens"; d2 := +inf where no force is due
-    auto phase_a = [&](const float4 A, const float2 B, uint32_t idx, const float2 mxh, const float2 myh, Saved& s,
-                       uint32_t& m0, uint32_t& m1) {
-        s.dx = __fadd2_rn(__fadd2_rn(make_float2(A.x, A.x), mxh), __fadd2_rn(make_float2(A.z, A.z), nxl));
-        s.dy = __fadd2_rn(__fadd2_rn(make_float2(A.y, A.y), myh), __fadd2_rn(make_float2(A.w, A.w), nyl));
-        const float2 d2 = __ffma2_rn(s.dx, s.dx, __fmul2_rn(s.dy, s.dy));
-        s.gm = B.x;
-        // per body: accept = !(d2 <= thr); use = accept && not the body's own leaf; d2s = use ? d2 : +inf; ballot(!accept)
-        asm volatile("{\n .reg .pred pa, pu;\n setp.gtu.f32 pa, %2, %3;\n setp.ne.and.u32 pu, %4, %5, pa;\n"
-                     " selp.f32 %0, %2, %6, pu;\n vote.sync.ballot.b32 %1, !pa, 0xffffffff;\n}"
-                     : "=f"(s.d2.x), "=r"(m0) : "f"(d2.x), "f"(B.y), "r"(selfn[0]), "r"(idx), "f"(kInf));
-        asm volatile("{\n .reg .pred pa, pu;\n setp.gtu.f32 pa, %2, %3;\n setp.ne.and.u32 pu, %4, %5, pa;\n"
-                     " selp.f32 %0, %2, %6, pu;\n vote.sync.ballot.b32 %1, !pa, 0xffffffff;\n}"
-                     : "=f"(s.d2.y), "=r"(m1) : "f"(d2.y), "f"(B.y), "r"(selfn[1]), "r"(idx), "f"(kInf));
-    };
-    // phase B for one child: G M / (d2 (d + eps)) to first order in eps / d, accumulation (project.cu:765-772)
-    auto phase_b = [&](const Saved& s) {
-        const float2 inv = make_float2(approx_rsqrt(s.d2.x), approx_rsqrt(s.d2.y));
-        const float2 t = __fmul2_rn(inv, inv);
-        const float2 u = __ffma2_rn(neg_eps2, t, inv);
-        const float2 g = __fmul2_rn(make_float2(s.gm, s.gm), __fmul2_rn(t, u));
-        accx = __ffma2_rn(g, s.dx, accx);
-        accy = __ffma2_rn(g, s.dy, accy);
-    };
-    // pop the top of the stack into `g` and request its four records
-    uint32_t sp = sbase;
-    auto pop_and_fetch = [&](Group& g) {
-        sp -= SE::kBytes;
-        uint32_t node, pm[2];
-        __syncwarp();             // lane 0's stores of earlier steps are visible to the whole warp
-        SE::load(sp, node, pm);
-        __syncwarp();             // nobody overwrites the slot before everybody has read it
-        g.base = 4u * node + 1u;
-        const NodeRec* __restrict__ rp = a.rec + g.base;
-        const bool a0 = (pm[0] >> lane) & 1u, a1 = (pm[1] >> lane) & 1u;
-        g.mxh = make_float2(a0 ? nxh.x : kFarLane, a1 ? nxh.y : kFarLane);
-        g.myh = make_float2(a0 ? nyh.x : kFarLane, a1 ? nyh.y : kFarLane);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            g.A[q] = __ldg(reinterpret_cast<const float4*>(rp + q));
-            g.B[q] = __ldg(reinterpret_cast<const float2*>(rp + q) + 2);
-        }
-    };
-    // one iteration on `cur`; fetches the next cell into `nxt` between the phases; returns whether there is one
-    auto iterate = [&](const Group& cur, Group& nxt) -> bool {
-        Saved s[4];
-#pragma unroll
-        for (uint32_t q = 0; q < 4; ++q) {
-            uint32_t m[2];
-            phase_a(cur.A[q], cur.B[q], cur.base + q, cur.mxh, cur.myh, s[q], m[0], m[1]);
-            const bool push = (m[0] | m[1]) != 0u;
-            SE::store_if(push & (lane == 0), sp, cur.base + q, m);
-            sp += push ? SE::kBytes : 0u;
-        }
-        const bool more = sp != sbase;       // warp-uniform
-        if (more) pop_and_fetch(nxt);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) phase_b(s[q]);
-        return more;
-    };
-
-    {   // the root (project.cu:711-715 pushes node 0)
-        const float4 A = __ldg(reinterpret_cast<const float4*>(a.rec));
-        const float2 B = __ldg(reinterpret_cast<const float2*>(a.rec) + 2);
-        const bool l0 = body[0] != 0xffffffffu, l1 = body[1] != 0xffffffffu;
-        const float2 mxh = make_float2(l0 ? nxh.x : kFarLane, l1 ? nxh.y : kFarLane);
-        const float2 myh = make_float2(l0 ? nyh.x : kFarLane, l1 ? nyh.y : kFarLane);
-        Saved s;
-        uint32_t m[2];
-        phase_a(A, B, 0u, mxh, myh, s, m[0], m[1]);
-        const bool push = (m[0] | m[1]) != 0u;
-        SE::store_if(push & (lane == 0), sp, 0u, m);
-        sp += push ? SE::kBytes : 0u;
-        phase_b(s);
-    }
-    if (sp != sbase) {
-        Group g0, g1;
-        pop_and_fetch(g0);
-        while (true) {                        // ping-pong between the two record groups: no register copies
-            if (!iterate(g0, g1)) break;
-            if (!iterate(g1, g0)) break;
         }
     }
     const float ax[2] = {accx.x, accx.y}, ay[2] = {accy.x, accy.y};
@@ -922,14 +750,13 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
     a.n_slots = own_n;
     a.G = p.G; a.dt = p.dt; a.theta = p.theta; a.dist_eps = p.dist_eps;
     a.t_count = t.count; a.t_first = t.first; a.finest_off = (uint32_t)d.level_off[d.finest];
-    a.remap_cols = 0;
     if (own_n <= 0) return;
     const bool fp64 = p.flags & BH_FLAG_FP64_TRAVERSAL, count = p.flags & BH_FLAG_COUNTERS;
     // two bodies per lane halve the node traffic and the control overhead per body, but need >= ~400k
     // bodies to keep every SM's warp slots full (ncu: profiles/r01_traverse_v4_*)
     const bool exact_leaves = p.flags & BH_FLAG_EXACT_LEAVES;   // extension: generic 1-body-per-lane / FP64 kernels only
     const bool leaves_pair = exact_leaves && p.reserved[0] == 2 && !(p.flags & (BH_FLAG_COUNTERS | BH_FLAG_FP64_TRAVERSAL));
-    const int bpl = leaves_pair ? 2 : exact_leaves ? 1 : (p.reserved[0] == 1) ? 1 : (p.reserved[0] >= 2 && p.reserved[0] <= 7) ? 2 : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
+    const int bpl = leaves_pair ? 2 : exact_leaves ? 1 : (p.reserved[0] == 1) ? 1 : (p.reserved[0] == 2 || p.reserved[0] == 3) ? 2 : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
     // previous operation on the stream = tree_top_kernel (or a peer-exchange kernel; g_pdl is off there)
 #define BH_GO(K) launch_chain(K, dim3(blocks), dim3(kTravThreads), st, true, a)
     if (fp64) {
@@ -946,26 +773,11 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
 #define BH_TRAV(B, I, C) BH_GO((traverse_f32_kernel<B, I, C>))
         if (leaves_pair) {
             const bool exact = p.flags & BH_FLAG_EXACT_EPS;
-            if (integrate) { if (exact) BH_GO((traverse_f32_pair_kernel<true, true, false, false, true>)); else BH_GO((traverse_f32_pair_kernel<true, false, false, false, true>)); }
-            else { if (exact) BH_GO((traverse_f32_pair_kernel<false, true, false, false, true>)); else BH_GO((traverse_f32_pair_kernel<false, false, false, false, true>)); }
+            if (integrate) { if (exact) BH_GO((traverse_f32_pair_kernel<true, true, true>)); else BH_GO((traverse_f32_pair_kernel<true, false, true>)); }
+            else { if (exact) BH_GO((traverse_f32_pair_kernel<false, true, true>)); else BH_GO((traverse_f32_pair_kernel<false, false, true>)); }
         } else if (exact_leaves) {
             if (integrate) { if (count) BH_GO((traverse_f32_kernel<1, true, true, true>)); else BH_GO((traverse_f32_kernel<1, true, false, true>)); }
             else { if (count) BH_GO((traverse_f32_kernel<1, false, true, true>)); else BH_GO((traverse_f32_kernel<1, false, false, true>)); }
-        } else if (bpl == 2 && !count && p.reserved[0] == 4 && !(p.flags & BH_FLAG_EXACT_EPS)) {
-            if (integrate) BH_GO((traverse_f32_pair_kernel<true, false, true>)); else BH_GO((traverse_f32_pair_kernel<false, false, true>));
-        } else if (bpl == 2 && !count && p.reserved[0] == 7 && !(p.flags & BH_FLAG_EXACT_EPS)) {
-            if (integrate) BH_GO((traverse_f32_pair_pipe_kernel<true>)); else BH_GO((traverse_f32_pair_pipe_kernel<false>));
-        } else if (bpl == 2 && !count && (p.reserved[0] == 5 || p.reserved[0] == 6) && !(p.flags & BH_FLAG_EXACT_EPS)) {
-            int dev = 0, sms = 148;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            a.remap_cols = (uint32_t)sms;
-            blocks = (blocks + a.remap_cols - 1) / a.remap_cols * a.remap_cols;    // padded: surplus blocks find no bodies
-            if (p.reserved[0] == 5) {
-                if (integrate) BH_GO((traverse_f32_pair_kernel<true, false, false, true>)); else BH_GO((traverse_f32_pair_kernel<false, false, false, true>));
-            } else {
-                if (integrate) BH_GO((traverse_f32_pair_kernel<true, false, true, true>)); else BH_GO((traverse_f32_pair_kernel<false, false, true, true>));
-            }
         } else if (bpl == 2 && !count && p.reserved[0] != 3) {
             const bool exact = p.flags & BH_FLAG_EXACT_EPS;
             if (integrate) { if (exact) BH_GO((traverse_f32_pair_kernel<true, true>)); else BH_GO((traverse_f32_pair_kernel<true, false>)); }

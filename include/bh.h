@@ -72,9 +72,7 @@ typedef struct bh_params {
     int32_t rank;         /* 0 .. n_ranks-1 */
     int32_t n_ranks;      /* 1 = single GPU */
     int32_t reserved[4];  /* reserved[0]: traversal tuning knob: 0 = default, 1 / 2 = bodies per lane (2 = packed pair
-                             kernel), 3 = generic kernel with 2 bodies per lane; experiments, not yet measured: 4 = pair kernel + L1
-                             prefetch, 5 = pair kernel + SM-local block order, 6 = both, 7 = pair kernel with the next cell's
-                             pop + fetch issued between the test phase and the force phase */
+                             kernel), 3 = generic kernel with 2 bodies per lane */
 } bh_params;
 
 typedef struct bh_ctx bh_ctx; /* opaque; owns device memory, stream, CUDA graph, NCCL comm */
@@ -87,7 +85,11 @@ typedef struct bh_counters {
     uint64_t warp_steps;   /* warp-level traversal steps actually executed (parent expansions) */
     uint64_t nodes;        /* nodes of the reference-equivalent tree (quadtree.size()) */
     uint64_t heavy_cells;  /* finest cells summed with the parallel path (see exact_leaf_max) */
-    uint64_t reserved[2];
+    uint64_t zero_mass_bodies; /* bodies of mass exactly 0 in the last bh_set_bodies: the reference treats a leaf holding
+                                  one as EMPTY and overwrites it (project.cu:393-405), which makes its topology depend
+                                  on the insertion order; the engine counts every body (order-independent tree) and
+                                  reports the condition here instead of reproducing it */
+    uint64_t reserved[1];
 } bh_counters;
 
 /* Accumulated device time per phase in microseconds (cudaEvent, only while profiling is on). */

@@ -53,7 +53,26 @@ def test_reference_arm_prints_the_contract_line():
     assert out.returncode == 0 and out.stdout.strip() == ""
     line = bench.cpu_reference_run(65_536, 1, 0, budget_s=5.0)[1]
     assert line["kind"] in ("reference", "port") and line["cores"] == 1 and line["value"] > 0
+    assert line["n_bodies"] == 65_536 and line["steps_executed"] >= 1     # the body count timed is a structured field
     json.dumps(line)
+
+
+def test_both_arms_name_the_same_workload():
+    """The driver compares the two arms' config: the reference arm must run (and say it runs) the N = 1M workload."""
+    assert bench.workload_string(1_000_000, 1) == bench.workload_string(bench.BODIES_PER_GPU, 1, "disk", 10)
+    assert "N=1000000" in bench.workload_string(1_000_000, 1)
+    import inspect
+    src = inspect.getsource(bench.run_reference)
+    assert "workload_string(n, 1)" in src and "cpu_reference_run(n," in src and "n = BODIES_PER_GPU" in src
+
+
+def test_bracket_plan_and_workload_generator():
+    assert bench.bracket_plan(20) == 50 and bench.bracket_plan(200) == 5 and bench.bracket_plan(1000) == 5
+    import numpy as np
+    pos, vel, mass = bench.make_workload(1000)
+    pos2, _, _ = bench.make_workload(2000)
+    assert np.array_equal(pos, pos2[:1000])                      # body i is a pure function of (seed, i)
+    assert (np.hypot(pos[:, 0], pos[:, 1]) <= 0.1 + 1e-12).all() and mass.min() >= 0.1 and mass.max() <= 0.5
 
 
 def test_shell_scripts_parse():

@@ -1,10 +1,6 @@
 """Adversarial inputs through the CUDA path (tree bit-exact, FP64-mode forces, NaN pattern) — the same cases
 tests/test_oracle.py pins against the live reference on the CPU.
-
-NOT YET RUN ON A GPU (written after round 1's GPU budget was spent); skipped unless BH_TEST_UNVALIDATED=1.
 """
-import os
-
 import numpy as np
 import pytest
 
@@ -12,13 +8,11 @@ import oracle
 from gpu_nbody_simulation_b200 import Simulation
 from test_oracle import _edge_case
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("BH_TEST_UNVALIDATED") != "1",
-                                 reason="edge-case GPU tests not yet validated on a GPU (set BH_TEST_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("kind", ["collinear", "all_coincident", "two_far_clusters", "tiny_separations", "lattice",
-                                  "zero_and_tiny_masses"])
+                                  "tiny_masses"])
 def test_edge_case_tree_and_fp64_forces(kind):
     n = 1000
     pos, mass = _edge_case(kind, n, np.random.default_rng(len(kind)))
@@ -40,3 +34,22 @@ def test_edge_case_tree_and_fp64_forces(kind):
             assert err <= 1e-12, err
         c = sim.counters()
         assert c["interactions"] == cnt["interactions"] and c["visits"] == cnt["visits"] and c["opens"] == cnt["opens"]
+
+
+def test_exactly_zero_masses_are_detected_not_reproduced():
+    """Bodies of mass exactly 0 are "ghosts" in the reference: a leaf holding one counts as empty and is overwritten by
+    the next arrival (is_empty_leaf tests TOTAL_MASS == 0, project.cu:393-405), so its topology depends on the insertion
+    order.  The engine builds the order-independent tree (every body counts) and REPORTS the condition instead:
+    bh_counters.reserved[0] = number of zero-mass bodies handed over.  The reference's own generators
+    draw masses from [0.1, 0.5] (project.cu:30-31) and never produce one."""
+    n = 1000
+    pos, mass = _edge_case("zero_and_tiny_masses", n, np.random.default_rng(20))
+    with Simulation(n, fp64=True, counters=True) as sim:
+        sim.set_bodies(pos, np.zeros((n, 2)), mass)
+        sim.build_tree()
+        assert sim.counters()["zero_mass_bodies"] == int((mass == 0.0).sum()) > 0
+        assert np.array_equal(sim.bounds(), oracle.root_bounds(pos))
+        # the tree over the bodies as handed over is the reference's tree when the zero masses are made non-zero
+        mass2 = np.where(mass == 0.0, 1e-300, mass)
+        tree = oracle.Tree(pos, mass2)
+        assert sim.tree_size() == tree.size

@@ -1,12 +1,6 @@
 """GPU tests of BH_FLAG_EXACT_LEAVES (extension) against the oracle's
 bho_compute_forces_exact_leaves.
-
-NOT YET RUN ON A GPU: the kernels were written after round 1's GPU budget was spent (the SASS of every
-pre-existing kernel was verified to be byte-identical, so the default paths are untouched).  The tests
-are therefore skipped unless BH_TEST_UNVALIDATED=1; validating them is the first item of round 2.
 """
-import os
-
 import numpy as np
 import pytest
 
@@ -14,9 +8,7 @@ import oracle
 from conftest import golden_inputs
 from gpu_nbody_simulation_b200 import BhError, Simulation
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("BH_TEST_UNVALIDATED") != "1",
-                                 reason="exact-leaves kernels not yet validated on a GPU (set BH_TEST_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 def rel_rms(a, b):
@@ -86,3 +78,26 @@ def test_root_is_the_multi_body_leaf_and_whole_step():
 def test_flag_is_single_rank_only():
     with pytest.raises(BhError):
         Simulation(1000, exact_leaves=True, rank=0, n_ranks=2)
+
+
+@pytest.mark.parametrize("bodies_per_lane", [0, 2])
+def test_whole_step_many_blocks_reads_pre_step_positions(bodies_per_lane):
+    """The member loop reads OTHER bodies' positions; an in-place fused integrator in a block that finished earlier
+    would hand it post-step positions (a race that a few co-resident blocks never show).  bh_step therefore runs the
+    forces-only kernel followed by one integrator launch when the flag is set: 200 000 bodies = 1 500+ blocks."""
+    from gpu_nbody_simulation_b200 import initial_conditions as ic
+    n = 200_000
+    pos, vel, mass = ic.uniform_disk(n, seed=7, round6=False)
+    want, _ = oracle.Tree(pos, mass).forces_exact_leaves(nthreads=oracle.max_threads())
+    acc_w, vel_w, pos_w = oracle.update(want, mass, vel, pos, 1.0)
+    with Simulation(n, exact_leaves=True, bodies_per_lane=bodies_per_lane) as sim:
+        sim.set_bodies(pos, vel, mass)
+        sim.step(1)
+        ok = np.isfinite(want).all(axis=1)
+        assert rel_rms(sim.forces()[ok], want[ok]) <= 1e-5
+        assert rel_rms(sim.accelerations()[ok], acc_w[ok]) <= 1e-5
+        assert rel_rms(sim.positions()[ok] - pos[ok], pos_w[ok] - pos[ok]) <= 1e-5
+        f1 = sim.forces().copy()
+        sim.set_bodies(pos, vel, mass)
+        sim.step(1)                                  # deterministic: a race would differ from run to run
+        assert np.array_equal(sim.forces(), f1)

@@ -1,18 +1,13 @@
 """Device-side seeded generator (bh_generate, csrc/generate.cu) against its host twin.
 
-NOT YET RUN ON A GPU (written after round 1's GPU budget was spent); skipped unless BH_TEST_UNVALIDATED=1.
 The host twin, the Philox known answers and the file writers are tested on the CPU in tests/test_generate.py.
 """
-import os
-
 import numpy as np
 import pytest
 
 import gpu_nbody_simulation_b200 as bh
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("BH_TEST_UNVALIDATED") != "1",
-                                 reason="device generator not yet validated on a GPU (set BH_TEST_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("kind", ["uniform_square", "uniform_disk", "plummer_2d"])

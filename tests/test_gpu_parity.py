@@ -424,12 +424,6 @@ def test_traversal_variants_agree(shipped40k):
     out = {}
     variants = {"bpl1": dict(bodies_per_lane=1), "pair": dict(bodies_per_lane=2),
                 "pair_exact_eps": dict(bodies_per_lane=2, exact_eps=True), "bpl2_generic": dict(bodies_per_lane=3)}
-    import os
-    if os.environ.get("BH_TEST_UNVALIDATED") == "1":       # written after round 1's GPU budget was spent
-        variants["pair_prefetch"] = dict(bodies_per_lane=4)
-        variants["pair_sm_local"] = dict(bodies_per_lane=5)
-        variants["pair_sm_local_prefetch"] = dict(bodies_per_lane=6)
-        variants["pair_pipelined"] = dict(bodies_per_lane=7)
     for name, kw in variants.items():
         with build(pos, vel, mass, **kw) as sim:
             sim.compute_forces()

@@ -259,7 +259,7 @@ def _edge_case(kind, n, rng):
         pos = np.stack(np.meshgrid(g, g), axis=-1).reshape(-1, 2)[:n]
         if len(pos) < n:
             pos = np.concatenate([pos, pos[: n - len(pos)] + 0.5 / 32])
-    elif kind == "zero_and_tiny_masses":
+    elif kind in ("zero_and_tiny_masses", "tiny_masses"):
         pos = rng.uniform(-0.1, 0.1, (n, 2))
     else:
         raise KeyError(kind)
@@ -267,11 +267,14 @@ def _edge_case(kind, n, rng):
     if kind == "zero_and_tiny_masses":            # nodes with mass <= 1e-15 are skipped (project.cu:617)
         mass[::3] = 0.0
         mass[1::3] = 1e-16
+    if kind == "tiny_masses":                     # non-zero but <= mass_eps: ordinary bodies for the build, skipped by the walk
+        mass[::3] = 1e-300
+        mass[1::3] = 1e-16
     return np.ascontiguousarray(pos, dtype=np.float64), mass
 
 
 @pytest.mark.parametrize("kind", ["collinear", "all_coincident", "two_far_clusters", "tiny_separations", "lattice",
-                                  "zero_and_tiny_masses"])
+                                  "zero_and_tiny_masses", "tiny_masses"])
 def test_oracle_equals_the_live_reference_on_edge_cases(kind):
     n = 1000
     if not oracle.ref_available(n):

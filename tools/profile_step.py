@@ -20,6 +20,7 @@ ap.add_argument("--max-depth", type=int, default=10)
 ap.add_argument("--bpl", type=int, default=0)
 ap.add_argument("--exact-eps", action="store_true")
 ap.add_argument("--exact-leaves", action="store_true", help="BH_FLAG_EXACT_LEAVES (extension)")
+ap.add_argument("--warmup", type=int, default=0, help="untimed steps before the profiled ones (A/B timing: use >= 10)")
 a = ap.parse_args()
 gen = {"disk": ic.uniform_disk, "plummer": ic.plummer_2d, "square": ic.uniform_square}[a.dist]
 pos, vel, mass = gen(a.n, seed=12345, round6=False)
@@ -28,6 +29,10 @@ with bh.Simulation(a.n, graph=False, fp64=a.fp64, counters=a.counters, max_depth
     sim.set_bodies(pos, vel, mass)
     sim.snapshot()
     sim.set_profiling(True)
+    if a.warmup:
+        sim.step_from_snapshot(a.warmup)
+        sim.synchronize()
+        sim.reset_timers()
     sim.step_from_snapshot(a.steps)
     sim.synchronize()
     t = sim.timers()
