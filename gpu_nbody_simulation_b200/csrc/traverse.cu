@@ -517,6 +517,260 @@ traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// FP32 traversal, production variant from round 2 on ("list kernel"): group-classified walk.
+//
+// The pair kernel above lets all 32 lanes test the SAME node (every lane = two bodies), so a warp spends a full
+// 37-instruction evaluation on every node it touches — also on the ~13 % of nodes that every body of the warp opens
+// and on the ~70 % that every body of the (sub)group accepts, where the per-body test is a foregone conclusion.
+// Here the TEST is done lane-per-NODE first: one round pops up to 8 cells from the warp's stack and hands their 32
+// children to the 32 lanes; every lane compares its child with the bounding box of the warp's 64 bodies
+// (conservative bounds on the distance of any body of the warp to the node's centre of mass):
+//
+//     all bodies certainly accept   (dmin^2 > thr (1 + delta), or the node is a leaf)  -> class A: force only
+//     all bodies certainly open     (dmax^2 <= thr (1 - delta))                        -> class O: push, no arithmetic
+//     zero-mass / empty node        (the reference skips it, project.cu:731)           -> dropped
+//     anything else                                                                   -> class M: per-body test
+//
+// Class-A nodes go to a staging list in shared memory and are then applied to all 64 bodies with the force
+// arithmetic only (no test, no predicate, no ballot: 18 instructions per node for two bodies per lane; 22 when the
+// node carries a partial body mask).  Class-M nodes are evaluated exactly like in the pair kernel (per-body test +
+// force + ballot of the opening bodies).  A stack entry is (cell, mask of the bodies that opened it); the children
+// of a cell are only ever applied to the bodies of its mask, so EACH BODY STILL SEES EXACTLY THE NODE SET OF THE
+// REFERENCE'S PER-BODY DFS: the box test only short-cuts decisions that the per-body test
+// `!(d2 <= thr)` would take identically for every body of the mask (the margins cover the FP32 rounding of both).
+// A single-body leaf is the own leaf of at most one body of the warp: its bit is cleared from the entry's mask
+// (the reference's self test, project.cu:760) by the classifying lane, which knows the body's sorted position from
+// the record (`first`).
+// Measured at N = 1M (uniform disk, cap 10), per warp of 64 bodies: 505 nodes touched, of which 20 zero-mass, 61
+// class O, 348 class A (128 with the full mask), 76 class M (tools/classify_nodes.c reproduces these counts).
+// ------------------------------------------------------------------------------------------------
+constexpr int kListStackCap = 128;         // entries; rounds shrink to plain DFS (1 cell) above kListStackSoft
+constexpr int kListStackSoft = 88;
+constexpr float kListDelta = 1e-4f;        // relative safety band of the box test on d^2 (FP32 rounding is ~1e-6)
+
+template <bool INTEGRATE, bool EXACT_EPS>
+__global__ void __launch_bounds__(kTravThreads, kPairMinBlocks * (256 / kTravThreads))
+traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
+    __shared__ __align__(16) uint4 s_stack[kTravWarps][kListStackCap];   // (cell, mask0, mask1, -)
+    __shared__ __align__(16) float4 s_nodeA[kTravWarps][32];             // staged nodes: chx chy clx cly
+    __shared__ __align__(16) uint4 s_nodeB[kTravWarps][32];              //               gm thr mask0 mask1 (bit patterns)
+    __shared__ uint32_t s_cell[kTravWarps][32];                          //               pyramid index (class M only)
+    pdl_entry();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warp_slot0 = ((int64_t)blockIdx.x * kTravWarps + warp) * 64;
+    uint4* const stack = s_stack[warp];
+    float4* const nodeA = s_nodeA[warp];
+    uint4* const nodeB = s_nodeB[warp];
+    uint32_t* const cellv = s_cell[warp];
+
+    uint32_t body[2], selfn[2];
+    float2 nxh, nyh, nxl, nyl;   // minus the scaled positions of body 0 (.x) and body 1 (.y), hi / lo floats
+    float2 accx = make_float2(0.f, 0.f), accy = make_float2(0.f, 0.f);
+    const float feps = a.consts->feps;
+    {
+        const double scale = a.consts->scale;
+        float t[2][4];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int64_t slot = warp_slot0 + b * 32 + lane;
+            body[b] = 0xffffffffu; selfn[b] = 0xffffffffu;
+            double px = 0.0, py = 0.0;
+            if (slot < a.n_slots) {
+                uint32_t sp = a.own_list ? a.own_list[slot] : (uint32_t)slot;
+                body[b] = a.sidx[sp];
+                selfn[b] = a.self_node[body[b]];
+                double2 p = a.pos_in[body[b]];
+                px = p.x; py = p.y;
+            }
+            const double sx = px * scale, sy = py * scale;
+            const float xh = (float)sx, yh = (float)sy;
+            t[b][0] = -xh; t[b][1] = -yh;
+            t[b][2] = -(float)(sx - (double)xh); t[b][3] = -(float)(sy - (double)yh);
+        }
+        nxh = make_float2(t[0][0], t[1][0]); nyh = make_float2(t[0][1], t[1][1]);
+        nxl = make_float2(t[0][2], t[1][2]); nyl = make_float2(t[0][3], t[1][3]);
+    }
+    const bool l0 = body[0] != 0xffffffffu, l1 = body[1] != 0xffffffffu;
+    const uint32_t live0 = __ballot_sync(0xffffffffu, l0), live1 = __ballot_sync(0xffffffffu, l1);
+    if (live0 == 0u) return;                       // no body in this warp (slots are handed out in order)
+    // bounding box of the warp's bodies (hi floats of the scaled positions; the lo parts are inside the margin below)
+    float bx0, bx1, by0, by1;
+    {
+        const float inf = __int_as_float(0x7f800000);
+        float x0 = inf, x1 = -inf, y0 = inf, y1 = -inf;
+        if (l0) { x0 = x1 = -nxh.x; y0 = y1 = -nyh.x; }
+        if (l1) { x0 = fminf(x0, -nxh.y); x1 = fmaxf(x1, -nxh.y); y0 = fminf(y0, -nyh.y); y1 = fmaxf(y1, -nyh.y); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+            y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        }
+        bx0 = x0; bx1 = x1; by0 = y0; by1 = y1;
+    }
+    // |true coordinate - hi float| <= 2^-24 |hi|: absolute slack of the box test per axis (plus the node's own below)
+    const float slack_x = 1.2e-7f * fmaxf(fabsf(bx0), fabsf(bx1)), slack_y = 1.2e-7f * fmaxf(fabsf(by0), fabsf(by1));
+    const float2 eps2 = make_float2(feps, feps), neg_eps2 = make_float2(-feps, -feps);
+    (void)eps2; (void)neg_eps2;
+    const uint32_t lanebit = 1u << lane;
+
+    // G M / (d2 (d + eps)) for both bodies of the lane (project.cu:765-769); d2 == 0 -> NaN like the reference
+    auto gfactor = [&](const float2 d2, const float gm) -> float2 {
+        if constexpr (EXACT_EPS) {
+            const float2 w = __fmul2_rn(d2, __fadd2_rn(make_float2(approx_sqrt(d2.x), approx_sqrt(d2.y)), eps2));
+            return __fmul2_rn(make_float2(gm, gm), make_float2(approx_rcp(w.x), approx_rcp(w.y)));
+        } else {
+            const float2 inv = make_float2(approx_rsqrt(d2.x), approx_rsqrt(d2.y));
+            const float2 t = __fmul2_rn(inv, inv);                       // 1 / d2
+            const float2 u = __ffma2_rn(neg_eps2, t, inv);               // 1 / (d + eps) ~= 1/d - eps/d2
+            return __fmul2_rn(make_float2(gm, gm), __fmul2_rn(t, u));
+        }
+    };
+    // class A, full mask: force arithmetic only
+    auto apply_full = [&](const float4 A, const float gm) {
+        const float2 dx = __fadd2_rn(__fadd2_rn(make_float2(A.x, A.x), nxh), __fadd2_rn(make_float2(A.z, A.z), nxl));
+        const float2 dy = __fadd2_rn(__fadd2_rn(make_float2(A.y, A.y), nyh), __fadd2_rn(make_float2(A.w, A.w), nyl));
+        const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+        const float2 g = gfactor(d2, gm);
+        accx = __ffma2_rn(g, dx, accx);
+        accy = __ffma2_rn(g, dy, accy);
+    };
+    // class A, partial mask (or a body's own leaf cleared from it): the select comes last — a body's own leaf has d2 == 0
+    auto apply_masked = [&](const float4 A, const float gm, const uint32_t m0, const uint32_t m1) {
+        const float2 dx = __fadd2_rn(__fadd2_rn(make_float2(A.x, A.x), nxh), __fadd2_rn(make_float2(A.z, A.z), nxl));
+        const float2 dy = __fadd2_rn(__fadd2_rn(make_float2(A.y, A.y), nyh), __fadd2_rn(make_float2(A.w, A.w), nyl));
+        const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+        const float2 g = gfactor(d2, gm);
+        const float2 f = make_float2((m0 & lanebit) ? g.x : 0.f, (m1 & lanebit) ? g.y : 0.f);
+        accx = __ffma2_rn(f, dx, accx);
+        accy = __ffma2_rn(f, dy, accy);
+    };
+    // class M: the per-body test of the pair kernel; returns the ballots of the bodies that open the node
+    auto eval_mixed = [&](const float4 A, const float gm, const float thr, const uint32_t idx, const uint32_t pm0,
+                          const uint32_t pm1, uint32_t& m0, uint32_t& m1) {
+        const bool a0 = pm0 & lanebit, a1 = pm1 & lanebit;
+        const float2 mxh = make_float2(a0 ? nxh.x : kFarLane, a1 ? nxh.y : kFarLane);
+        const float2 myh = make_float2(a0 ? nyh.x : kFarLane, a1 ? nyh.y : kFarLane);
+        const float2 dx = __fadd2_rn(__fadd2_rn(make_float2(A.x, A.x), mxh), __fadd2_rn(make_float2(A.z, A.z), nxl));
+        const float2 dy = __fadd2_rn(__fadd2_rn(make_float2(A.y, A.y), myh), __fadd2_rn(make_float2(A.w, A.w), nyl));
+        const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+        const float2 g = gfactor(d2, gm);
+        float2 f;
+        // per body: accept = !(d2 <= thr); use = accept && not the body's own leaf; f = use ? g : 0; ballot(!accept)
+        asm volatile("{\n .reg .pred pa, pu;\n setp.gtu.f32 pa, %2, %3;\n setp.ne.and.u32 pu, %4, %5, pa;\n"
+                     " selp.f32 %0, %6, 0f00000000, pu;\n vote.sync.ballot.b32 %1, !pa, 0xffffffff;\n}"
+                     : "=f"(f.x), "=r"(m0) : "f"(d2.x), "f"(thr), "r"(selfn[0]), "r"(idx), "f"(g.x));
+        asm volatile("{\n .reg .pred pa, pu;\n setp.gtu.f32 pa, %2, %3;\n setp.ne.and.u32 pu, %4, %5, pa;\n"
+                     " selp.f32 %0, %6, 0f00000000, pu;\n vote.sync.ballot.b32 %1, !pa, 0xffffffff;\n}"
+                     : "=f"(f.y), "=r"(m1) : "f"(d2.y), "f"(thr), "r"(selfn[1]), "r"(idx), "f"(g.y));
+        accx = __ffma2_rn(f, dx, accx);
+        accy = __ffma2_rn(f, dy, accy);
+    };
+
+    int top = 0;
+    {   // the root (project.cu:711-715 pushes node 0): per-body test
+        const float4 A = __ldg(reinterpret_cast<const float4*>(a.rec));
+        const float2 B = __ldg(reinterpret_cast<const float2*>(a.rec) + 2);
+        uint32_t m0, m1;
+        eval_mixed(A, B.x, B.y, 0u, live0, live1, m0, m1);
+        if ((m0 | m1) != 0u) {
+            if (lane == 0) stack[0] = make_uint4(0u, m0, m1, 0u);
+            top = 1;
+        }
+        __syncwarp();
+    }
+    const uint32_t lanemask_lt = lanebit - 1u;
+    while (top > 0) {
+        // ---- pop up to 8 cells; lane l takes child (l & 3) of popped cell (l >> 2) ----
+        int k = (kListStackSoft - top) / 3;
+        k = k < 1 ? 1 : (k > 8 ? 8 : k);
+        k = k > top ? top : k;
+        const int e = lane >> 2;
+        const bool valid = e < k;
+        uint4 ent = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) ent = stack[top - 1 - e];
+        top -= k;
+        const uint32_t child = 4u * ent.x + 1u + (uint32_t)(lane & 3);
+        float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint4 Bq = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) {
+            A = __ldg(reinterpret_cast<const float4*>(a.rec + child));
+            Bq = __ldg(reinterpret_cast<const uint4*>(a.rec + child) + 1);       // gm thr count first
+        }
+        const float gm = __uint_as_float(Bq.x), thr = __uint_as_float(Bq.y);
+        uint32_t pm0 = ent.y, pm1 = ent.z;
+        // ---- classify: 0 dropped, 1 A full mask, 2 A partial mask, 3 O, 4 M ----
+        int cls = 0;
+        if (valid && gm != 0.f) {
+            if (thr < 0.f) {                                  // a leaf: everybody in the mask accepts it
+                cls = 1;
+                if (Bq.z == 1u) {                             // single body: it may be one of ours -> the self test
+                    if (a.own_list) cls = 4;                  // slots are indirect: let the per-body test decide
+                    else {
+                        const int64_t slot = (int64_t)Bq.w - warp_slot0;
+                        if (slot >= 0 && slot < 64) { if (slot < 32) pm0 &= ~(1u << slot); else pm1 &= ~(1u << (slot - 32)); }
+                    }
+                }
+            } else {
+                const float ex = slack_x + 1.2e-7f * fabsf(A.x), ey = slack_y + 1.2e-7f * fabsf(A.y);
+                const float nx = fmaxf(fmaxf(bx0 - A.x, A.x - bx1) - ex, 0.f), ny = fmaxf(fmaxf(by0 - A.y, A.y - by1) - ey, 0.f);
+                const float fx = fmaxf(A.x - bx0, bx1 - A.x) + ex, fy = fmaxf(A.y - by0, by1 - A.y) + ey;
+                const float dmin2 = fmaf(nx, nx, ny * ny), dmax2 = fmaf(fx, fx, fy * fy);
+                cls = (dmin2 > thr * (1.f + kListDelta)) ? 1 : (dmax2 <= thr * (1.f - kListDelta)) ? 3 : 4;
+            }
+            if (cls == 1 && (pm0 != live0 || pm1 != live1)) cls = 2;
+            if ((pm0 | pm1) == 0u) cls = 0;                   // (a lone body's own leaf)
+        }
+        const uint32_t bF = __ballot_sync(0xffffffffu, cls == 1), bP = __ballot_sync(0xffffffffu, cls == 2);
+        const uint32_t bO = __ballot_sync(0xffffffffu, cls == 3), bM = __ballot_sync(0xffffffffu, cls == 4);
+        const int nF = __popc(bF), nP = __popc(bP), nM = __popc(bM);
+        if (cls == 3) stack[top + __popc(bO & lanemask_lt)] = make_uint4(child, pm0, pm1, 0u);
+        top += __popc(bO);
+        if (cls == 1 || cls == 2 || cls == 4) {
+            const int at = cls == 1 ? __popc(bF & lanemask_lt) : cls == 2 ? nF + __popc(bP & lanemask_lt)
+                                                                         : nF + nP + __popc(bM & lanemask_lt);
+            nodeA[at] = A;
+            nodeB[at] = make_uint4(Bq.x, Bq.y, pm0, pm1);
+            cellv[at] = child;
+        }
+        __syncwarp();
+        // ---- apply the staged nodes to the warp's 64 bodies ----
+        int i = 0;
+#pragma unroll 2
+        for (; i < nF; ++i) {
+            const float4 SA = nodeA[i];
+            apply_full(SA, __uint_as_float(nodeB[i].x));
+        }
+#pragma unroll 2
+        for (; i < nF + nP; ++i) {
+            const float4 SA = nodeA[i];
+            const uint4 SB = nodeB[i];
+            apply_masked(SA, __uint_as_float(SB.x), SB.z, SB.w);
+        }
+        for (; i < nF + nP + nM; ++i) {
+            const float4 SA = nodeA[i];
+            const uint4 SB = nodeB[i];
+            const uint32_t c = cellv[i];
+            uint32_t m0, m1;
+            eval_mixed(SA, __uint_as_float(SB.x), __uint_as_float(SB.y), c, SB.z, SB.w, m0, m1);
+            if ((m0 | m1) != 0u) {
+                if (lane == 0) stack[top] = make_uint4(c, m0, m1, 0u);
+                ++top;
+            }
+        }
+        __syncwarp();
+    }
+    const float ax[2] = {accx.x, accx.y}, ay[2] = {accy.x, accy.y};
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        if (body[b] != 0xffffffffu) {
+            const double2 p = a.pos_in[body[b]];
+            const double mi = a.mass[body[b]];
+            finish_body<INTEGRATE>(a, body[b], p.x, p.y, mi, mi * (double)ax[b], mi * (double)ay[b]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP64 verification traversal: the reference's expressions, one body per lane
 // ------------------------------------------------------------------------------------------------
 template <bool INTEGRATE, bool COUNT, bool EXACT = false>
@@ -756,7 +1010,7 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
     // bodies to keep every SM's warp slots full (ncu: profiles/r01_traverse_v4_*)
     const bool exact_leaves = p.flags & BH_FLAG_EXACT_LEAVES;   // extension: generic 1-body-per-lane / FP64 kernels only
     const bool leaves_pair = exact_leaves && p.reserved[0] == 2 && !(p.flags & (BH_FLAG_COUNTERS | BH_FLAG_FP64_TRAVERSAL));
-    const int bpl = leaves_pair ? 2 : exact_leaves ? 1 : (p.reserved[0] == 1) ? 1 : (p.reserved[0] == 2 || p.reserved[0] == 3) ? 2 : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
+    const int bpl = leaves_pair ? 2 : exact_leaves ? 1 : (p.reserved[0] == 1) ? 1 : (p.reserved[0] == 2 || p.reserved[0] == 3 || p.reserved[0] == 8) ? 2 : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
     // previous operation on the stream = tree_top_kernel (or a peer-exchange kernel; g_pdl is off there)
 #define BH_GO(K) launch_chain(K, dim3(blocks), dim3(kTravThreads), st, true, a)
     if (fp64) {
@@ -778,6 +1032,10 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
         } else if (exact_leaves) {
             if (integrate) { if (count) BH_GO((traverse_f32_kernel<1, true, true, true>)); else BH_GO((traverse_f32_kernel<1, true, false, true>)); }
             else { if (count) BH_GO((traverse_f32_kernel<1, false, true, true>)); else BH_GO((traverse_f32_kernel<1, false, false, true>)); }
+        } else if (bpl == 2 && !count && (p.reserved[0] == 0 || p.reserved[0] == 8)) {
+            const bool exact = p.flags & BH_FLAG_EXACT_EPS;
+            if (integrate) { if (exact) BH_GO((traverse_f32_list_kernel<true, true>)); else BH_GO((traverse_f32_list_kernel<true, false>)); }
+            else { if (exact) BH_GO((traverse_f32_list_kernel<false, true>)); else BH_GO((traverse_f32_list_kernel<false, false>)); }
         } else if (bpl == 2 && !count && p.reserved[0] != 3) {
             const bool exact = p.flags & BH_FLAG_EXACT_EPS;
             if (integrate) { if (exact) BH_GO((traverse_f32_pair_kernel<true, true>)); else BH_GO((traverse_f32_pair_kernel<true, false>)); }

@@ -146,6 +146,30 @@ def test_forces_fp32_mode_within_1e5(name):
         assert rel_rms(f, want) <= 1e-5      # north_star: 1e-5 relative RMS, FP32
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_forces_list_kernel_within_1e5(name):
+    """The production kernel above 500k bodies (group-classified walk, traverse_f32_list_kernel), forced here on the
+    small golden cases: root-only trees, coincident clusters, ragged last warps, and — below — whole steps."""
+    pos, vel, mass, g = golden_inputs(name)
+    want = g["forces0"]
+    for kw in (dict(), dict(exact_eps=True)):
+        with build(pos, vel, mass, bodies_per_lane=8, **kw) as sim:
+            sim.compute_forces()
+            f = sim.forces()
+            if name == "tiny_2_coincident":      # documented limit of the FP32 mode, see above
+                assert f.shape == want.shape
+                continue
+            assert np.array_equal(np.isnan(f), np.isnan(want))
+            assert rel_rms(f, want) <= 1e-5
+    if name != "tiny_2_coincident":
+        with Simulation(len(mass), bodies_per_lane=8) as a, Simulation(len(mass), bodies_per_lane=1) as b:
+            a.set_bodies(pos, vel, mass); a.step(1)          # fused integrator epilogue
+            b.set_bodies(pos, vel, mass); b.step(1)
+            ok = np.isfinite(b.positions()).all(axis=1)
+            assert np.array_equal(np.isfinite(a.positions()).all(axis=1), ok)
+            assert rel_rms(a.positions()[ok], b.positions()[ok]) <= 2e-6
+
+
 def test_forces_shipped_40000_both_modes(shipped40k):
     g = shipped40k
     pos, vel, mass = g["pos"], g["vel"], g["mass"]
@@ -423,7 +447,8 @@ def test_traversal_variants_agree(shipped40k):
     want, _ = oracle.Tree(pos, mass).forces(nthreads=oracle.max_threads())
     out = {}
     variants = {"bpl1": dict(bodies_per_lane=1), "pair": dict(bodies_per_lane=2),
-                "pair_exact_eps": dict(bodies_per_lane=2, exact_eps=True), "bpl2_generic": dict(bodies_per_lane=3)}
+                "pair_exact_eps": dict(bodies_per_lane=2, exact_eps=True), "bpl2_generic": dict(bodies_per_lane=3),
+                "list": dict(bodies_per_lane=8), "list_exact_eps": dict(bodies_per_lane=8, exact_eps=True)}
     for name, kw in variants.items():
         with build(pos, vel, mass, **kw) as sim:
             sim.compute_forces()
