@@ -517,7 +517,7 @@ traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// FP32 traversal, production variant from round 2 on ("list kernel"): group-classified walk.
+// FP32 traversal, production variant from round 2 on ("list kernel"): group-classified walk in a warp-local frame.
 //
 // The pair kernel above lets all 32 lanes test the SAME node (every lane = two bodies), so a warp spends a full
 // 37-instruction evaluation on every node it touches — also on the ~13 % of nodes that every body of the warp opens
@@ -531,30 +531,53 @@ traverse_f32_pair_kernel(const __grid_constant__ TravArgs a) {
 //     zero-mass / empty node        (the reference skips it, project.cu:731)           -> dropped
 //     anything else                                                                   -> class M: per-body test
 //
-// Class-A nodes go to a staging list in shared memory and are then applied to all 64 bodies with the force
-// arithmetic only (no test, no predicate, no ballot: 18 instructions per node for two bodies per lane; 22 when the
-// node carries a partial body mask).  Class-M nodes are evaluated exactly like in the pair kernel (per-body test +
-// force + ballot of the opening bodies).  A stack entry is (cell, mask of the bodies that opened it); the children
-// of a cell are only ever applied to the bodies of its mask, so EACH BODY STILL SEES EXACTLY THE NODE SET OF THE
-// REFERENCE'S PER-BODY DFS: the box test only short-cuts decisions that the per-body test
+// Class-A nodes go to staging lists in shared memory and are then applied to all 64 bodies with the force
+// arithmetic only (no test, no predicate, no ballot).  Class-M nodes are evaluated like in the pair kernel (per-body
+// test + force + ballot of the opening bodies).  A stack entry is (cell, mask of the bodies that opened it); the
+// children of a cell are only ever applied to the bodies of its mask, so EACH BODY STILL SEES EXACTLY THE NODE SET
+// OF THE REFERENCE'S PER-BODY DFS: the box test only short-cuts decisions that the per-body test
 // `!(d2 <= thr)` would take identically for every body of the mask (the margins cover the FP32 rounding of both).
 // A single-body leaf is the own leaf of at most one body of the warp: its bit is cleared from the entry's mask
 // (the reference's self test, project.cu:760) by the classifying lane, which knows the body's sorted position from
 // the record (`first`).
+//
+// Warp-local frame.  All coordinates are taken relative to the centre O of the warp's bounding box (FP64
+// subtraction by the classifying lane / once per body), so a class-A node that is FAR from the box (dmin^2 >=
+// diag^2 / 64, 85 % of them) needs no double-float arithmetic at all: fl(C - O) - fl(x - O) has a relative error of
+// at most 2^-24 (2 + 2 diag / d) <= 1.1e-6 per interaction, and the displacement is ONE packed add per coordinate
+// instead of three.  NEAR class-A nodes and class-M nodes keep the double-float displacement (2^-48 of the frame),
+// which the dominant close interactions need.
 // Measured at N = 1M (uniform disk, cap 10), per warp of 64 bodies: 505 nodes touched, of which 20 zero-mass, 61
-// class O, 348 class A (128 with the full mask), 76 class M (tools/classify_nodes.c reproduces these counts).
+// class O, 348 class A (about 290 far), 76 class M (tools/classify_nodes.c reproduces these counts on the CPU).
 // ------------------------------------------------------------------------------------------------
 constexpr int kListStackCap = 128;         // entries; rounds shrink to plain DFS (1 cell) above kListStackSoft
 constexpr int kListStackSoft = 88;
 constexpr float kListDelta = 1e-4f;        // relative safety band of the box test on d^2 (FP32 rounding is ~1e-6)
 
+struct ListWarpConsts {                    // per warp, written once, read by every round's classification
+    float oxh, oxl, oyh, oyl;              // frame origin (scaled units), exact as hi + lo
+    float bx0, bx1, by0, by1;              // the warp's bounding box in the local frame
+    float slack, far2;                     // absolute slack of the box test; diag^2 / 64
+    uint32_t live0, live1;                 // lanes whose body 0 / body 1 exists
+};
+
+__device__ __forceinline__ void sts_v4_if(bool doit, uint4* p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %0, 0;\n @p st.shared.v4.u32 [%1], {%2, %3, %4, %5};\n}" ::"r"((uint32_t)doit),
+                 "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+#ifndef BH_LIST_MIN_BLOCKS
+#define BH_LIST_MIN_BLOCKS 7    // per 128 threads: <= 72 registers, 28 warps per SM
+#endif
 template <bool INTEGRATE, bool EXACT_EPS>
-__global__ void __launch_bounds__(kTravThreads, kPairMinBlocks * (256 / kTravThreads))
+__global__ void __launch_bounds__(kTravThreads, BH_LIST_MIN_BLOCKS)
 traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
     __shared__ __align__(16) uint4 s_stack[kTravWarps][kListStackCap];   // (cell, mask0, mask1, -)
-    __shared__ __align__(16) float4 s_nodeA[kTravWarps][32];             // staged nodes: chx chy clx cly
-    __shared__ __align__(16) uint4 s_nodeB[kTravWarps][32];              //               gm thr mask0 mask1 (bit patterns)
-    __shared__ uint32_t s_cell[kTravWarps][32];                          //               pyramid index (class M only)
+    __shared__ __align__(16) float4 s_nodeA[kTravWarps][32];             // staged nodes, local frame: far class A: cx cy gm - ;
+                                                                         //   near class A / class M: chx chy clx cly
+    __shared__ __align__(16) uint4 s_nodeB[kTravWarps][32];              // gm thr mask0 mask1 (bit patterns)
+    __shared__ uint32_t s_cell[kTravWarps][32];                          //              pyramid index (class M only)
+    __shared__ __align__(16) ListWarpConsts s_wc[kTravWarps];
     pdl_entry();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t warp_slot0 = ((int64_t)blockIdx.x * kTravWarps + warp) * 64;
@@ -564,12 +587,12 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
     uint32_t* const cellv = s_cell[warp];
 
     uint32_t body[2], selfn[2];
-    float2 nxh, nyh, nxl, nyl;   // minus the scaled positions of body 0 (.x) and body 1 (.y), hi / lo floats
+    float2 nxh, nyh, nxl, nyl;   // minus the local-frame positions of body 0 (.x) and body 1 (.y), hi / lo floats
     float2 accx = make_float2(0.f, 0.f), accy = make_float2(0.f, 0.f);
     const float feps = a.consts->feps;
     {
         const double scale = a.consts->scale;
-        float t[2][4];
+        double sx[2], sy[2];
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
             const int64_t slot = warp_slot0 + b * 32 + lane;
@@ -582,33 +605,48 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
                 double2 p = a.pos_in[body[b]];
                 px = p.x; py = p.y;
             }
-            const double sx = px * scale, sy = py * scale;
-            const float xh = (float)sx, yh = (float)sy;
-            t[b][0] = -xh; t[b][1] = -yh;
-            t[b][2] = -(float)(sx - (double)xh); t[b][3] = -(float)(sy - (double)yh);
+            sx[b] = px * scale; sy[b] = py * scale;
         }
-        nxh = make_float2(t[0][0], t[1][0]); nyh = make_float2(t[0][1], t[1][1]);
-        nxl = make_float2(t[0][2], t[1][2]); nyl = make_float2(t[0][3], t[1][3]);
-    }
-    const bool l0 = body[0] != 0xffffffffu, l1 = body[1] != 0xffffffffu;
-    const uint32_t live0 = __ballot_sync(0xffffffffu, l0), live1 = __ballot_sync(0xffffffffu, l1);
-    if (live0 == 0u) return;                       // no body in this warp (slots are handed out in order)
-    // bounding box of the warp's bodies (hi floats of the scaled positions; the lo parts are inside the margin below)
-    float bx0, bx1, by0, by1;
-    {
+        const bool l0 = body[0] != 0xffffffffu, l1 = body[1] != 0xffffffffu;
+        const uint32_t live0 = __ballot_sync(0xffffffffu, l0), live1 = __ballot_sync(0xffffffffu, l1);
+        if (live0 == 0u) return;                       // no body in this warp (slots are handed out in order)
+        // bounding box of the warp's bodies (floats rounded outwards by the slack below), frame origin = its centre
         const float inf = __int_as_float(0x7f800000);
         float x0 = inf, x1 = -inf, y0 = inf, y1 = -inf;
-        if (l0) { x0 = x1 = -nxh.x; y0 = y1 = -nyh.x; }
-        if (l1) { x0 = fminf(x0, -nxh.y); x1 = fmaxf(x1, -nxh.y); y0 = fminf(y0, -nyh.y); y1 = fmaxf(y1, -nyh.y); }
+        if (l0) { x0 = x1 = (float)sx[0]; y0 = y1 = (float)sy[0]; }
+        if (l1) { x0 = fminf(x0, (float)sx[1]); x1 = fmaxf(x1, (float)sx[1]); y0 = fminf(y0, (float)sy[1]); y1 = fmaxf(y1, (float)sy[1]); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
             y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
         }
-        bx0 = x0; bx1 = x1; by0 = y0; by1 = y1;
+        const double ox = 0.5 * ((double)x0 + (double)x1), oy = 0.5 * ((double)y0 + (double)y1);
+        float t[2][4];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const double rx = sx[b] - ox, ry = sy[b] - oy;
+            const float xh = (float)rx, yh = (float)ry;
+            t[b][0] = -xh; t[b][1] = -yh;
+            t[b][2] = -(float)(rx - (double)xh); t[b][3] = -(float)(ry - (double)yh);
+        }
+        nxh = make_float2(t[0][0], t[1][0]); nyh = make_float2(t[0][1], t[1][1]);
+        nxl = make_float2(t[0][2], t[1][2]); nyl = make_float2(t[0][3], t[1][3]);
+        if (lane == 0) {
+            ListWarpConsts wc;
+            wc.oxh = (float)ox; wc.oxl = (float)(ox - (double)wc.oxh);     // midpoint of two floats: hi + lo is exact
+            wc.oyh = (float)oy; wc.oyl = (float)(oy - (double)wc.oyh);
+            // the float box was formed from rounded coordinates: |true - float| <= 2^-24 |coordinate|
+            const float mag = fmaxf(fmaxf(fabsf(x0), fabsf(x1)), fmaxf(fabsf(y0), fabsf(y1)));
+            wc.bx0 = (float)((double)x0 - ox); wc.bx1 = (float)((double)x1 - ox);
+            wc.by0 = (float)((double)y0 - oy); wc.by1 = (float)((double)y1 - oy);
+            wc.slack = 1.2e-7f * mag;
+            const float wx = wc.bx1 - wc.bx0, wy = wc.by1 - wc.by0;
+            wc.far2 = 0.015625f * fmaf(wx, wx, wy * wy);
+            wc.live0 = live0; wc.live1 = live1;
+            s_wc[warp] = wc;
+        }
+        __syncwarp();
     }
-    // |true coordinate - hi float| <= 2^-24 |hi|: absolute slack of the box test per axis (plus the node's own below)
-    const float slack_x = 1.2e-7f * fmaxf(fabsf(bx0), fabsf(bx1)), slack_y = 1.2e-7f * fmaxf(fabsf(by0), fabsf(by1));
     const float2 eps2 = make_float2(feps, feps), neg_eps2 = make_float2(-feps, -feps);
     (void)eps2; (void)neg_eps2;
     const uint32_t lanebit = 1u << lane;
@@ -625,17 +663,24 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
             return __fmul2_rn(make_float2(gm, gm), __fmul2_rn(t, u));
         }
     };
-    // class A, full mask: force arithmetic only
-    auto apply_full = [&](const float4 A, const float gm) {
-        const float2 dx = __fadd2_rn(__fadd2_rn(make_float2(A.x, A.x), nxh), __fadd2_rn(make_float2(A.z, A.z), nxl));
-        const float2 dy = __fadd2_rn(__fadd2_rn(make_float2(A.y, A.y), nyh), __fadd2_rn(make_float2(A.w, A.w), nyl));
+    // far class A: single-float displacement in the local frame
+    auto apply_far = [&](const float4 F) {
+        const float2 dx = __fadd2_rn(make_float2(F.x, F.x), nxh), dy = __fadd2_rn(make_float2(F.y, F.y), nyh);
         const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
-        const float2 g = gfactor(d2, gm);
+        const float2 g = gfactor(d2, F.z);
         accx = __ffma2_rn(g, dx, accx);
         accy = __ffma2_rn(g, dy, accy);
     };
-    // class A, partial mask (or a body's own leaf cleared from it): the select comes last — a body's own leaf has d2 == 0
-    auto apply_masked = [&](const float4 A, const float gm, const uint32_t m0, const uint32_t m1) {
+    auto apply_far_masked = [&](const float4 F, const uint2 m) {
+        const float2 dx = __fadd2_rn(make_float2(F.x, F.x), nxh), dy = __fadd2_rn(make_float2(F.y, F.y), nyh);
+        const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+        const float2 g = gfactor(d2, F.z);
+        const float2 f = make_float2((m.x & lanebit) ? g.x : 0.f, (m.y & lanebit) ? g.y : 0.f);
+        accx = __ffma2_rn(f, dx, accx);
+        accy = __ffma2_rn(f, dy, accy);
+    };
+    // near class A: double-float displacement; the select comes last — a body's own leaf has d2 == 0
+    auto apply_near = [&](const float4 A, const float gm, const uint32_t m0, const uint32_t m1) {
         const float2 dx = __fadd2_rn(__fadd2_rn(make_float2(A.x, A.x), nxh), __fadd2_rn(make_float2(A.z, A.z), nxl));
         const float2 dy = __fadd2_rn(__fadd2_rn(make_float2(A.y, A.y), nyh), __fadd2_rn(make_float2(A.w, A.w), nyl));
         const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
@@ -665,13 +710,37 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
         accx = __ffma2_rn(f, dx, accx);
         accy = __ffma2_rn(f, dy, accy);
     };
+    // a record's centre of mass (ch + cl) in the local frame, as a double-float pair: TwoSum of the hi parts (exact),
+    // the lo parts and the rounding error folded in, then renormalised — FP32 adds only (the FP64 pipe and its
+    // conversions share the SFU issue port with the MUFUs of the force loops)
+    auto to_local = [&](const float4 R, const ListWarpConsts& wc) -> float4 {
+        float4 out;
+        {
+            const float a_ = R.x, b_ = -wc.oxh;
+            const float s_ = a_ + b_, bb = s_ - a_;
+            const float e_ = (a_ - (s_ - bb)) + (b_ - bb);
+            const float t_ = (R.z - wc.oxl) + e_;
+            out.x = s_ + t_;
+            out.z = t_ - (out.x - s_);
+        }
+        {
+            const float a_ = R.y, b_ = -wc.oyh;
+            const float s_ = a_ + b_, bb = s_ - a_;
+            const float e_ = (a_ - (s_ - bb)) + (b_ - bb);
+            const float t_ = (R.w - wc.oyl) + e_;
+            out.y = s_ + t_;
+            out.w = t_ - (out.y - s_);
+        }
+        return out;
+    };
 
     int top = 0;
     {   // the root (project.cu:711-715 pushes node 0): per-body test
-        const float4 A = __ldg(reinterpret_cast<const float4*>(a.rec));
+        const float4 R = __ldg(reinterpret_cast<const float4*>(a.rec));
         const float2 B = __ldg(reinterpret_cast<const float2*>(a.rec) + 2);
+        const ListWarpConsts& wc = s_wc[warp];
         uint32_t m0, m1;
-        eval_mixed(A, B.x, B.y, 0u, live0, live1, m0, m1);
+        eval_mixed(to_local(R, wc), B.x, B.y, 0u, wc.live0, wc.live1, m0, m1);
         if ((m0 | m1) != 0u) {
             if (lane == 0) stack[0] = make_uint4(0u, m0, m1, 0u);
             top = 1;
@@ -690,72 +759,96 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
         if (valid) ent = stack[top - 1 - e];
         top -= k;
         const uint32_t child = 4u * ent.x + 1u + (uint32_t)(lane & 3);
-        float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 R = make_float4(0.f, 0.f, 0.f, 0.f);
         uint4 Bq = make_uint4(0u, 0u, 0u, 0u);
         if (valid) {
-            A = __ldg(reinterpret_cast<const float4*>(a.rec + child));
+            R = __ldg(reinterpret_cast<const float4*>(a.rec + child));
             Bq = __ldg(reinterpret_cast<const uint4*>(a.rec + child) + 1);       // gm thr count first
         }
         const float gm = __uint_as_float(Bq.x), thr = __uint_as_float(Bq.y);
         uint32_t pm0 = ent.y, pm1 = ent.z;
-        // ---- classify: 0 dropped, 1 A full mask, 2 A partial mask, 3 O, 4 M ----
+        // ---- classify: 0 dropped, 1 far A full mask, 2 far A partial mask, 3 near A, 4 O, 5 M ----
         int cls = 0;
+        float4 L = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid && gm != 0.f) {
+            const ListWarpConsts wc = s_wc[warp];
+            L = to_local(R, wc);
+            const float ex = wc.slack + 1.2e-7f * fabsf(L.x), ey = wc.slack + 1.2e-7f * fabsf(L.y);
+            const float nx = fmaxf(fmaxf(wc.bx0 - L.x, L.x - wc.bx1) - ex, 0.f), ny = fmaxf(fmaxf(wc.by0 - L.y, L.y - wc.by1) - ey, 0.f);
+            const float dmin2 = fmaf(nx, nx, ny * ny);
             if (thr < 0.f) {                                  // a leaf: everybody in the mask accepts it
                 cls = 1;
                 if (Bq.z == 1u) {                             // single body: it may be one of ours -> the self test
-                    if (a.own_list) cls = 4;                  // slots are indirect: let the per-body test decide
+                    if (a.own_list) cls = 5;                  // slots are indirect: let the per-body test decide
                     else {
                         const int64_t slot = (int64_t)Bq.w - warp_slot0;
                         if (slot >= 0 && slot < 64) { if (slot < 32) pm0 &= ~(1u << slot); else pm1 &= ~(1u << (slot - 32)); }
                     }
                 }
             } else {
-                const float ex = slack_x + 1.2e-7f * fabsf(A.x), ey = slack_y + 1.2e-7f * fabsf(A.y);
-                const float nx = fmaxf(fmaxf(bx0 - A.x, A.x - bx1) - ex, 0.f), ny = fmaxf(fmaxf(by0 - A.y, A.y - by1) - ey, 0.f);
-                const float fx = fmaxf(A.x - bx0, bx1 - A.x) + ex, fy = fmaxf(A.y - by0, by1 - A.y) + ey;
-                const float dmin2 = fmaf(nx, nx, ny * ny), dmax2 = fmaf(fx, fx, fy * fy);
-                cls = (dmin2 > thr * (1.f + kListDelta)) ? 1 : (dmax2 <= thr * (1.f - kListDelta)) ? 3 : 4;
+                const float fx = fmaxf(L.x - wc.bx0, wc.bx1 - L.x) + ex, fy = fmaxf(L.y - wc.by0, wc.by1 - L.y) + ey;
+                const float dmax2 = fmaf(fx, fx, fy * fy);
+                cls = (dmin2 > thr * (1.f + kListDelta)) ? 1 : (dmax2 <= thr * (1.f - kListDelta)) ? 4 : 5;
             }
-            if (cls == 1 && (pm0 != live0 || pm1 != live1)) cls = 2;
+            if (cls == 1) cls = !(dmin2 >= wc.far2) ? 3 : (pm0 != wc.live0 || pm1 != wc.live1) ? 2 : 1;
             if ((pm0 | pm1) == 0u) cls = 0;                   // (a lone body's own leaf)
         }
-        const uint32_t bF = __ballot_sync(0xffffffffu, cls == 1), bP = __ballot_sync(0xffffffffu, cls == 2);
-        const uint32_t bO = __ballot_sync(0xffffffffu, cls == 3), bM = __ballot_sync(0xffffffffu, cls == 4);
-        const int nF = __popc(bF), nP = __popc(bP), nM = __popc(bM);
-        if (cls == 3) stack[top + __popc(bO & lanemask_lt)] = make_uint4(child, pm0, pm1, 0u);
-        top += __popc(bO);
-        if (cls == 1 || cls == 2 || cls == 4) {
-            const int at = cls == 1 ? __popc(bF & lanemask_lt) : cls == 2 ? nF + __popc(bP & lanemask_lt)
-                                                                         : nF + nP + __popc(bM & lanemask_lt);
-            nodeA[at] = A;
-            nodeB[at] = make_uint4(Bq.x, Bq.y, pm0, pm1);
-            cellv[at] = child;
+        const uint32_t b1 = __ballot_sync(0xffffffffu, cls == 1), b2 = __ballot_sync(0xffffffffu, cls == 2);
+        const uint32_t b3 = __ballot_sync(0xffffffffu, cls == 3), b4 = __ballot_sync(0xffffffffu, cls == 4);
+        const uint32_t b5 = __ballot_sync(0xffffffffu, cls == 5);
+        const int n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3), n5 = __popc(b5);
+        sts_v4_if(cls == 4, stack + top + __popc(b4 & lanemask_lt), child, pm0, pm1, 0u);
+        top += __popc(b4);
+        {   // one staging array for the four applied classes, in class order: far full | far masked | near | M
+            const uint32_t mine = cls == 1 ? b1 : cls == 2 ? b2 : cls == 3 ? b3 : b5;
+            const int base = cls == 1 ? 0 : cls == 2 ? n1 : cls == 3 ? n1 + n2 : n1 + n2 + n3;
+            const int at = base + __popc(mine & lanemask_lt);
+            const bool far = cls == 1 || cls == 2, staged = cls != 0 && cls != 4;
+            // far entries: (cx, cy, gm, -) so that one 128-bit load feeds the force loop; near / M: the double-float pair
+            sts_v4_if(staged, reinterpret_cast<uint4*>(nodeA + at), __float_as_uint(L.x), __float_as_uint(L.y),
+                      far ? Bq.x : __float_as_uint(L.z), __float_as_uint(L.w));
+            sts_v4_if(staged, nodeB + at, Bq.x, Bq.y, pm0, pm1);
+            if (cls == 5) cellv[at] = child;
         }
         __syncwarp();
         // ---- apply the staged nodes to the warp's 64 bodies ----
         int i = 0;
+#pragma unroll 4
+        for (; i < n1; ++i) apply_far(nodeA[i]);
 #pragma unroll 2
-        for (; i < nF; ++i) {
-            const float4 SA = nodeA[i];
-            apply_full(SA, __uint_as_float(nodeB[i].x));
-        }
-#pragma unroll 2
-        for (; i < nF + nP; ++i) {
-            const float4 SA = nodeA[i];
+        for (; i < n1 + n2; ++i) {
             const uint4 SB = nodeB[i];
-            apply_masked(SA, __uint_as_float(SB.x), SB.z, SB.w);
+            apply_far_masked(nodeA[i], make_uint2(SB.z, SB.w));
         }
-        for (; i < nF + nP + nM; ++i) {
+#pragma unroll 2
+        for (; i < n1 + n2 + n3; ++i) {
+            const uint4 SB = nodeB[i];
+            apply_near(nodeA[i], __uint_as_float(SB.x), SB.z, SB.w);
+        }
+        // class M: the per-body test, the only class that pushes here; two nodes per iteration (independent chains)
+        const int endM = n1 + n2 + n3 + n5;
+        for (; i + 1 < endM; i += 2) {
+            const float4 SA0 = nodeA[i], SA1 = nodeA[i + 1];
+            const uint4 SB0 = nodeB[i], SB1 = nodeB[i + 1];
+            const uint32_t c0 = cellv[i], c1 = cellv[i + 1];
+            uint32_t p0, p1, q0, q1;
+            eval_mixed(SA0, __uint_as_float(SB0.x), __uint_as_float(SB0.y), c0, SB0.z, SB0.w, p0, p1);
+            eval_mixed(SA1, __uint_as_float(SB1.x), __uint_as_float(SB1.y), c1, SB1.z, SB1.w, q0, q1);
+            const bool pushp = (p0 | p1) != 0u, pushq = (q0 | q1) != 0u;
+            sts_v4_if(pushp && lane == 0, stack + top, c0, p0, p1, 0u);
+            top += pushp;
+            sts_v4_if(pushq && lane == 0, stack + top, c1, q0, q1, 0u);
+            top += pushq;
+        }
+        if (i < endM) {
             const float4 SA = nodeA[i];
             const uint4 SB = nodeB[i];
             const uint32_t c = cellv[i];
             uint32_t m0, m1;
             eval_mixed(SA, __uint_as_float(SB.x), __uint_as_float(SB.y), c, SB.z, SB.w, m0, m1);
-            if ((m0 | m1) != 0u) {
-                if (lane == 0) stack[top] = make_uint4(c, m0, m1, 0u);
-                ++top;
-            }
+            const bool push = (m0 | m1) != 0u;
+            sts_v4_if(push && lane == 0, stack + top, c, m0, m1, 0u);
+            top += push;
         }
         __syncwarp();
     }
