@@ -578,6 +578,7 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     BH_ALLOC(c->rec_alloc, np + 4);
     c->tree.rec = c->rec_alloc + 3;   // 96-byte lead-in: sibling groups (4p+1 .. 4p+4) start on 128-byte lines
     BH_ALLOC(c->tree.self_node, n);
+    BH_ALLOC(c->tree.tile_queue, 2);
     // One allocation: [tree.count: all levels, finest level last][zeroed scratch block][huge-cell tickets].
     // Everything from the finest level's counts to the end is zeroed by ONE memset per step (zero_scratch).
     const int nbins = 1 << c->sp.nbins_log2;
@@ -632,6 +633,7 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     for (auto& ev : c->ev_trav) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto& ev : c->ev_vel) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_dl, cudaEventDisableTiming);
+    cudaMemsetAsync(c->tree.tile_queue, 0, 2 * sizeof(uint32_t), c->stream);
     cudaMemsetAsync(c->acc, 0, sizeof(double2) * n, c->stream);
     cudaMemsetAsync(c->force, 0, sizeof(double2) * n, c->stream);
     cudaMemsetAsync(c->tree.count, 0, sizeof(uint32_t) * (np_pad + words + huge_words), c->stream);
@@ -653,7 +655,7 @@ int bh_destroy(bh_ctx* c) {
     if (c->comm_buf) cudaFree(c->comm_buf);
     void* ptrs[] = {c->pos, c->vel, c->acc, c->force, c->snap_pos, c->snap_vel, c->mass, c->keys[0],
                     c->keys[1], c->idx[0], c->idx[1], c->consts, c->tree.mass, c->tree.comx, c->tree.comy,
-                    c->tree.count /* + scratch + tickets */, c->tree.first, c->tree.flags, c->rec_alloc, c->tree.self_node,
+                    c->tree.count /* + scratch + tickets */, c->tree.first, c->tree.flags, c->rec_alloc, c->tree.self_node, c->tree.tile_queue,
                     c->s.bbox_partial, c->s.heavy_list, c->s.huge_list, c->s.huge_partial, c->s.cell_bnd,
                     c->packed, c->chunk_lists, c->chunk_counts, c->cell_sums, c->bbox_raw};
     for (void* p : ptrs) if (p) cudaFree(p);

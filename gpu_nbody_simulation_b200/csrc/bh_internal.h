@@ -61,6 +61,7 @@ struct TreeArrays {
     uint32_t* flags;   // kNode* (verification / counting paths)
     NodeRec* rec;
     uint32_t* self_node;  // per body: pyramid index of the leaf holding only that body, else 0xffffffff
+    uint32_t* tile_queue; // [2] work queue of the list traversal kernel (self-resetting, zero between launches)
 };
 
 struct Scratch {

@@ -32,6 +32,8 @@
 // COM differs from them by one FP64 ulp) cannot be resolved; use the FP64 mode for those.
 //
 // FP64 mode (BH_FLAG_FP64_TRAVERSAL): the reference's expressions verbatim on the FP64 tree arrays.
+#include <algorithm>
+
 #include "bh_internal.h"
 
 namespace bh {
@@ -69,6 +71,9 @@ struct TravArgs {
     const uint32_t* t_count;    // bodies per pyramid cell
     const uint32_t* t_first;    // sorted position of a cell's first body
     uint32_t finest_off;        // pyramid index of the first cap-level cell
+    // list kernel: [0] next 64-body tile (warps fetch their work one tile at a time), [1] warps that found the queue
+    // empty — the last one resets both words, so the pair is zero again when the kernel ends
+    uint32_t* tile_queue;
 };
 
 __device__ __forceinline__ float approx_sqrt(float x) {
@@ -580,16 +585,31 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
     __shared__ __align__(16) ListWarpConsts s_wc[kTravWarps];
     pdl_entry();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t warp_slot0 = ((int64_t)blockIdx.x * kTravWarps + warp) * 64;
     uint4* const stack = s_stack[warp];
     float4* const nodeA = s_nodeA[warp];
     uint4* const nodeB = s_nodeB[warp];
     uint32_t* const cellv = s_cell[warp];
+    const float feps = a.consts->feps;
+    const uint32_t n_tiles = (uint32_t)((a.n_slots + 63) >> 6);
+    // Persistent warps: every warp fetches 64-body tiles from a global queue until it is empty, so a warp slot is
+    // never idle while work is left (with one tile per warp and 4-warp blocks, a block's slot stayed occupied by its
+    // slowest warp: ncu showed 23 of 28 possible warps resident on average).
+  for (;;) {
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(a.tile_queue, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= n_tiles) {
+        if (lane == 0) {
+            const uint32_t total = gridDim.x * kTravWarps;
+            if (atomicAdd(a.tile_queue + 1, 1u) == total - 1u) { a.tile_queue[0] = 0u; a.tile_queue[1] = 0u; }
+        }
+        return;
+    }
+    const int64_t warp_slot0 = (int64_t)tile * 64;
 
     uint32_t body[2], selfn[2];
     float2 nxh, nyh, nxl, nyl;   // minus the local-frame positions of body 0 (.x) and body 1 (.y), hi / lo floats
     float2 accx = make_float2(0.f, 0.f), accy = make_float2(0.f, 0.f);
-    const float feps = a.consts->feps;
     {
         const double scale = a.consts->scale;
         double sx[2], sy[2];
@@ -609,7 +629,6 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
         }
         const bool l0 = body[0] != 0xffffffffu, l1 = body[1] != 0xffffffffu;
         const uint32_t live0 = __ballot_sync(0xffffffffu, l0), live1 = __ballot_sync(0xffffffffu, l1);
-        if (live0 == 0u) return;                       // no body in this warp (slots are handed out in order)
         // bounding box of the warp's bodies (floats rounded outwards by the slack below), frame origin = its centre
         const float inf = __int_as_float(0x7f800000);
         float x0 = inf, x1 = -inf, y0 = inf, y1 = -inf;
@@ -861,6 +880,8 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
             finish_body<INTEGRATE>(a, body[b], p.x, p.y, mi, mi * (double)ax[b], mi * (double)ay[b]);
         }
     }
+    __syncwarp();       // the warp's shared arrays are reused by its next tile
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1097,6 +1118,7 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
     a.n_slots = own_n;
     a.G = p.G; a.dt = p.dt; a.theta = p.theta; a.dist_eps = p.dist_eps;
     a.t_count = t.count; a.t_first = t.first; a.finest_off = (uint32_t)d.level_off[d.finest];
+    a.tile_queue = t.tile_queue;
     if (own_n <= 0) return;
     const bool fp64 = p.flags & BH_FLAG_FP64_TRAVERSAL, count = p.flags & BH_FLAG_COUNTERS;
     // two bodies per lane halve the node traffic and the control overhead per body, but need >= ~400k
@@ -1127,6 +1149,17 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
             else { if (count) BH_GO((traverse_f32_kernel<1, false, true, true>)); else BH_GO((traverse_f32_kernel<1, false, false, true>)); }
         } else if (bpl == 2 && !count && (p.reserved[0] == 0 || p.reserved[0] == 8)) {
             const bool exact = p.flags & BH_FLAG_EXACT_EPS;
+            // persistent warps: as many blocks as can be resident (or fewer when there are not that many tiles)
+            static int resident = 0;
+            if (!resident) {
+                int dev = 0, sms = 148, per_sm = BH_LIST_MIN_BLOCKS;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, traverse_f32_list_kernel<true, false>, kTravThreads, 0);
+                resident = sms * (per_sm > 0 ? per_sm : BH_LIST_MIN_BLOCKS);
+            }
+            const unsigned tiles = (unsigned)((own_n + 63) / 64);
+            blocks = std::min<unsigned>((tiles + kTravWarps - 1) / kTravWarps, (unsigned)resident);
             if (integrate) { if (exact) BH_GO((traverse_f32_list_kernel<true, true>)); else BH_GO((traverse_f32_list_kernel<true, false>)); }
             else { if (exact) BH_GO((traverse_f32_list_kernel<false, true>)); else BH_GO((traverse_f32_list_kernel<false, false>)); }
         } else if (bpl == 2 && !count && p.reserved[0] != 3) {
