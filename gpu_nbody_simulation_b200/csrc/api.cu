@@ -116,7 +116,7 @@ struct bh_ctx {
     const void* host_graph_key[4] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t host_graph_kernels = 0;
     bool host_graph_failed = false;
-    bool host_pipeline_multi = false;   // env BH_HOST_PIPELINE_MULTI=1 (experiment, see bh_step_host)
+    bool host_pipeline_multi = true;    // multi-rank bh_step_host pipelined like the single-rank one (BH_HOST_PIPELINE_MULTI=0: plain sequence)
     // BH_HOST_TRACE=1: timeline of one bh_step_host call (direct submission), printed to stderr
     bool host_trace = false;
     std::vector<std::pair<const char*, cudaEvent_t>> trace_ev;
@@ -554,7 +554,7 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     { const char* e = getenv("BH_KEYS_TABLE"); c->keys_table = e && e[0] == '1'; }
     { const char* e = getenv("BH_PDL"); c->pdl = e && e[0] == '1' && p->n_ranks == 1; }
     { const char* e = getenv("BH_HOST_TRACE"); c->host_trace = e && e[0] == '1'; }
-    { const char* e = getenv("BH_HOST_PIPELINE_MULTI"); c->host_pipeline_multi = e && e[0] == '1'; }
+    { const char* e = getenv("BH_HOST_PIPELINE_MULTI"); c->host_pipeline_multi = !(e && e[0] == '0'); }   // default on
     { const char* e = getenv("BH_HOST_CHUNKS"); if (e && atoi(e) >= 1) c->host_chunks = std::min(atoi(e), kMaxHostChunks); }
     if (p->device >= 0) c->device = p->device;
     else if ((e = cudaGetDevice(&c->device)) != cudaSuccess) { set_error("cudaGetDevice: %s", cudaGetErrorString(e)); delete c; return BH_ERR_CUDA; }
@@ -814,9 +814,10 @@ int bh_step_from_snapshot(bh_ctx* c, int32_t nsteps) {
 int bh_step_host(bh_ctx* c, const double* pos, const double* vel, const double* mass, double* out_pos) {
     if (!c || !pos || !vel || !mass || !out_pos) { set_error("null argument"); return BH_ERR_INVALID; }
     if (c->p.n_ranks > 1 && c->host_pipeline_multi && c->p2p_ready && !c->profiling) {
-        // EXPERIMENT (env BH_HOST_PIPELINE_MULTI=1, written after round 1's GPU budget was spent, not yet run):
         // the single-rank pipeline for one rank's slice — positions up, then bounds / keys / sort while masses
-        // and velocities are still in flight; integrator + download on the high-priority stream.
+        // and velocities are still in flight; integrator + download on the high-priority stream.  Bit-identical to
+        // the plain sequence below (tests/multi_gpu_check.py --host-step, profiles/r02_multi_gpu_check_g2.log);
+        // 2 GPUs, 1M bodies each: 1.72 -> 1.56 ms per step.
         DeviceGuard g(c->device);
         const int64_t lo = c->own_lo, cnt = c->own_hi - c->own_lo;
         BH_CUDA_OK(cudaEventRecord(c->ev0, c->stream));
