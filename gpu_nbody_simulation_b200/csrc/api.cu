@@ -267,7 +267,7 @@ int enqueue_build(bh_ctx* c, bool full = false, const double2* src = nullptr, cu
         launch_keys(src, c->d.n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream, 0,
                     c->s.cell_bnd);
         prof_mark(c, 1);
-        launch_sort(c->keys, c->idx, c->d.n, c->sp, c->s, &c->sorted, c->stream);
+        launch_sort(c->keys, c->idx, c->d.n, c->sp, c->s, &c->sorted, c->stream, 0u);
         prof_mark(c, 2);
         launch_tree(c->keys[c->sorted], c->idx[c->sorted], src, c->mass, c->d.n, c->p, c->d, c->tree, c->s, c->consts,
                     c->stream);
@@ -284,7 +284,7 @@ int enqueue_build(bh_ctx* c, bool full = false, const double2* src = nullptr, cu
         launch_keys(src + lo, n_own, c->d, c->sp_own, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream,
                     (uint32_t)lo, c->s.cell_bnd);
         prof_mark(c, 1);
-        launch_sort(c->keys, c->idx, n_own, c->sp_own, c->s, &c->sorted, c->stream);
+        launch_sort(c->keys, c->idx, n_own, c->sp_own, c->s, &c->sorted, c->stream, (uint32_t)lo);
         prof_mark(c, 2);
         if (mass_ready) cudaStreamWaitEvent(c->stream, mass_ready, 0);
         launch_tree_runs(c->keys[c->sorted], c->idx[c->sorted], src, c->mass, n_own, c->p, c->d, c->tree, c->s,
@@ -476,7 +476,7 @@ int enqueue_host_step(bh_ctx* c, const double* pos, const double* vel, const dou
     BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[0], 0));
     launch_bounds(c->pos, n, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream);
     launch_keys(c->pos, n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream, 0, c->s.cell_bnd);
-    launch_sort(c->keys, c->idx, n, c->sp, c->s, &c->sorted, c->stream);
+    launch_sort(c->keys, c->idx, n, c->sp, c->s, &c->sorted, c->stream, 0u);
     if (nch > 1) launch_chunk_lists(c->idx[c->sorted], n, cb, c->chunk_counts, c->chunk_lists, c->stream);
     trace_mark(c, "gpu: sort+lists done", c->stream);
     BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[1], 0));
@@ -551,7 +551,9 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     c->p = *p;
     // A/B switches (environment, read once per context)
     { const char* e = getenv("BH_SNAPSHOT_COPY"); c->snapshot_by_copy = e && e[0] == '1'; }
-    { const char* e = getenv("BH_KEYS_TABLE"); c->keys_table = e && e[0] == '1'; }
+    // cell keys from the boundary table (same bits as the per-body bisection): 220 -> 159 us for bounds + keys at 16M
+    // bodies (the bisection is 415 instructions per body), +2 us at 1M; BH_KEYS_TABLE=0 / 1 forces either
+    { const char* e = getenv("BH_KEYS_TABLE"); c->keys_table = e ? e[0] == '1' : (p->n_bodies / p->n_ranks >= 4000000); }
     { const char* e = getenv("BH_PDL"); c->pdl = e && e[0] == '1' && p->n_ranks == 1; }
     { const char* e = getenv("BH_HOST_TRACE"); c->host_trace = e && e[0] == '1'; }
     { const char* e = getenv("BH_HOST_PIPELINE_MULTI"); c->host_pipeline_multi = !(e && e[0] == '0'); }   // default on
@@ -609,9 +611,8 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     BH_ALLOC(c->s.heavy_list, c->d.ncells_finest);
     BH_ALLOC(c->s.huge_list, c->s.max_huge);
     BH_ALLOC(c->s.huge_partial, (size_t)c->s.max_huge * kHugeParts * 3);
-    // Cell keys: per-body FP64 bisection by default.  The boundary-table variant (BH_KEYS_TABLE=1, same bits)
-    // measured no faster on B200 at 1M bodies (bounds + keys 38.5 us vs 37.2 us: the key kernel is bound by its
-    // loads and shared-memory histogram atomics, not by the 2 x 9 FP64 bisections), so it stays opt-in.
+    // Cell keys: per-body FP64 bisection below 4M bodies per rank, the boundary-table variant (same bits) above:
+    // at 1M bodies the two are equal (latency-bound), at 16M the table saves 60 us.
     if (c->keys_table) BH_ALLOC(c->s.cell_bnd, 2 * (((size_t)1 << c->d.finest) + 1));
     if (p->n_ranks > 1) {
         BH_ALLOC(c->cell_sums, 4 * c->d.ncells_finest); BH_ALLOC(c->bbox_raw, 4);
@@ -1042,13 +1043,14 @@ int bh_get_counters(bh_ctx* c, bh_counters* out) {
     if (!c || !out) { set_error("null argument"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     unsigned long long v[8];
-    uint32_t heavy = 0;
+    uint32_t heavy = 0, huge = 0;
     BH_CUDA_OK(cudaMemcpyAsync(v, c->s.counters, sizeof v, cudaMemcpyDeviceToHost, c->stream));
     BH_CUDA_OK(cudaMemcpyAsync(&heavy, c->s.heavy_count, 4, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(&huge, c->s.huge_count, 4, cudaMemcpyDeviceToHost, c->stream));
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
     memset(out, 0, sizeof *out);
     out->interactions = v[0]; out->visits = v[1]; out->opens = v[2]; out->warp_steps = v[3]; out->nodes = v[4];
-    out->heavy_cells = heavy;
+    out->heavy_cells = (uint64_t)heavy + huge;   // cell_runs_kernel queues the two kinds separately
     out->zero_mass_bodies = c->zero_mass_bodies;
     return BH_OK;
 }

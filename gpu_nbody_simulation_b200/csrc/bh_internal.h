@@ -135,7 +135,7 @@ void launch_tree_levels(const uint32_t* sidx, const double2* pos, const double* 
                         const Dims& d, TreeArrays& t, Scratch& s, const StepConsts* consts, const double* sums,
                         cudaStream_t st);
 void launch_sort(uint32_t* keys[2], uint32_t* vals[2], int64_t n, const SortPlan& sp, Scratch& s,
-                 int* result_buf, cudaStream_t st);
+                 int* result_buf, cudaStream_t st, uint32_t val_base);   // values of pass 0 = val_base + input position
 void launch_tree(const uint32_t* skeys, const uint32_t* sidx, const double2* pos, const double* mass,
                  int64_t n, const bh_params& p, const Dims& d, TreeArrays& t, Scratch& s,
                  const StepConsts* consts, cudaStream_t st);

@@ -237,8 +237,7 @@ keys_kernel(const double2* __restrict__ pos, int64_t n, int finest, const StepCo
                 key = (key << 2) | (uint32_t)bx | ((uint32_t)by << 1);
             }
         }
-        keys[i] = key;
-        idx[i] = idx_base + (uint32_t)i;
+        keys[i] = key;               // (the first sort pass generates the body indices idx_base + i itself)
         for (int ps = 0; ps < passes; ++ps)
             atomicAdd(&hist[ps * kMaxBins + ((key >> (ps * bits_per_pass)) & dmask)], 1u);
     }

@@ -23,11 +23,17 @@ constexpr uint32_t kFlagAgg = 1u << 30;   // tile published its own digit count
 constexpr uint32_t kFlagIncl = 2u << 30;  // tile published the inclusive prefix over tiles 0..t
 constexpr uint32_t kValMask = (1u << 30) - 1u;
 
-template <int NBINS_LOG2>
-__global__ void __launch_bounds__(kSortThreads)
+// FIRST: the values of the first pass are the body indices in input order (val[g] = val_base + g): they are
+// generated instead of being read, and the key kernel does not have to write them.
+#ifndef BH_SORT_MIN_BLOCKS
+#define BH_SORT_MIN_BLOCKS 3     // <= 80 registers: 24 warps per SM instead of 16 (the pass is latency-bound)
+#endif
+template <int NBINS_LOG2, bool FIRST>
+__global__ void __launch_bounds__(kSortThreads, BH_SORT_MIN_BLOCKS)
 onesweep_pass(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
-              int bits, const uint32_t* __restrict__ digit_hist, uint32_t* tile_state, uint32_t* ticket) {
+              int bits, const uint32_t* __restrict__ digit_hist, uint32_t* tile_state, uint32_t* ticket,
+              uint32_t val_base) {
     constexpr int NBINS = 1 << NBINS_LOG2;
     constexpr int NWARPS = kSortThreads / 32;
     constexpr int PER_T = NBINS / kSortThreads;  // digits owned per thread (1 or 2)
@@ -177,7 +183,8 @@ onesweep_pass(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__
             uint32_t d = (key[k] >> shift) & dmask;
             uint32_t dst = s_base[d] + s_warp[warp][d] + rank[k];
             keys_out[dst] = key[k];
-            vals_out[dst] = vals_in[g];
+            if constexpr (FIRST) vals_out[dst] = val_base + (uint32_t)g;
+            else vals_out[dst] = vals_in[g];
         }
     }
 }
@@ -185,21 +192,20 @@ onesweep_pass(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__
 }  // namespace
 
 void launch_sort(uint32_t* keys[2], uint32_t* vals[2], int64_t n, const SortPlan& sp, Scratch& s,
-                 int* result_buf, cudaStream_t st) {
+                 int* result_buf, cudaStream_t st, uint32_t val_base) {
     int cur = 0;
     const int nbins = 1 << sp.nbins_log2;
     for (int pass = 0; pass < sp.passes; ++pass) {
         uint32_t* state = s.tile_state + (size_t)pass * sp.ntiles * nbins;
         const uint32_t* hist = s.digit_hist + (size_t)pass * kMaxBins;
         int shift = pass * sp.bits_per_pass;
-        if (sp.nbins_log2 == 9)
-            launch_chain(onesweep_pass<9>, dim3(sp.ntiles), dim3(kSortThreads), st, true, (const uint32_t*)keys[cur],
-                         (const uint32_t*)vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, sp.bits_per_pass, hist, state,
-                         s.tickets + pass);
-        else
-            launch_chain(onesweep_pass<8>, dim3(sp.ntiles), dim3(kSortThreads), st, true, (const uint32_t*)keys[cur],
-                         (const uint32_t*)vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, sp.bits_per_pass, hist, state,
-                         s.tickets + pass);
+#define BH_PASS(NB, F)                                                                                                   \
+        launch_chain(onesweep_pass<NB, F>, dim3(sp.ntiles), dim3(kSortThreads), st, true, (const uint32_t*)keys[cur],   \
+                     (const uint32_t*)vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, sp.bits_per_pass, hist, state,  \
+                     s.tickets + pass, val_base)
+        if (sp.nbins_log2 == 9) { if (pass == 0) BH_PASS(9, true); else BH_PASS(9, false); }
+        else { if (pass == 0) BH_PASS(8, true); else BH_PASS(8, false); }
+#undef BH_PASS
         ++g_launches;
         cur ^= 1;
     }

@@ -117,7 +117,7 @@ __device__ __forceinline__ void store_cell(const TreeArrays& t, uint64_t at, con
 __global__ void __launch_bounds__(256)
 cell_runs_kernel(const uint32_t* __restrict__ skeys, int64_t n, uint32_t* __restrict__ cnt_f,
                  uint32_t* __restrict__ first_f, uint32_t exact_leaf_max, uint32_t* __restrict__ heavy_list,
-                 uint32_t* __restrict__ heavy_count) {
+                 uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ huge_list, uint32_t* __restrict__ huge_count) {
     pdl_entry();
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -127,22 +127,40 @@ cell_runs_kernel(const uint32_t* __restrict__ skeys, int64_t n, uint32_t* __rest
     const bool tail = in && (j + 1 >= n || skeys[j + 1] != k);
     // run start: the nearest head at or below this lane inside the warp, else binary search
     const uint32_t heads = __ballot_sync(0xffffffffu, head) & (0xffffffffu >> (31 - lane));
-    if (!tail) return;
-    int64_t lo;
-    if (heads) {
-        lo = j - lane + (31 - __clz(heads));
-    } else {
-        lo = 0;
-        int64_t hi = j - lane;   // the run began before this warp's first key
-        while (lo < hi) {        // first position with key >= k
-            int64_t mid = (lo + hi) >> 1;
-            if (skeys[mid] < k) lo = mid + 1; else hi = mid;
+    uint32_t c = 0;
+    if (tail) {
+        int64_t lo;
+        if (heads) {
+            lo = j - lane + (31 - __clz(heads));
+        } else {
+            lo = 0;
+            int64_t hi = j - lane;   // the run began before this warp's first key
+            while (lo < hi) {        // first position with key >= k
+                int64_t mid = (lo + hi) >> 1;
+                if (skeys[mid] < k) lo = mid + 1; else hi = mid;
+            }
         }
+        c = (uint32_t)(j + 1 - lo);
+        cnt_f[k] = c;
+        first_f[k] = (uint32_t)lo;
     }
-    uint32_t c = (uint32_t)(j + 1 - lo);
-    cnt_f[k] = c;
-    first_f[k] = (uint32_t)lo;
-    if (c > exact_leaf_max) heavy_list[atomicAdd(heavy_count, 1u)] = k;
+    // queue over-full cells: ONE atomic per warp and queue (at 16M bodies nearly every cell is over-full; one atomic per
+    // cell on a single counter serialised 143 000 of them)
+    const bool over = c > exact_leaf_max, huge = over && c > kHugeCellMin, heavy = over && !huge;
+    const uint32_t mh = __ballot_sync(0xffffffffu, heavy), mg = __ballot_sync(0xffffffffu, huge);
+    const uint32_t lt = (1u << lane) - 1u;
+    if (mh) {
+        uint32_t base = 0;
+        if (lane == __ffs(mh) - 1) base = atomicAdd(heavy_count, (uint32_t)__popc(mh));
+        base = __shfl_sync(0xffffffffu, base, __ffs(mh) - 1);
+        if (heavy) heavy_list[base + __popc(mh & lt)] = k;                   // one block-independent warp each
+    }
+    if (mg) {
+        uint32_t base = 0;
+        if (lane == __ffs(mg) - 1) base = atomicAdd(huge_count, (uint32_t)__popc(mg));
+        base = __shfl_sync(0xffffffffu, base, __ffs(mg) - 1);
+        if (huge) huge_list[base + __popc(mg & lt)] = k;                     // summed by kHugeParts blocks each
+    }
 }
 
 // ---- parallel (non-sequential) summation for very full finest cells -------------------------------
@@ -173,49 +191,58 @@ __device__ __forceinline__ void write_cell_sums(double* m_f, double* cx_f, doubl
     else { cx_f[cell] = tm > 0.0 ? sx / tm : 0.0; cy_f[cell] = tm > 0.0 ? sy / tm : 0.0; }
 }
 
-__global__ void __launch_bounds__(256)
-heavy_cells_kernel(const uint32_t* __restrict__ heavy_list, const uint32_t* __restrict__ heavy_count,
+constexpr int kHeavyBlocks = 148 * 4;     // blocks [0, kHeavyBlocks) of heavy_huge_kernel sum heavy cells, one cell at a time
+constexpr int kHugeSlots = 16;            // the remaining kHugeParts x kHugeSlots blocks sum huge cells, kHugeParts blocks per cell
+
+// One WARP per heavy cell (lane-strided partial sums, then a xor-butterfly: a fixed shape for a given body count, so the
+// sums are deterministic and identical on every rank).  A whole block per cell (round 1) left 224 of 256 threads idle on
+// the typical heavy cell of ~70-100 bodies: at 16M bodies, where a third of the finest cells is heavy, that kernel alone
+// took 695 us.
+__device__ __forceinline__ void heavy_cells(uint32_t block, uint32_t nblocks,
+                   const uint32_t* __restrict__ heavy_list, const uint32_t* __restrict__ heavy_count,
                    const uint32_t* __restrict__ cnt_f, const uint32_t* __restrict__ first_f,
                    const uint32_t* __restrict__ sidx, const double2* __restrict__ pos,
                    const double* __restrict__ mass, double* __restrict__ m_f, double* __restrict__ cx_f,
-                   double* __restrict__ cy_f, bool raw_sums, uint32_t* __restrict__ huge_list,
-                   uint32_t* __restrict__ huge_count) {
-    __shared__ double sm[3][256];
-    pdl_entry();
+                   double* __restrict__ cy_f, bool raw_sums) {
     const uint32_t nheavy = *heavy_count;
-    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+    const uint32_t lane = threadIdx.x & 31u, warps_per_block = blockDim.x >> 5;
+    for (uint32_t h = block * warps_per_block + (threadIdx.x >> 5); h < nheavy; h += nblocks * warps_per_block) {
         const uint32_t cell = heavy_list[h];
         const uint32_t c = cnt_f[cell], f = first_f[cell];
-        if (c > kHugeCellMin) {                      // block-uniform
-            if (threadIdx.x == 0) huge_list[atomicAdd(huge_count, 1u)] = cell;
-            continue;
-        }
         double m = 0.0, sx = 0.0, sy = 0.0;
-        for (uint32_t i = threadIdx.x; i < c; i += 256) {
-            const uint32_t b = sidx[f + i];
-            const double mb = mass[b];
-            const double2 x = pos[b];
-            m += mb; sx += mb * x.x; sy += mb * x.y;
+        for (uint32_t i0 = lane; i0 < c; i0 += 128) {      // four independent gathers in flight per lane
+            uint32_t b[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) b[k] = (i0 + 32 * k < c) ? __ldg(sidx + f + i0 + 32 * k) : 0xffffffffu;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (b[k] != 0xffffffffu) {
+                    const double mb = __ldg(mass + b[k]);
+                    const double2 x = __ldg(pos + b[k]);
+                    m += mb; sx += mb * x.x; sy += mb * x.y;
+                }
+            }
         }
-        block_sum3(m, sx, sy, sm);
-        if (threadIdx.x == 0) write_cell_sums(m_f, cx_f, cy_f, cell, m, sx, sy, raw_sums);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m += __shfl_xor_sync(0xffffffffu, m, o);
+            sx += __shfl_xor_sync(0xffffffffu, sx, o);
+            sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        }
+        if (lane == 0) write_cell_sums(m_f, cx_f, cy_f, cell, m, sx, sy, raw_sums);
     }
 }
 
-// grid = (kHugeParts, slots): block (p, s) sums part p of huge cell s, s + slots, ...
-__global__ void __launch_bounds__(256)
-huge_cells_kernel(const uint32_t* __restrict__ huge_list, const uint32_t* __restrict__ huge_count,
+// block (p, slot) sums part p of huge cell slot, slot + kHugeSlots, ...
+__device__ __forceinline__ void huge_cells(uint32_t p, uint32_t slot, double (*sm)[256], bool& last,
+                  const uint32_t* __restrict__ huge_list, const uint32_t* __restrict__ huge_count,
                   const uint32_t* __restrict__ cnt_f, const uint32_t* __restrict__ first_f,
                   const uint32_t* __restrict__ sidx, const double2* __restrict__ pos,
                   const double* __restrict__ mass, double* __restrict__ m_f, double* __restrict__ cx_f,
                   double* __restrict__ cy_f, bool raw_sums, double* __restrict__ partial,
                   uint32_t* __restrict__ tickets) {
-    __shared__ double sm[3][256];
-    __shared__ bool last;
-    pdl_entry();
     const uint32_t nhuge = *huge_count;
-    const uint32_t p = blockIdx.x;
-    for (uint32_t h = blockIdx.y; h < nhuge; h += gridDim.y) {
+    for (uint32_t h = slot; h < nhuge; h += kHugeSlots) {
         const uint32_t cell = huge_list[h];
         const uint32_t c = cnt_f[cell], f = first_f[cell];
         const uint32_t per = (c + kHugeParts - 1) / kHugeParts;
@@ -248,6 +275,28 @@ huge_cells_kernel(const uint32_t* __restrict__ huge_list, const uint32_t* __rest
     }
 }
 
+// One launch for both kinds of over-full finest cells (cell_runs_kernel queues them separately).
+__global__ void __launch_bounds__(256)
+heavy_huge_kernel(const uint32_t* __restrict__ heavy_list, const uint32_t* __restrict__ heavy_count,
+                  const uint32_t* __restrict__ huge_list, const uint32_t* __restrict__ huge_count,
+                  const uint32_t* __restrict__ cnt_f, const uint32_t* __restrict__ first_f,
+                  const uint32_t* __restrict__ sidx, const double2* __restrict__ pos,
+                  const double* __restrict__ mass, double* __restrict__ m_f, double* __restrict__ cx_f,
+                  double* __restrict__ cy_f, bool raw_sums, double* __restrict__ partial,
+                  uint32_t* __restrict__ tickets) {
+    __shared__ double sm[3][256];
+    __shared__ bool last;
+    pdl_entry();
+    if (blockIdx.x < kHeavyBlocks) {
+        heavy_cells(blockIdx.x, kHeavyBlocks, heavy_list, heavy_count, cnt_f, first_f, sidx, pos, mass, m_f, cx_f, cy_f,
+                    raw_sums);
+    } else {
+        const uint32_t b = blockIdx.x - kHeavyBlocks;
+        huge_cells(b % kHugeParts, b / kHugeParts, sm, last, huge_list, huge_count, cnt_f, first_f, sidx, pos, mass, m_f,
+                   cx_f, cy_f, raw_sums, partial, tickets);
+    }
+}
+
 // ---- sharded build: this rank's partial sums per finest cell (count, m, m x, m y) ------------------
 // sums = [4][ncells] doubles, all-reduced over the ranks before the level pass.  Cells queued as
 // heavy were already summed (raw) by heavy_cells_kernel.
@@ -273,6 +322,45 @@ cell_partial_kernel(const uint32_t* __restrict__ cnt_f, const uint32_t* __restri
     sums[ncells + c] = m; sums[2 * ncells + c] = sx; sums[3 * ncells + c] = sy;
 }
 
+// ---- top levels (F-5 .. 0): run by the LAST block of tree_bottom_kernel to finish (atomic ticket), level by level
+// through global memory — 341 cells at the default cap; a separate single-block launch cost 8 us.
+template <bool SHARDED>
+__device__ __forceinline__ void tree_top_levels(const TreeArrays& t, const Dims& d, int top_level,
+                                                const uint32_t* __restrict__ sidx, const double2* __restrict__ pos,
+                                                const double* __restrict__ mass, double G, double mass_eps, double scale,
+                                                unsigned long long* __restrict__ counters,
+                                                const StepConsts* __restrict__ consts, uint32_t* s_int) {
+    const int F = d.finest;
+    if (threadIdx.x == 0) *s_int = 0;
+    __syncthreads();
+    uint32_t n_internal = 0;
+    for (int level = top_level; level >= 0; --level) {
+        uint64_t ncells = 1ull << (2 * level);
+        uint64_t off = d.level_off[level], offc = d.level_off[level + 1];
+        for (uint64_t c = threadIdx.x; c < ncells; c += blockDim.x) {
+            Cell ch[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint64_t a = offc + 4 * c + q;
+                ch[q].m = __ldcg(t.mass + a); ch[q].cx = __ldcg(t.comx + a); ch[q].cy = __ldcg(t.comy + a);
+                ch[q].cnt = __ldcg(t.count + a); ch[q].first = __ldcg(t.first + a);
+            }
+            Cell up = combine4<SHARDED>(ch, sidx, pos, mass, t.self_node, offc + 4 * c, true);
+            store_cell(t, off + c, up, level, F, G, mass_eps, scale, consts->thr2[level], sidx);
+            n_internal += (up.cnt >= 2u);
+        }
+        __threadfence();
+        __syncthreads();   // level `level` complete and visible to the block
+    }
+    if (n_internal) atomicAdd(s_int, n_internal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // counters[5] holds the internal cells counted by all blocks' bottom levels
+        unsigned long long internal = *reinterpret_cast<volatile unsigned long long*>(counters + 5) + *s_int;
+        counters[4] = 1ull + 4ull * internal;   // quadtree.size() of the reference
+    }
+}
+
 // ---- bottom kernel: finest cells + up to five levels above -----------------------------------------
 // Block b owns finest cells [256 b, 256 b + 256) = one subtree rooted four levels up; thread t
 // owns ONE finest cell (maximum parallelism for the latency-bound leaf pass).  Levels F-1 and F-2
@@ -295,7 +383,7 @@ __global__ void __launch_bounds__(kBottomThreads)
 tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, const double2* __restrict__ pos,
                    const double* __restrict__ mass, double G0, double mass_eps, uint32_t exact_leaf_max,
                    unsigned long long* __restrict__ counters, const StepConsts* __restrict__ consts,
-                   const double* __restrict__ sums) {
+                   const double* __restrict__ sums, uint32_t* __restrict__ done_ticket) {
     pdl_entry();
     const int F = d.finest;
     const double scale = consts->scale;
@@ -306,6 +394,7 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
     __shared__ Cell s_b[kBottomThreads / 64];     // level F-3 results (4 per block)
     __shared__ Cell s_c[1];
     __shared__ uint32_t s_internal[kBottomThreads / 32];
+    __shared__ uint32_t s_last;
     uint32_t n_internal = 0;
 
     // ---- level F: one cell per thread
@@ -359,7 +448,7 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
         store_cell(t, offF + code, cur, F, F, G, mass_eps, scale, consts->thr2[F], sidx);
     }
     if (F == 0) {
-        if (blockIdx.x == 0 && tid == 0) atomicAdd(&counters[4], 1ull);   // the root alone
+        if (blockIdx.x == 0 && tid == 0) counters[4] = 1ull;   // the root alone
         return;
     }
     int level = F;
@@ -419,46 +508,16 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
         uint32_t tot = 0;
         for (int w = 0; w < kBottomThreads / 32; ++w) tot += s_internal[w];
         if (tot) atomicAdd(&counters[5], (unsigned long long)tot);
+        __threadfence();                                   // this block's cells and count are visible before the ticket
+        s_last = atomicAdd(done_ticket, 1u) == gridDim.x - 1u;
     }
-}
-
-// ---- top kernel: remaining levels (F-6 .. 0), one block, level by level through global memory ----
-template <bool SHARDED>
-__global__ void __launch_bounds__(1024)
-tree_top_kernel(TreeArrays t, Dims d, int top_level, const uint32_t* __restrict__ sidx,
-                const double2* __restrict__ pos, const double* __restrict__ mass, double G0, double mass_eps,
-                unsigned long long* __restrict__ counters, const StepConsts* __restrict__ consts) {
-    pdl_entry();
-    const int F = d.finest;
-    const double scale = consts->scale;
-    const double G = G0 * scale * scale;
-    __shared__ uint32_t s_int;
-    if (threadIdx.x == 0) s_int = 0;
     __syncthreads();
-    uint32_t n_internal = 0;
-    for (int level = top_level; level >= 0; --level) {
-        uint64_t ncells = 1ull << (2 * level);
-        uint64_t off = d.level_off[level], offc = d.level_off[level + 1];
-        for (uint64_t c = threadIdx.x; c < ncells; c += blockDim.x) {
-            Cell ch[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint64_t a = offc + 4 * c + q;
-                ch[q].m = t.mass[a]; ch[q].cx = t.comx[a]; ch[q].cy = t.comy[a];
-                ch[q].cnt = t.count[a]; ch[q].first = t.first[a];
-            }
-            Cell up = combine4<SHARDED>(ch, sidx, pos, mass, t.self_node, offc + 4 * c, true);
-            store_cell(t, off + c, up, level, F, G, mass_eps, scale, consts->thr2[level], sidx);
-            n_internal += (up.cnt >= 2u);
-        }
-        __syncthreads();   // level `level` complete and visible to the block
-    }
-    if (n_internal) atomicAdd(&s_int, n_internal);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // counters[5] holds internal cells counted by the bottom kernel
-        unsigned long long internal = counters[5] + s_int;
-        counters[4] = 1ull + 4ull * internal;   // quadtree.size() of the reference
+    if (s_last) {                                          // block-uniform: the last block finishes the pyramid
+        __threadfence();
+        if (tid == 0) *done_ticket = 0u;
+        int top_level = F - 5;                             // this kernel covered F .. F-4
+        if (top_level < 0) top_level = -1;                 // the bottom levels already reached the root: only the node count remains
+        tree_top_levels<SHARDED>(t, d, top_level, sidx, pos, mass, G, mass_eps, scale, counters, consts, &s_internal[0]);
     }
 }
 
@@ -475,30 +534,25 @@ void launch_tree_runs(const uint32_t* skeys, const uint32_t* sidx, const double2
     uint32_t exact_max = (uint32_t)(p.exact_leaf_max < 0 ? 0 : p.exact_leaf_max);
     if (n > 0) {
         launch_chain(cell_runs_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), st, true, skeys, n, cnt_f, first_f,
-                     exact_max, s.heavy_list, s.heavy_count);
+                     exact_max, s.heavy_list, s.heavy_count, s.huge_list, s.huge_count);
         ++g_launches;
     }
+    const unsigned hh_blocks = kHeavyBlocks + kHugeParts * kHugeSlots;
     if (sums) {
-        heavy_cells_kernel<<<148 * 4, 256, 0, st>>>(s.heavy_list, s.heavy_count, cnt_f, first_f, sidx, pos, mass,
-                                                    sums + nc, sums + 2 * nc, sums + 3 * nc, true, s.huge_list, s.huge_count);
-        huge_cells_kernel<<<dim3(kHugeParts, 16), 256, 0, st>>>(s.huge_list, s.huge_count, cnt_f, first_f, sidx, pos, mass,
-                                                                sums + nc, sums + 2 * nc, sums + 3 * nc, true,
-                                                                s.huge_partial, s.huge_tickets);
-        g_launches += 2;
+        heavy_huge_kernel<<<hh_blocks, 256, 0, st>>>(s.heavy_list, s.heavy_count, s.huge_list, s.huge_count, cnt_f, first_f,
+                                                     sidx, pos, mass, sums + nc, sums + 2 * nc, sums + 3 * nc, true,
+                                                     s.huge_partial, s.huge_tickets);
+        ++g_launches;
         cell_partial_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(cnt_f, first_f, nc, sidx, pos, mass, exact_max,
                                                                           sums);
         ++g_launches;
     } else {
         // (n > 0 here: the previous operation on the stream is cell_runs_kernel)
-        launch_chain(heavy_cells_kernel, dim3(148 * 4), dim3(256), st, n > 0, (const uint32_t*)s.heavy_list,
-                     (const uint32_t*)s.heavy_count, (const uint32_t*)cnt_f, (const uint32_t*)first_f, sidx, pos, mass,
-                     t.mass + d.level_off[F], t.comx + d.level_off[F], t.comy + d.level_off[F], false, s.huge_list,
-                     s.huge_count);
-        launch_chain(huge_cells_kernel, dim3(kHugeParts, 16), dim3(256), st, true, (const uint32_t*)s.huge_list,
-                     (const uint32_t*)s.huge_count, (const uint32_t*)cnt_f, (const uint32_t*)first_f, sidx, pos, mass,
-                     t.mass + d.level_off[F], t.comx + d.level_off[F], t.comy + d.level_off[F], false, s.huge_partial,
-                     s.huge_tickets);
-        g_launches += 2;
+        launch_chain(heavy_huge_kernel, dim3(hh_blocks), dim3(256), st, n > 0, (const uint32_t*)s.heavy_list,
+                     (const uint32_t*)s.heavy_count, (const uint32_t*)s.huge_list, (const uint32_t*)s.huge_count,
+                     (const uint32_t*)cnt_f, (const uint32_t*)first_f, sidx, pos, mass, t.mass + d.level_off[F],
+                     t.comx + d.level_off[F], t.comy + d.level_off[F], false, s.huge_partial, s.huge_tickets);
+        ++g_launches;
     }
 }
 
@@ -509,20 +563,12 @@ void launch_tree_levels(const uint32_t* sidx, const double2* pos, const double* 
     const int F = d.finest;
     uint32_t exact_max = (uint32_t)(p.exact_leaf_max < 0 ? 0 : p.exact_leaf_max);
     unsigned blocks = (unsigned)((d.ncells_finest + kBottomThreads - 1) / kBottomThreads);
+    // bbox_ticket is free again here (the bounds kernel resets it) — reused as the "blocks done" ticket
     if (sums) tree_bottom_kernel<true><<<blocks, kBottomThreads, 0, st>>>(t, d, sidx, pos, mass, p.G, p.mass_eps, exact_max,
-                                                                        s.counters, consts, sums);
+                                                                        s.counters, consts, sums, s.bbox_ticket);
     else launch_chain(tree_bottom_kernel<false>, dim3(blocks), dim3(kBottomThreads), st, true, t, d, sidx, pos, mass, p.G,
-                      p.mass_eps, exact_max, s.counters, consts, (const double*)nullptr);
+                      p.mass_eps, exact_max, s.counters, consts, (const double*)nullptr, s.bbox_ticket);
     ++g_launches;
-    int top_level = F - 5;   // bottom kernel covered F .. F-4
-    if (F >= 1) {
-        if (top_level < 0) top_level = -1;
-        // when the bottom kernel already reached the root (F <= 4) only the node count remains
-        if (sums) tree_top_kernel<true><<<1, 1024, 0, st>>>(t, d, top_level, sidx, pos, mass, p.G, p.mass_eps, s.counters, consts);
-        else launch_chain(tree_top_kernel<false>, dim3(1), dim3(1024), st, true, t, d, top_level, sidx, pos, mass, p.G,
-                          p.mass_eps, s.counters, consts);
-        ++g_launches;
-    }
 }
 
 void launch_tree(const uint32_t* skeys, const uint32_t* sidx, const double2* pos, const double* mass,

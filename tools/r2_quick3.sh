@@ -1,0 +1,6 @@
+#!/usr/bin/env bash
+set -u
+mkdir -p gpurun_out
+( timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 ) > gpurun_out/quick3_pytest.log
+for n in 1000000 16000000; do for t in x; do echo "== n $n"; timeout 300 python tools/profile_step.py --n $n --warmup 10 --steps 20 2>&1 | tail -1; done; done > gpurun_out/quick3_ab.log 2>&1
+tail -3 gpurun_out/quick3_pytest.log; cat gpurun_out/quick3_ab.log
