@@ -330,7 +330,7 @@ def run_ours(args):
     strong_only = args.total_bodies > 0
     n = args.total_bodies if strong_only else BODIES_PER_GPU * world
     K, W = args.steps, args.warmup
-    R = args.brackets if args.brackets > 0 else bracket_plan(K)
+    R = args.brackets if args.brackets > 0 else (3 if args.quick else bracket_plan(K))
 
     def barrier():
         if dist is not None:
@@ -442,6 +442,10 @@ def run_ours(args):
     sim.set_profiling(False)
     phases = {k: t[k] / max(t["steps"], 1) for k in ("bounds_keys_us", "sort_us", "build_us", "traverse_us",
                                                      "exchange_us", "total_us")}
+    phases_all = None
+    if dist is not None:      # every rank's phases (rank skew shows up as waiting time in the phases that exchange)
+        phases_all = [None] * world
+        dist.all_gather_object(phases_all, {k: round(v, 1) for k, v in phases.items()})
     # interactions of THIS rank's bodies: counting variant of the traversal kernel on a second context (multi-rank:
     # NCCL exchange, one step)
     simc = make_sim(n, world, counters=True, p2p=False)
@@ -510,7 +514,7 @@ def run_ours(args):
     for _ in range(max(1, min(W, 3))):
         sim.step_host(hp, hv, hm, hout)
     e2e_runs = []
-    for _ in range(max(3, min(R, 10))):
+    for _ in range(1 if args.quick else max(3, min(R, 10))):
         barrier()
         t0 = time.perf_counter()
         for _ in range(K):
@@ -648,7 +652,7 @@ def run_ours(args):
                            else "single GPU", "host_numa_node": numa, "host_numa_note": numa_why},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "accuracy": accuracy, "cpu_baseline": cpu_baseline, "gpu_baseline": gpu_baseline,
-                "phases_us": phases, "strong": strong, "direct": direct,
+                "phases_us": phases, "phases_us_all_ranks": phases_all, "strong": strong, "direct": direct,
                 "value_l2_flushed": n * K / (ms_flushed * 1e-3)}
         print(json.dumps(line), flush=True)
         if args.reference_lines:
@@ -681,9 +685,13 @@ def main():
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-reduces instead of the peer-memory exchange")
     ap.add_argument("--total-bodies", type=int, default=0,
                     help="strong scaling: total body count over all GPUs (default: weak scaling, 1M per GPU)")
+    ap.add_argument("--quick", action="store_true",
+                    help="headline brackets + phases only (no e2e, accuracy, baselines, strong, direct): scaling scripts")
     ap.add_argument("--reference-lines", action="store_true",
                     help="also print the reference program's two timing lines (for scripts/gpu_scaling_script.sh)")
     args = ap.parse_args()
+    if args.quick:
+        args.no_cpu_baseline = args.no_gpu_baseline = args.no_strong = args.no_direct = True
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

@@ -42,6 +42,7 @@ ABI_SYMBOLS = (
     "bh_dump_quadtree", "bh_get_counters", "bh_set_profiling", "bh_get_timers", "bh_reset_timers",
     "bh_last_step_ms", "bh_direct_forces", "bh_load_text", "bh_append_positions_txt", "bh_measure_fp32_peak",
     "bh_generate", "bh_generate_host", "bh_philox4x32_10", "bh_write_init_files",
+    "bh_trajectory_begin", "bh_trajectory_record", "bh_trajectory_end",
 )
 GENERATOR_KINDS = {"uniform_square": 0, "uniform_disk": 1, "plummer_2d": 2}   # BH_GEN_* of include/bh.h
 
@@ -132,6 +133,9 @@ def lib():
     L.bh_load_text.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, dp, dp, dp]
     L.bh_append_positions_txt.argtypes = [C.c_char_p, dp, C.c_int64, C.c_double, C.c_int]
     L.bh_measure_fp32_peak.argtypes = [C.c_int32, dp, dp]
+    L.bh_trajectory_begin.argtypes = [vp, C.c_char_p, C.c_int32]
+    L.bh_trajectory_record.argtypes = [vp, C.c_double]
+    L.bh_trajectory_end.argtypes = [vp]
     L.bh_generate.argtypes = [vp, C.c_int32, C.c_uint64]
     L.bh_generate_host.argtypes = [C.c_int32, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, dp, dp, dp]
     L.bh_philox4x32_10.argtypes = [u32p, u32p, u32p]
@@ -188,6 +192,13 @@ def generate_host(kind: str, n_bodies: int, seed: int = 12345, first: int = 0, r
     _check(lib().bh_generate_host(GENERATOR_KINDS[kind], seed, first, n_bodies, int(round6), pos.ctypes.data_as(dp),
                                   vel.ctypes.data_as(dp), mass.ctypes.data_as(dp)))
     return pos, vel, mass
+
+
+def append_positions_txt(path: str, pos, time: float, truncate: bool = False):
+    """savePositions (project.cu:855-863): append one frame "time i x y \\n" per body to `path` (synchronous)."""
+    pos = _f64(pos, (-1, 2))
+    _check(lib().bh_append_positions_txt(path.encode(), pos.ctypes.data_as(C.POINTER(C.c_double)), pos.shape[0],
+                                         float(time), 1 if truncate else 0))
 
 
 def philox4x32_10(counter, key):
@@ -412,6 +423,16 @@ class Simulation:
         ms = C.c_float()
         _check(lib().bh_last_step_ms(self._h, C.byref(ms)))
         return ms.value
+
+    # ---- trajectory output (positions.txt of plot_2d.py), asynchronous ----
+    def trajectory_begin(self, path: str, stride: int = 1):
+        _check(lib().bh_trajectory_begin(self._h, path.encode(), stride))
+
+    def trajectory_record(self, time: float):
+        _check(lib().bh_trajectory_record(self._h, C.c_double(time)))
+
+    def trajectory_end(self):
+        _check(lib().bh_trajectory_end(self._h))
 
     def direct_forces(self, want_output: bool = True):
         ms = C.c_float()

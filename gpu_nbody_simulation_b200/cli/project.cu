@@ -17,8 +17,9 @@
 // SURVEY §2.1).  Differences from the reference, all opt-in or documented in DESIGN.md:
 //   * initial conditions come from the three text files (the reference's README toggle); if they
 //     are absent, a SEEDED uniform square (bh_generate_host, project.cu:30-35 ranges) replaces the time-seeded cuRAND;
-//   * -DBH_POSITIONS_TXT=1 also writes the trajectory file positions.txt that plot_2d.py reads
-//     (format of savePositions, project.cu:855-863), which the reference's GPU path never writes;
+//   * -DBH_POSITIONS_TXT=1 [-DBH_POSITIONS_STRIDE=k] also writes the trajectory file positions.txt that plot_2d.py
+//     reads (format of savePositions, project.cu:855-863), which the reference's GPU path never writes: one open
+//     file, every k-th state, copied and formatted asynchronously (bh_trajectory_*);
 //   * cap-level single leaves print the occupant's real position (reference: out-of-bounds read).
 #ifndef N_BODIES
 #define N_BODIES (1000 * 40)
@@ -43,6 +44,9 @@
 #endif
 #ifndef BH_POSITIONS_TXT
 #define BH_POSITIONS_TXT 0
+#endif
+#ifndef BH_POSITIONS_STRIDE
+#define BH_POSITIONS_STRIDE 1     // with BH_POSITIONS_TXT: write every k-th state (t = 0, k, 2k, ... steps)
 #endif
 #ifndef BH_FP64
 #define BH_FP64 0
@@ -98,7 +102,10 @@ int main() {
     if (bh_set_bodies(ctx, pos.data(), vel.data(), mass.data()) != BH_OK) die("bh_set_bodies");
     if (bh_set_profiling(ctx, 1) != BH_OK) die("bh_set_profiling");
     double t = 0.0;
-    if (BH_POSITIONS_TXT) bh_append_positions_txt("positions.txt", pos.data(), n, t, 1);
+    if (BH_POSITIONS_TXT) {
+        if (bh_trajectory_begin(ctx, "positions.txt", BH_POSITIONS_STRIDE) != BH_OK) die("bh_trajectory_begin");
+        if (bh_trajectory_record(ctx, t) != BH_OK) die("bh_trajectory_record");           // project.cu:879
+    }
     for (int step = 0; step < n_steps; ++step) {
         t += DELTA_T;                                                            // project.cu:956
         const bool first = step == 0, last = step == n_steps - 1 && step != 0;   // project.cu:962-965
@@ -108,11 +115,9 @@ int main() {
                 die("bh_dump_quadtree");
         }
         if (bh_step(ctx, 1) != BH_OK) die("bh_step");
-        if (BH_POSITIONS_TXT) {
-            if (bh_get_positions(ctx, pos.data()) != BH_OK) die("bh_get_positions");
-            bh_append_positions_txt("positions.txt", pos.data(), n, t, 0);
-        }
+        if (BH_POSITIONS_TXT && bh_trajectory_record(ctx, t) != BH_OK) die("bh_trajectory_record");   // project.cu:907
     }
+    if (BH_POSITIONS_TXT && bh_trajectory_end(ctx) != BH_OK) die("bh_trajectory_end");
     if (bh_get_positions(ctx, pos.data()) != BH_OK) die("bh_get_positions");     // project.cu:1010
     bh_timers tm;
     bh_get_timers(ctx, &tm);

@@ -144,6 +144,13 @@ struct bh_ctx {
     bool bodies_set = false, tree_valid = false, have_snapshot = false, timed = false;
     bool tree_built = false;         // some tree has been built (node count / root box of the last build stay readable after a step)
     uint64_t zero_mass_bodies = 0;   // counted on the host by bh_set_bodies (see bh_counters)
+    // trajectory output (bh_trajectory_*): two device snapshots + two pinned host buffers, background writer
+    FrameWriter* traj = nullptr;
+    double2* traj_dev[2] = {nullptr, nullptr};
+    double* traj_host[2] = {nullptr, nullptr};
+    cudaEvent_t traj_snap[2] = {nullptr, nullptr}, traj_ready[2] = {nullptr, nullptr};
+    int traj_stride = 1, traj_slot = 0;
+    int64_t traj_calls = 0;
     size_t step_zero_bytes = 0;      // see zero_scratch
     bool pdl = false;                // env BH_PDL=1: programmatic dependent launch along the single-GPU chain
     bool keys_table = false;         // env BH_KEYS_TABLE=1: cell keys from the boundary table instead of per-body bisection
@@ -289,6 +296,7 @@ int enqueue_build(bh_ctx* c, bool full = false, const double2* src = nullptr, cu
         if (mass_ready) cudaStreamWaitEvent(c->stream, mass_ready, 0);
         launch_tree_runs(c->keys[c->sorted], c->idx[c->sorted], src, c->mass, n_own, c->p, c->d, c->tree, c->s,
                          c->cell_sums, c->stream);
+        prof_mark(c, 6);
         const double* reduced = c->cell_sums;
         if (c->p2p_ready) {   // reduce-scatter + all-gather by direct peer stores, summed in rank order
             launch_peer_allreduce_cells(c->pc, c->cell_sums, c->stream);
@@ -296,6 +304,7 @@ int enqueue_build(bh_ctx* c, bool full = false, const double2* src = nullptr, cu
         } else {
             BH_TRY(allreduce_f64(c, c->cell_sums, 4 * c->d.ncells_finest, ncclSum));
         }
+        prof_mark(c, 7);
         launch_tree_levels(c->idx[c->sorted], src, c->mass, c->p, c->d, c->tree, c->s, c->consts, reduced, c->stream);
         c->tree_full = false;
     }
@@ -351,7 +360,12 @@ void accumulate_profile(bh_ctx* c) {
     c->timers.sort_us += ms[1] * 1e3;
     c->timers.build_us += ms[2] * 1e3;
     c->timers.traverse_us += ms[3] * 1e3;   // traversal with the fused integrator
-    c->timers.exchange_us += ms[4] * 1e3;
+    if (c->p.n_ranks > 1 && !c->tree_full) {   // sharded build: the per-cell sum exchange is the middle part of the build phase
+        float ex = 0.f;
+        cudaEventElapsedTime(&ex, c->pev[6], c->pev[7]);
+        c->timers.exchange_us += ex * 1e3;
+        c->timers.build_us -= ex * 1e3;
+    }
     c->timers.total_us += (ms[0] + ms[1] + ms[2] + ms[3] + ms[4]) * 1e3;
     c->timers.steps += 1;
 }
@@ -647,6 +661,7 @@ int bh_create(const bh_params* p, bh_ctx** out) {
 int bh_destroy(bh_ctx* c) {
     if (!c) return BH_OK;
     DeviceGuard g(c->device);
+    if (c->traj) bh_trajectory_end(c);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& gr : c->graph) if (gr) cudaGraphExecDestroy(gr);
     if (c->comm) { NcclApi* api = nccl_api(); if (api) api->CommDestroy(c->comm); }
@@ -1138,6 +1153,60 @@ int bh_load_text(const char* mf, const char* pf, const char* vf, int64_t n, doub
 
 int bh_append_positions_txt(const char* path, const double* pos, int64_t n, double time, int truncate) {
     return append_positions_txt(path, pos, n, time, truncate);
+}
+
+int bh_trajectory_begin(bh_ctx* c, const char* path, int32_t stride) {
+    if (!c || !path || stride < 1) { set_error("bh_trajectory_begin: bad arguments"); return BH_ERR_INVALID; }
+    if (c->p.n_ranks > 1) { set_error("bh_trajectory_begin: single-rank contexts only"); return BH_ERR_INVALID; }
+    if (c->traj) { set_error("bh_trajectory_begin: a trajectory is already open"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    const size_t n = (size_t)c->d.n;
+    for (int k = 0; k < 2; ++k) {
+        if (!c->traj_dev[k]) BH_TRY(dev_alloc(&c->traj_dev[k], n));
+        if (!c->traj_host[k]) BH_CUDA_OK(cudaMallocHost((void**)&c->traj_host[k], sizeof(double2) * n));
+        if (!c->traj_snap[k]) BH_CUDA_OK(cudaEventCreateWithFlags(&c->traj_snap[k], cudaEventDisableTiming));
+        if (!c->traj_ready[k]) BH_CUDA_OK(cudaEventCreateWithFlags(&c->traj_ready[k], cudaEventDisableTiming));
+    }
+    c->traj = new FrameWriter(path, c->d.n, c->device);
+    if (!c->traj->ok()) { delete c->traj; c->traj = nullptr; return BH_ERR_IO; }
+    c->traj_stride = stride; c->traj_slot = 0; c->traj_calls = 0;
+    return BH_OK;
+}
+
+int bh_trajectory_record(bh_ctx* c, double time) {
+    if (!c || !c->traj) { set_error("bh_trajectory_record: no open trajectory"); return BH_ERR_INVALID; }
+    if (!c->bodies_set) { set_error("bh_trajectory_record: no bodies"); return BH_ERR_INVALID; }
+    if ((c->traj_calls++ % c->traj_stride) != 0) return BH_OK;
+    DeviceGuard g(c->device);
+    const int k = c->traj_slot;
+    c->traj_slot ^= 1;
+    c->traj->acquire(k);        // the frame two records ago has left this buffer (back-pressure if the disk is slower)
+    // device snapshot on the compute stream (the next step's integrator overwrites c->pos in place), then the
+    // device-to-host copy on the side stream, overlapping the following steps
+    BH_CUDA_OK(cudaMemcpyAsync(c->traj_dev[k], c->pos, sizeof(double2) * c->d.n, cudaMemcpyDeviceToDevice, c->stream));
+    BH_CUDA_OK(cudaEventRecord(c->traj_snap[k], c->stream));
+    BH_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->traj_snap[k], 0));
+    BH_CUDA_OK(cudaMemcpyAsync(c->traj_host[k], c->traj_dev[k], sizeof(double2) * c->d.n, cudaMemcpyDeviceToHost, c->copy_stream));
+    BH_CUDA_OK(cudaEventRecord(c->traj_ready[k], c->copy_stream));
+    c->traj->submit(k, c->traj_host[k], time, (void*)c->traj_ready[k]);
+    return BH_OK;
+}
+
+int bh_trajectory_end(bh_ctx* c) {
+    if (!c || !c->traj) { set_error("bh_trajectory_end: no open trajectory"); return BH_ERR_INVALID; }
+    DeviceGuard g(c->device);
+    c->traj->finish();
+    const bool ok = c->traj->ok();
+    delete c->traj;
+    c->traj = nullptr;
+    for (int k = 0; k < 2; ++k) {
+        if (c->traj_dev[k]) { cudaFree(c->traj_dev[k]); c->traj_dev[k] = nullptr; }
+        if (c->traj_host[k]) { cudaFreeHost(c->traj_host[k]); c->traj_host[k] = nullptr; }
+        if (c->traj_snap[k]) { cudaEventDestroy(c->traj_snap[k]); c->traj_snap[k] = nullptr; }
+        if (c->traj_ready[k]) { cudaEventDestroy(c->traj_ready[k]); c->traj_ready[k] = nullptr; }
+    }
+    if (!ok) { set_error("trajectory file: write failed"); return BH_ERR_IO; }
+    return BH_OK;
 }
 
 int bh_measure_fp32_peak(int32_t device, double* tflops, double* mhz) {

@@ -1,12 +1,18 @@
 // Host-side text formats of the reference and the canonical (reference-equivalent) node table.
 #include "host_io.h"
 
+#include <cuda_runtime.h>
+
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <fstream>
+#include <mutex>
 #include <sstream>
 #include <string>
+#include <thread>
 
 #include "../../include/bh.h"
 
@@ -146,6 +152,87 @@ double round6(double v) {
     char buf[64];
     snprintf(buf, sizeof buf, "%.6g", v);
     return strtod(buf, nullptr);
+}
+
+
+// ---- background trajectory writer ---------------------------------------------------------------------------------
+struct FrameWriter::Impl {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    struct Job { int slot; const double* host; double time; void* ev; };
+    std::deque<Job> q;
+    bool busy[2] = {false, false};
+    bool stop = false;
+    int64_t n = 0;
+    int device = 0;
+};
+
+FrameWriter::FrameWriter(const char* path, int64_t n, int device) : impl_(new Impl), f_(fopen(path, "w")) {
+    impl_->n = n; impl_->device = device;
+    if (!f_) { set_error("cannot open %s", path); return; }
+    setvbuf((FILE*)f_, nullptr, _IOFBF, 1 << 22);
+    impl_->th = std::thread([this] {
+        cudaSetDevice(impl_->device);
+        std::string text;
+        for (;;) {
+            Impl::Job job;
+            {
+                std::unique_lock<std::mutex> lk(impl_->mu);
+                impl_->cv.wait(lk, [this] { return impl_->stop || !impl_->q.empty(); });
+                if (impl_->q.empty()) return;
+                job = impl_->q.front();
+            }
+            if (job.ev && cudaEventSynchronize((cudaEvent_t)job.ev) != cudaSuccess) failed_ = true;
+            // savePositions, project.cu:855-863: std::to_string == "%f" for double, "%d" for int; trailing space
+            text.clear();
+            char line[128];
+            for (int64_t i = 0; i < impl_->n; ++i) {
+                const int len = snprintf(line, sizeof line, "%f %lld %f %f \n", job.time, (long long)i, job.host[2 * i],
+                                         job.host[2 * i + 1]);
+                text.append(line, (size_t)len);
+                if (text.size() > (1u << 20)) { if (fwrite(text.data(), 1, text.size(), (FILE*)f_) != text.size()) failed_ = true; text.clear(); }
+            }
+            if (!text.empty() && fwrite(text.data(), 1, text.size(), (FILE*)f_) != text.size()) failed_ = true;
+            {
+                std::lock_guard<std::mutex> lk(impl_->mu);
+                impl_->q.pop_front();
+                impl_->busy[job.slot] = false;
+            }
+            impl_->cv.notify_all();
+        }
+    });
+}
+
+void FrameWriter::acquire(int slot) {
+    std::unique_lock<std::mutex> lk(impl_->mu);
+    impl_->cv.wait(lk, [&] { return !impl_->busy[slot]; });
+}
+
+void FrameWriter::submit(int slot, const double* host, double time, void* ready_event) {
+    {
+        std::lock_guard<std::mutex> lk(impl_->mu);
+        impl_->busy[slot] = true;
+        impl_->q.push_back({slot, host, time, ready_event});
+    }
+    impl_->cv.notify_all();
+}
+
+void FrameWriter::finish() {
+    std::unique_lock<std::mutex> lk(impl_->mu);
+    impl_->cv.wait(lk, [this] { return impl_->q.empty(); });
+    if (f_) fflush((FILE*)f_);
+}
+
+FrameWriter::~FrameWriter() {
+    if (impl_->th.joinable()) {
+        finish();
+        { std::lock_guard<std::mutex> lk(impl_->mu); impl_->stop = true; }
+        impl_->cv.notify_all();
+        impl_->th.join();
+    }
+    if (f_) fclose((FILE*)f_);
+    delete impl_;
 }
 
 }  // namespace bh

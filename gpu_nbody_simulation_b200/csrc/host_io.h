@@ -27,4 +27,24 @@ int write_init_files(const char* mf, const char* pf, const char* vf, int64_t n, 
                      const double* vel);
 double round6(double v);   // value after a round trip through the "%.6g" text format
 
+// Trajectory file (savePositions format, project.cu:855-863) written by a background thread: the producer hands over
+// frames (n bodies in a pinned host buffer, a time stamp, the CUDA event recorded after the copy into the buffer); the
+// thread waits for the event, formats the frame and appends it to ONE open file while the producer keeps stepping.
+class FrameWriter {
+public:
+    FrameWriter(const char* path, int64_t n, int device);
+    ~FrameWriter();                        // flushes, joins
+    bool ok() const { return f_ != nullptr && !failed_; }
+    // blocks until buffer `slot` (0 / 1) is no longer being written out
+    void acquire(int slot);
+    // queue buffer `slot` = host positions [n][2]; `ready` is a cudaEvent_t recorded after the copy into it
+    void submit(int slot, const double* host, double time, void* ready_event);
+    void finish();                         // wait until everything queued is on disk
+private:
+    struct Impl;
+    Impl* impl_;
+    void* f_;
+    bool failed_ = false;
+};
+
 }  // namespace bh

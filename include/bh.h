@@ -202,6 +202,18 @@ int bh_load_text(const char* masses_file, const char* positions_file, const char
 /* savePositions project.cu:855-863: appends "time i x y \n" (std::to_string, 6 decimals) */
 int bh_append_positions_txt(const char* path, const double* pos_xy_host, int64_t n, double time, int truncate);
 
+/* ---- trajectory output: the file plot_2d.py reads, format of savePositions (project.cu:855-863:
+ * one "time i x y \n" line per body and frame, std::to_string formatting).  The reference's CPU programs rebuild and
+ * append the whole file synchronously; here ONE file stays open, every `stride`-th recorded state is snapshotted on
+ * the device (10 us at 1M bodies), copied to one of two pinned host buffers on a side stream and formatted by a
+ * background thread while the simulation keeps stepping (at 1M bodies x 1000 steps an unstrided file would be 40 GB,
+ * SURVEY H7).  Single-rank contexts. ---- */
+int bh_trajectory_begin(bh_ctx* ctx, const char* path, int32_t stride);
+/* call once for the initial state (time 0, project.cu:879) and once after every step (project.cu:907): the 1st,
+ * (1 + stride)-th, ... calls are written; returns as soon as the copies are enqueued */
+int bh_trajectory_record(bh_ctx* ctx, double time);
+int bh_trajectory_end(bh_ctx* ctx);   /* waits until every recorded frame is on disk, closes the file */
+
 /* ---- measurement helpers ---- */
 /* FP32 FMA peak of the device measured with a register-resident FMA loop, in TFLOP/s */
 int bh_measure_fp32_peak(int32_t device, double* tflops, double* sm_clock_mhz_est);

@@ -14,7 +14,7 @@ for n_b in "${bodies[@]}"; do
         for ((i=1; i<=repeats; i++)); do
             if [ "$g" -eq 1 ]; then launcher="python"; else
                 launcher="python -m torch.distributed.run --nnodes=1 --nproc-per-node $g --master-addr 127.0.0.1 --master-port $((29500 + g))"; fi
-            line=$($launcher "$here/../bench.py" --gpus $g --steps $steps --total-bodies $n_b --no-cpu-baseline --reference-lines | tail -1)
+            line=$($launcher "$here/../bench.py" --gpus $g --steps $steps --total-bodies $n_b --quick --reference-lines | tail -1)
             echo "$n_b, $g, $steps, $line" >> $output
             echo "n_bodies=$n_b gpus=$g repeat $i/$repeats: $line"
         done

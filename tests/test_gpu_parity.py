@@ -426,6 +426,69 @@ def test_cli_project_drop_in(tmp_path):
     assert np.allclose(traj[:n, 2:], np.round(p, 6), atol=1e-6)
 
 
+def test_trajectory_writer_async_strided_equals_synchronous_append(tmp_path):
+    """positions.txt (savePositions format, project.cu:855-863; what plot_2d.py:3-14 reads) written by
+    the asynchronous strided writer (one open file, device snapshot + pinned double buffer + background thread) is byte
+    for byte what the synchronous per-step append (pinned against the reference's savePositions in tests/test_abi.py)
+    gives for the same states."""
+    import gpu_nbody_simulation_b200 as bh
+    pos, vel, mass, _ = golden_inputs("shipped_40000")
+    n, steps, stride = 20000, 7, 3
+    pos, vel, mass = pos[:n], vel[:n], mass[:n]
+    kw = dict(G=6.67e-11 * 1e-6)                      # gentle dynamics: finite, changing positions every step
+    a_path, b_path = str(tmp_path / "async.txt"), str(tmp_path / "sync.txt")
+    with Simulation(n, **kw) as sim:
+        sim.set_bodies(pos, vel, mass)
+        sim.trajectory_begin(a_path, stride)
+        sim.trajectory_record(0.0)
+        for s in range(steps):
+            sim.step(1)
+            sim.trajectory_record(float(s + 1))
+        sim.trajectory_end()
+    with Simulation(n, **kw) as sim:
+        sim.set_bodies(pos, vel, mass)
+        bh.append_positions_txt(b_path, sim.positions(), 0.0, truncate=True)
+        for s in range(steps):
+            sim.step(1)
+            if (s + 1) % stride == 0:
+                bh.append_positions_txt(b_path, sim.positions(), float(s + 1), truncate=False)
+    a, b = open(a_path, "rb").read(), open(b_path, "rb").read()
+    assert a == b and a.count(b"\n") == n * (1 + steps // stride)
+    with Simulation(n, rank=0, n_ranks=1) as sim:      # misuse is an error, not a crash
+        with pytest.raises(bh.BhError):
+            sim.trajectory_record(0.0)
+
+
+def test_gpu_scaling_script_feeds_the_reference_plot_regexes(tmp_path):
+    """scripts/gpu_scaling_script.sh (the reference's first_scaling_script.sh shape with GPUs in the
+    n_threads column) produces a results file that the parser of plot_first_scale.py (regexes at :55-59, restated here —
+    matplotlib is not installed, the script cannot be imported) reads: one configuration line and the two timing
+    sentences per run."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BODIES="200000", GPUS="1", REPEATS="2", STEPS="5")
+    subprocess.run(["bash", os.path.join(root, "scripts", "gpu_scaling_script.sh")], cwd=str(tmp_path), env=env, check=True,
+                   capture_output=True, text=True, timeout=600)
+    line_thread_regex = re.compile(r"^\s*(\d+)\s*,\s*([^,]+)\s*,\s*(\d+)\s*,")                 # plot_first_scale.py:55
+    parallel_regex = re.compile(r"GPU parallel computation took\s+(\d+)\s+microseconds")          # :58
+    total_regex = re.compile(r"GPU total computation took\s+(\d+)\s+milliseconds\.")              # :59
+    par, tot = {}, {}
+    for line in open(tmp_path / "gpu_scaling_results.txt"):
+        line = line.strip()
+        if not line or "n_bodies" in line.lower():
+            continue
+        m = line_thread_regex.search(line)
+        assert m and int(m.group(1)) == 200000 and int(m.group(3)) == 5
+        threads = m.group(2).strip()
+        mp, mt = parallel_regex.search(line), total_regex.search(line)
+        assert mp and mt, line
+        par.setdefault(threads, []).append(int(mp.group(1)))
+        tot.setdefault(threads, []).append(int(mt.group(1)))
+    assert list(par) == ["1"] and len(par["1"]) == 2 and min(par["1"]) > 0 and len(tot["1"]) == 2
+
+
 def test_step_host_pipelined_equals_plain_sequence():
     pos, vel, mass, _ = golden_inputs("shipped_40000")
     with Simulation(40000) as a, Simulation(40000) as b:

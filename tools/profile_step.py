@@ -20,10 +20,18 @@ ap.add_argument("--max-depth", type=int, default=10)
 ap.add_argument("--bpl", type=int, default=0)
 ap.add_argument("--exact-eps", action="store_true")
 ap.add_argument("--exact-leaves", action="store_true", help="BH_FLAG_EXACT_LEAVES (extension)")
+ap.add_argument("--presort", action="store_true", help="hand the bodies over in Morton order of the initial distribution")
 ap.add_argument("--warmup", type=int, default=0, help="untimed steps before the profiled ones (A/B timing: use >= 10)")
 a = ap.parse_args()
 gen = {"disk": ic.uniform_disk, "plummer": ic.plummer_2d, "square": ic.uniform_square}[a.dist]
 pos, vel, mass = gen(a.n, seed=12345, round6=False)
+if a.presort:
+    import numpy as np
+    with bh.Simulation(a.n, max_depth=a.max_depth) as tmp:
+        tmp.set_bodies(pos, vel, mass)
+        tmp.build_tree()
+        order = tmp.sorted_order().astype(np.int64)
+    pos, vel, mass = np.ascontiguousarray(pos[order]), np.ascontiguousarray(vel[order]), np.ascontiguousarray(mass[order])
 with bh.Simulation(a.n, graph=False, fp64=a.fp64, counters=a.counters, max_depth=a.max_depth, bodies_per_lane=a.bpl, exact_eps=a.exact_eps,
                    exact_leaves=a.exact_leaves) as sim:
     sim.set_bodies(pos, vel, mass)
