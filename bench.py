@@ -154,10 +154,56 @@ def pin_to_gpu_numa_node(dev):
     return pin_to_gpu_numa_node_why(dev)[0]
 
 
+def probe_best_numa_node(dev, mb=64):
+    """When sysfs does not name the GPU's node: measure it.  For every NUMA node with CPUs in this process's cpuset, bind
+    to its CPUs, allocate a pinned buffer there (first touch) and time a host-to-device copy; the fastest node wins.
+    Returns (node, {node: GB/s}) or (None, reason)."""
+    import glob
+    import torch
+    nodes = {}
+    for d in sorted(glob.glob("/sys/devices/system/node/node[0-9]*")):
+        try:
+            cpus = set()
+            for part in open(os.path.join(d, "cpulist")).read().strip().split(","):
+                if part:
+                    lo, _, hi = part.partition("-")
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                nodes[int(os.path.basename(d)[4:])] = cpus
+        except (OSError, ValueError):
+            continue
+    if len(nodes) < 2:
+        return None, f"{len(nodes)} NUMA node(s) with CPUs of this cpuset: nothing to choose"
+    before = os.sched_getaffinity(0)
+    rates = {}
+    dst = torch.empty(mb << 20, dtype=torch.uint8, device=f"cuda:{dev}")
+    for node, cpus in nodes.items():
+        os.sched_setaffinity(0, cpus)
+        src = torch.empty(mb << 20, dtype=torch.uint8).pin_memory()
+        src.fill_(1)                                             # first touch on this node
+        dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        rates[node] = 4 * (mb << 20) / (time.perf_counter() - t0) / 1e9
+        del src
+    os.sched_setaffinity(0, before)
+    best = max(rates, key=rates.get)
+    return best, {k: round(v, 1) for k, v in rates.items()}
+
+
 def pin_to_gpu_numa_node_why(dev):
     node, why = numa_node_of_gpu(dev)
     if node is None:
-        return None, why
+        try:
+            node, rates = probe_best_numa_node(dev)
+        except Exception as e:
+            node, rates = None, f"probe failed: {type(e).__name__}: {e}"
+        if node is None:
+            return None, f"{why}; probe: {rates}"
+        why = f"sysfs names no node; measured H2D GB/s per node {rates}"
     try:
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
@@ -167,7 +213,7 @@ def pin_to_gpu_numa_node_why(dev):
         if not cpus:
             return None, f"node {node}: none of its CPUs is in this process's cpuset"
         os.sched_setaffinity(0, cpus)
-        return node, f"bound to the {len(cpus)} CPUs of node {node}"
+        return node, f"bound to the {len(cpus)} CPUs of node {node} ({why})"
     except Exception as e:
         return None, f"node {node}: {type(e).__name__}: {e}"
 

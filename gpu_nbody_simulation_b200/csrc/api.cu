@@ -82,6 +82,32 @@ static void nccl_load() {
         }                                                                                       \
     } while (0)
 
+// ---- resident Morton order: kernels (see bh_ctx::perm) ----
+__global__ void __launch_bounds__(256)
+reorder_gather_kernel(const uint32_t* __restrict__ sidx, int64_t n, const double2* __restrict__ pos,
+                      const double2* __restrict__ vel, const double2* __restrict__ acc, const double2* __restrict__ force,
+                      const double* __restrict__ mass, const uint32_t* __restrict__ perm, double2* __restrict__ o2,
+                      double* __restrict__ o1, uint32_t* __restrict__ ou) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t b = sidx[j];
+    o2[j] = pos[b]; o2[n + j] = vel[b]; o2[2 * n + j] = acc[b]; o2[3 * n + j] = force[b];
+    o1[j] = mass[b];
+    ou[j] = perm ? perm[b] : b;
+}
+// out[perm[j]] = in[j]  (internal -> original order)
+__global__ void __launch_bounds__(256)
+unpermute2_kernel(const double2* __restrict__ in, const uint32_t* __restrict__ perm, int64_t n, double2* __restrict__ out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[perm[j]] = in[j];
+}
+// out[j] = in[perm[j]]  (original -> internal order)
+__global__ void __launch_bounds__(256)
+permute2_kernel(const double2* __restrict__ in, const uint32_t* __restrict__ perm, int64_t n, double2* __restrict__ out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[j] = in[perm[j]];
+}
+
 }  // namespace bh
 
 using namespace bh;
@@ -144,6 +170,17 @@ struct bh_ctx {
     bool bodies_set = false, tree_valid = false, have_snapshot = false, timed = false;
     bool tree_built = false;         // some tree has been built (node count / root box of the last build stay readable after a step)
     uint64_t zero_mass_bodies = 0;   // counted on the host by bh_set_bodies (see bh_counters)
+    // Resident Morton order (single rank): the body arrays are physically re-sorted into the order of the last sort
+    // from time to time, so that "body index" ~ "sorted position": the per-body gathers / scatters of the build
+    // and of the traversal prologue / epilogue become (nearly) coalesced.  `perm` maps the internal index to the
+    // caller's original index; setters and getters go through it, so the C-ABI keeps its ORIGINAL-order contract.
+    uint32_t* perm = nullptr;        // [n]; meaningful only while !perm_identity
+    bool perm_identity = true;
+    bool auto_reorder = true;        // env BH_REORDER=0 disables; always off in FP64 mode and multi-rank contexts
+    int steps_since_reorder = 0;
+    double2* ro_tmp2 = nullptr;      // [4][n] double2: gather targets of pos, vel, acc, force
+    double* ro_tmp1 = nullptr;       // [n]
+    uint32_t* ro_tmpu = nullptr;     // [n]
     // trajectory output (bh_trajectory_*): two device snapshots + two pinned host buffers, background writer
     FrameWriter* traj = nullptr;
     double2* traj_dev[2] = {nullptr, nullptr};
@@ -193,6 +230,8 @@ int dev_alloc(T** ptr, size_t count) {
 }
 
 #define BH_TRY(expr) do { int rc__ = (expr); if (rc__ != BH_OK) return rc__; } while (0)
+
+constexpr int kReorderEvery = 16;   // steps between two physical re-sorts of the body arrays (resident Morton order)
 
 struct DeviceGuard {
     int prev = -1;
@@ -263,7 +302,8 @@ int allreduce_f64(bh_ctx* c, double* buf, size_t count, ncclRedOp_t op) {
 // (out-of-place step: every kernel reads the snapshot, only the fused integrator writes c->pos / c->vel,
 // so no restore copy is needed).
 // `mass_ready` (optional, pipelined host step): event to wait for before the first kernel that reads masses.
-int enqueue_build(bh_ctx* c, bool full = false, const double2* src = nullptr, cudaEvent_t mass_ready = nullptr) {
+int enqueue_build(bh_ctx* c, bool full = false, const double2* src = nullptr, cudaEvent_t mass_ready = nullptr);
+int enqueue_build(bh_ctx* c, bool full, const double2* src, cudaEvent_t mass_ready) {
     if (!src) src = c->pos;
     g_pdl = c->pdl;
     zero_scratch(c);
@@ -294,18 +334,15 @@ int enqueue_build(bh_ctx* c, bool full = false, const double2* src = nullptr, cu
         launch_sort(c->keys, c->idx, n_own, c->sp_own, c->s, &c->sorted, c->stream, (uint32_t)lo);
         prof_mark(c, 2);
         if (mass_ready) cudaStreamWaitEvent(c->stream, mass_ready, 0);
+        const PeerComm* pc = c->p2p_ready ? &c->pc : nullptr;
+        // peer exchange: the partial sums of the non-empty cells go straight into every rank's inbox, the level pass
+        // adds the contributions in rank order; otherwise one NCCL all-reduce of the dense sums
         launch_tree_runs(c->keys[c->sorted], c->idx[c->sorted], src, c->mass, n_own, c->p, c->d, c->tree, c->s,
-                         c->cell_sums, c->stream);
+                         c->cell_sums, c->stream, pc);
         prof_mark(c, 6);
-        const double* reduced = c->cell_sums;
-        if (c->p2p_ready) {   // reduce-scatter + all-gather by direct peer stores, summed in rank order
-            launch_peer_allreduce_cells(c->pc, c->cell_sums, c->stream);
-            reduced = reinterpret_cast<const double*>(c->comm_buf + c->pc.off_sums);
-        } else {
-            BH_TRY(allreduce_f64(c, c->cell_sums, 4 * c->d.ncells_finest, ncclSum));
-        }
+        if (!pc) BH_TRY(allreduce_f64(c, c->cell_sums, 4 * c->d.ncells_finest, ncclSum));
         prof_mark(c, 7);
-        launch_tree_levels(c->idx[c->sorted], src, c->mass, c->p, c->d, c->tree, c->s, c->consts, reduced, c->stream);
+        launch_tree_levels(c->idx[c->sorted], src, c->mass, c->p, c->d, c->tree, c->s, c->consts, c->cell_sums, c->stream, pc);
         c->tree_full = false;
     }
     prof_mark(c, 3);
@@ -370,6 +407,9 @@ void accumulate_profile(bh_ctx* c) {
     c->timers.steps += 1;
 }
 
+bool reorder_allowed(const bh_ctx* c);
+int enqueue_reorder(bh_ctx* c);
+
 int run_steps(bh_ctx* c, int nsteps, bool from_snapshot) {
     if (!c->bodies_set) { set_error("bh_step before bh_set_bodies"); return BH_ERR_INVALID; }
     if (from_snapshot && !c->have_snapshot) { set_error("no snapshot taken"); return BH_ERR_INVALID; }
@@ -394,11 +434,14 @@ int run_steps(bh_ctx* c, int nsteps, bool from_snapshot) {
             cudaGraphDestroy(graph);
         }
         for (int s = 0; s < nsteps; ++s) {
+            if (!from_snapshot && reorder_allowed(c) && ++c->steps_since_reorder > kReorderEvery) BH_TRY(enqueue_reorder(c));
             BH_CUDA_OK(cudaGraphLaunch(c->graph[gi], c->stream));
             g_launches += c->graph_kernels[gi];
         }
     } else {
         for (int s = 0; s < nsteps; ++s) {
+            if (!from_snapshot && reorder_allowed(c) && !c->profiling && ++c->steps_since_reorder > kReorderEvery)
+                BH_TRY(enqueue_reorder(c));
             BH_TRY(enqueue_step(c, from_snapshot));
             accumulate_profile(c);
         }
@@ -411,11 +454,61 @@ int run_steps(bh_ctx* c, int nsteps, bool from_snapshot) {
     return BH_OK;
 }
 
+// ---- resident Morton order -----------------------------------------------------------------------------------------
+int reorder_alloc(bh_ctx* c) {
+    const size_t n = (size_t)c->d.n;
+    if (!c->ro_tmp2) BH_TRY(dev_alloc(&c->ro_tmp2, 4 * n));
+    if (!c->ro_tmp1) BH_TRY(dev_alloc(&c->ro_tmp1, n));
+    if (!c->ro_tmpu) BH_TRY(dev_alloc(&c->ro_tmpu, n));
+    if (!c->perm) BH_TRY(dev_alloc(&c->perm, n));
+    return BH_OK;
+}
+
+bool reorder_allowed(const bh_ctx* c) {
+    return c->auto_reorder && c->p.n_ranks == 1 && !(c->p.flags & BH_FLAG_FP64_TRAVERSAL);
+}
+
+// Sort the bodies by their current cell keys and move the state arrays into that order (asynchronous on the stream).
+int enqueue_reorder(bh_ctx* c) {
+    BH_TRY(reorder_alloc(c));
+    BH_TRY(enqueue_build(c, false, nullptr, nullptr));
+    const int64_t n = c->d.n;
+    reorder_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+        c->idx[c->sorted], n, c->pos, c->vel, c->acc, c->force, c->mass, c->perm_identity ? nullptr : c->perm, c->ro_tmp2,
+        c->ro_tmp1, c->ro_tmpu);
+    ++g_launches;
+    BH_TRY(check_launch());
+    const size_t b2 = sizeof(double2) * (size_t)n;
+    BH_CUDA_OK(cudaMemcpyAsync(c->pos, c->ro_tmp2, b2, cudaMemcpyDeviceToDevice, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(c->vel, c->ro_tmp2 + n, b2, cudaMemcpyDeviceToDevice, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(c->acc, c->ro_tmp2 + 2 * n, b2, cudaMemcpyDeviceToDevice, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(c->force, c->ro_tmp2 + 3 * n, b2, cudaMemcpyDeviceToDevice, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(c->mass, c->ro_tmp1, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+    BH_CUDA_OK(cudaMemcpyAsync(c->perm, c->ro_tmpu, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->have_snapshot) {         // keep a snapshot taken earlier consistent with the new internal order
+        permute2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->snap_pos, c->idx[c->sorted], n, c->ro_tmp2);
+        permute2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->snap_vel, c->idx[c->sorted], n, c->ro_tmp2 + n);
+        BH_TRY(check_launch());
+        BH_CUDA_OK(cudaMemcpyAsync(c->snap_pos, c->ro_tmp2, b2, cudaMemcpyDeviceToDevice, c->stream));
+        BH_CUDA_OK(cudaMemcpyAsync(c->snap_vel, c->ro_tmp2 + n, b2, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    c->perm_identity = false;
+    c->steps_since_reorder = 0;
+    c->tree_valid = false;          // sorted positions / self_node refer to the old internal indices
+    return BH_OK;
+}
+
 int copy_out2(bh_ctx* c, const double2* dev, double* host, bool gather_ranks) {
     if (!host) { set_error("null output buffer"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     // multi-rank: every rank only keeps its own slice current; getters are collective and gather first
     if (gather_ranks && c->p.n_ranks > 1) BH_TRY(exchange_slices(c, (void*)dev, sizeof(double2)));
+    if (!c->perm_identity) {     // internal (resident Morton) order -> the caller's original order
+        BH_TRY(reorder_alloc(c));
+        unpermute2_kernel<<<(unsigned)((c->d.n + 255) / 256), 256, 0, c->stream>>>(dev, c->perm, c->d.n, c->ro_tmp2);
+        BH_TRY(check_launch());
+        dev = c->ro_tmp2;
+    }
     BH_CUDA_OK(cudaMemcpyAsync(host, dev, sizeof(double2) * c->d.n, cudaMemcpyDeviceToHost, c->stream));
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
     return peer_error(c);
@@ -570,6 +663,7 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     { const char* e = getenv("BH_KEYS_TABLE"); c->keys_table = e ? e[0] == '1' : (p->n_bodies / p->n_ranks >= 4000000); }
     { const char* e = getenv("BH_PDL"); c->pdl = e && e[0] == '1' && p->n_ranks == 1; }
     { const char* e = getenv("BH_HOST_TRACE"); c->host_trace = e && e[0] == '1'; }
+    { const char* e = getenv("BH_REORDER"); c->auto_reorder = !(e && e[0] == '0'); }
     { const char* e = getenv("BH_HOST_PIPELINE_MULTI"); c->host_pipeline_multi = !(e && e[0] == '0'); }   // default on
     { const char* e = getenv("BH_HOST_CHUNKS"); if (e && atoi(e) >= 1) c->host_chunks = std::min(atoi(e), kMaxHostChunks); }
     if (p->device >= 0) c->device = p->device;
@@ -673,7 +767,8 @@ int bh_destroy(bh_ctx* c) {
                     c->keys[1], c->idx[0], c->idx[1], c->consts, c->tree.mass, c->tree.comx, c->tree.comy,
                     c->tree.count /* + scratch + tickets */, c->tree.first, c->tree.flags, c->rec_alloc, c->tree.self_node, c->tree.tile_queue,
                     c->s.bbox_partial, c->s.heavy_list, c->s.huge_list, c->s.huge_partial, c->s.cell_bnd,
-                    c->packed, c->chunk_lists, c->chunk_counts, c->cell_sums, c->bbox_raw};
+                    c->packed, c->chunk_lists, c->chunk_counts, c->cell_sums, c->bbox_raw, c->perm, c->ro_tmp2, c->ro_tmp1,
+                    c->ro_tmpu};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -743,7 +838,7 @@ int bh_attach_peers(bh_ctx* c, const void* handles, int32_t n_handles) {
         for (auto& gr : c->graph) if (gr) { cudaGraphExecDestroy(gr); gr = nullptr; }
         c->p2p_ready = false;
     }
-    BH_CUDA_OK(cudaMemset(c->comm_buf, 0, c->pc.off_rs));   // box slots, flags, error word, sequence number, tickets
+    BH_CUDA_OK(cudaMemset(c->comm_buf, 0, c->comm_bytes));   // box slots, flags, error word, sequence number, tickets, inbox
     for (int r = 0; r < c->p.n_ranks; ++r) {
         if (r == c->p.rank) continue;
         cudaIpcMemHandle_t h;
@@ -775,6 +870,8 @@ int bh_set_bodies(bh_ctx* c, const double* pos, const double* vel, const double*
     BH_TRY(check_launch());
     c->bodies_set = true;
     c->tree_valid = false;
+    c->perm_identity = true;                       // caller's order
+    c->steps_since_reorder = kReorderEvery - 1;    // a multi-step run re-sorts the arrays before its second step
     return BH_OK;
 }
 
@@ -783,9 +880,15 @@ static int set_vec(bh_ctx* c, double2* dst, const double* src) {
     if (!c->bodies_set) { set_error("bh_set_bodies first"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     const int64_t n = c->d.n;
-    (void)n;
-    BH_CUDA_OK(cudaMemcpyAsync(dst + c->own_lo, src + 2 * c->own_lo, sizeof(double2) * (c->own_hi - c->own_lo),
-                               cudaMemcpyHostToDevice, c->stream));
+    if (!c->perm_identity) {    // the arrays are in resident order: upload in the caller's order, then permute
+        BH_TRY(reorder_alloc(c));
+        BH_CUDA_OK(cudaMemcpyAsync(c->ro_tmp2, src, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
+        permute2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->ro_tmp2, c->perm, n, dst);
+        BH_TRY(check_launch());
+    } else {
+        BH_CUDA_OK(cudaMemcpyAsync(dst + c->own_lo, src + 2 * c->own_lo, sizeof(double2) * (c->own_hi - c->own_lo),
+                                   cudaMemcpyHostToDevice, c->stream));
+    }
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
     c->tree_valid = false;
     return BH_OK;
@@ -797,6 +900,8 @@ int bh_snapshot(bh_ctx* c) {
     if (!c || !c->bodies_set) { set_error("bh_snapshot: no bodies"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     const int64_t n = c->d.n;
+    // steps that restart from the snapshot cannot re-sort the arrays in between: take the snapshot in resident order
+    if (reorder_allowed(c)) BH_TRY(enqueue_reorder(c));
     if (!c->snap_pos) { BH_TRY(dev_alloc(&c->snap_pos, (size_t)n)); BH_TRY(dev_alloc(&c->snap_vel, (size_t)n)); }
     BH_CUDA_OK(cudaMemcpyAsync(c->snap_pos, c->pos, sizeof(double2) * n, cudaMemcpyDeviceToDevice, c->stream));
     BH_CUDA_OK(cudaMemcpyAsync(c->snap_vel, c->vel, sizeof(double2) * n, cudaMemcpyDeviceToDevice, c->stream));
@@ -880,6 +985,7 @@ int bh_step_host(bh_ctx* c, const double* pos, const double* vel, const double* 
     }
     DeviceGuard g(c->device);
     const int64_t n = c->d.n;
+    c->perm_identity = true;     // the call overwrites the whole state in the caller's order
     // exact leaves read other bodies' positions during the walk: chunk k's integrator must not overlap chunk k+1's walk
     const int nch = (c->p.flags & BH_FLAG_EXACT_LEAVES) ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(c->host_chunks, n / 4096));
     if (nch > 1 && !c->chunk_lists) {
@@ -984,13 +1090,24 @@ static int fetch_sorted(bh_ctx* c, std::vector<uint32_t>& keys, std::vector<uint
     return BH_OK;
 }
 
+// internal -> original index; empty = identity
+static int fetch_perm(bh_ctx* c, std::vector<uint32_t>& perm) {
+    perm.clear();
+    if (c->perm_identity) return BH_OK;
+    perm.resize(c->d.n);
+    BH_CUDA_OK(cudaMemcpyAsync(perm.data(), c->perm, 4 * c->d.n, cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return BH_OK;
+}
+
 int bh_get_body_keys(bh_ctx* c, uint32_t* out) {
     if (!c || !out || !c->tree_valid) { set_error("bh_get_body_keys: no tree for the current positions (call bh_build_tree; a step moves the bodies)"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     BH_TRY(ensure_full_tree(c));
-    std::vector<uint32_t> keys, idx;
+    std::vector<uint32_t> keys, idx, perm;
     BH_TRY(fetch_sorted(c, keys, idx));
-    for (int64_t j = 0; j < c->d.n; ++j) out[idx[j]] = keys[j];
+    BH_TRY(fetch_perm(c, perm));
+    for (int64_t j = 0; j < c->d.n; ++j) out[perm.empty() ? idx[j] : perm[idx[j]]] = keys[j];
     return BH_OK;
 }
 
@@ -998,9 +1115,10 @@ int bh_get_sorted_order(bh_ctx* c, uint32_t* out) {
     if (!c || !out || !c->tree_valid) { set_error("bh_get_sorted_order: no tree for the current positions (call bh_build_tree; a step moves the bodies)"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     BH_TRY(ensure_full_tree(c));
-    std::vector<uint32_t> keys, idx;
+    std::vector<uint32_t> keys, idx, perm;
     BH_TRY(fetch_sorted(c, keys, idx));
-    for (int64_t j = 0; j < c->d.n; ++j) out[j] = idx[j];
+    BH_TRY(fetch_perm(c, perm));
+    for (int64_t j = 0; j < c->d.n; ++j) out[j] = perm.empty() ? idx[j] : perm[idx[j]];
     return BH_OK;
 }
 
@@ -1032,6 +1150,7 @@ static int fetch_host_tree(bh_ctx* c, HostTree& ht) {
     BH_CUDA_OK(cudaMemcpyAsync(&h, c->consts, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
     ht.bounds[0] = h.xmin; ht.bounds[1] = h.xmax; ht.bounds[2] = h.ymin; ht.bounds[3] = h.ymax;
+    BH_TRY(fetch_perm(c, ht.perm));
     return BH_OK;
 }
 
@@ -1123,6 +1242,8 @@ int bh_generate(bh_ctx* c, int32_t kind, uint64_t seed) {
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
     c->mass_complete = c->p.n_ranks == 1;
     c->zero_mass_bodies = 0;                 // log-uniform in [0.1, 0.5]
+    c->perm_identity = true;
+    c->steps_since_reorder = kReorderEvery - 1;
     c->bodies_set = true;
     c->tree_valid = false;
     return BH_OK;
@@ -1183,7 +1304,12 @@ int bh_trajectory_record(bh_ctx* c, double time) {
     c->traj->acquire(k);        // the frame two records ago has left this buffer (back-pressure if the disk is slower)
     // device snapshot on the compute stream (the next step's integrator overwrites c->pos in place), then the
     // device-to-host copy on the side stream, overlapping the following steps
-    BH_CUDA_OK(cudaMemcpyAsync(c->traj_dev[k], c->pos, sizeof(double2) * c->d.n, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->perm_identity) {
+        BH_CUDA_OK(cudaMemcpyAsync(c->traj_dev[k], c->pos, sizeof(double2) * c->d.n, cudaMemcpyDeviceToDevice, c->stream));
+    } else {                    // resident order -> the caller's body order
+        unpermute2_kernel<<<(unsigned)((c->d.n + 255) / 256), 256, 0, c->stream>>>(c->pos, c->perm, c->d.n, c->traj_dev[k]);
+        BH_TRY(check_launch());
+    }
     BH_CUDA_OK(cudaEventRecord(c->traj_snap[k], c->stream));
     BH_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->traj_snap[k], 0));
     BH_CUDA_OK(cudaMemcpyAsync(c->traj_host[k], c->traj_dev[k], sizeof(double2) * c->d.n, cudaMemcpyDeviceToHost, c->copy_stream));

@@ -98,8 +98,8 @@ constexpr int kMaxPeers = 8;   // GPUs of one NVSwitch box
 struct PeerComm {
     int rank, n_ranks;
     uint8_t* peer_base[kMaxPeers];   // peer_base[rank] is this rank's own buffer
-    size_t off_bbox, off_bbox_flag, off_rs_flag, off_ag_flag, off_err, off_rs, off_sums;
-    uint64_t ncells, slice;          // finest cells, cells per rank slice
+    size_t off_bbox, off_bbox_flag, off_in_flag, off_err, off_inbox;
+    uint64_t ncells;                 // finest cells; inbox = [source rank][4][ncells] doubles (count, m, m x, m y)
     unsigned long long timeout_ns;   // wall-clock bound of every flag wait (env BH_PEER_TIMEOUT_MS, default 4000)
 };
 
@@ -122,18 +122,19 @@ void launch_bounds(const double2* pos, int64_t n, const bh_params& p, const Dims
                    StepConsts* consts, int grid, cudaStream_t st, double* raw_out = nullptr,
                    const PeerComm* pc = nullptr);
 void peer_comm_layout(PeerComm& pc, int rank, int n_ranks, uint64_t ncells, size_t* total_bytes);
-void launch_peer_allreduce_cells(const PeerComm& pc, const double* local_sums, cudaStream_t st);
 void launch_bounds_finalize(const double* raw, const bh_params& p, const Dims& d, Scratch& s, StepConsts* consts,
                             cudaStream_t st);
 void launch_keys(const double2* pos, int64_t n, const Dims& d, const SortPlan& sp, const StepConsts* consts,
                  uint32_t* keys, uint32_t* idx, uint32_t* digit_hist, cudaStream_t st, uint32_t idx_base,
                  const double* cell_bnd);   // cell_bnd: Scratch::cell_bnd (table lookup) or nullptr (bisection)
+// pc != nullptr (sharded build with the peer-memory exchange): the partial sums of this rank's non-empty cells go
+// straight into every rank's inbox (launch_tree_runs), and the level pass adds the ranks' contributions itself
 void launch_tree_runs(const uint32_t* skeys, const uint32_t* sidx, const double2* pos, const double* mass,
                       int64_t n, const bh_params& p, const Dims& d, TreeArrays& t, Scratch& s, double* sums,
-                      cudaStream_t st);
+                      cudaStream_t st, const PeerComm* pc = nullptr);
 void launch_tree_levels(const uint32_t* sidx, const double2* pos, const double* mass, const bh_params& p,
                         const Dims& d, TreeArrays& t, Scratch& s, const StepConsts* consts, const double* sums,
-                        cudaStream_t st);
+                        cudaStream_t st, const PeerComm* pc = nullptr);
 void launch_sort(uint32_t* keys[2], uint32_t* vals[2], int64_t n, const SortPlan& sp, Scratch& s,
                  int* result_buf, cudaStream_t st, uint32_t val_base);   // values of pass 0 = val_base + input position
 void launch_tree(const uint32_t* skeys, const uint32_t* sidx, const double2* pos, const double* mass,

@@ -24,6 +24,7 @@
 // `exact_leaf_max` bodies, whose (inherently sequential) running average is replaced by a
 // fixed-shape parallel sum (relative difference ~1e-16; deterministic, identical on every rank).
 #include "bh_internal.h"
+#include "peer_comm.cuh"
 
 namespace bh {
 
@@ -300,26 +301,57 @@ heavy_huge_kernel(const uint32_t* __restrict__ heavy_list, const uint32_t* __res
 // ---- sharded build: this rank's partial sums per finest cell (count, m, m x, m y) ------------------
 // sums = [4][ncells] doubles, all-reduced over the ranks before the level pass.  Cells queued as
 // heavy were already summed (raw) by heavy_cells_kernel.
+// PUSH (peer-memory exchange): the sums of every non-empty cell also go into this rank's slot of every rank's inbox
+// (its own included); the last block to finish raises the flag of the step at every peer.
+template <bool PUSH>
 __global__ void __launch_bounds__(256)
 cell_partial_kernel(const uint32_t* __restrict__ cnt_f, const uint32_t* __restrict__ first_f, uint64_t ncells,
                     const uint32_t* __restrict__ sidx, const double2* __restrict__ pos,
-                    const double* __restrict__ mass, uint32_t exact_leaf_max, double* __restrict__ sums) {
+                    const double* __restrict__ mass, uint32_t exact_leaf_max, double* __restrict__ sums,
+                    const __grid_constant__ PeerComm pc) {
     const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncells) return;
-    const uint32_t cnt = cnt_f[c];
-    sums[c] = (double)cnt;
-    if (cnt > exact_leaf_max) return;              // m, mx, my written by heavy_cells_kernel
-    double m = 0.0, sx = 0.0, sy = 0.0;
-    const uint32_t f = cnt ? first_f[c] : 0u;
-    for (uint32_t i = 0; i < cnt; ++i) {
-        const uint32_t b = __ldg(sidx + f + i);
-        const double mb = __ldg(mass + b);
-        const double2 x = __ldg(pos + b);
-        m = __dadd_rn(m, mb);
-        sx = __dadd_rn(sx, __dmul_rn(mb, x.x));
-        sy = __dadd_rn(sy, __dmul_rn(mb, x.y));
+    if (c < ncells) {
+        const uint32_t cnt = cnt_f[c];
+        double m = 0.0, sx = 0.0, sy = 0.0;
+        if (cnt > exact_leaf_max) {                    // m, mx, my written by heavy_huge_kernel
+            if constexpr (PUSH) { m = sums[ncells + c]; sx = sums[2 * ncells + c]; sy = sums[3 * ncells + c]; }
+        } else {
+            const uint32_t f = cnt ? first_f[c] : 0u;
+            for (uint32_t i = 0; i < cnt; ++i) {
+                const uint32_t b = __ldg(sidx + f + i);
+                const double mb = __ldg(mass + b);
+                const double2 x = __ldg(pos + b);
+                m = __dadd_rn(m, mb);
+                sx = __dadd_rn(sx, __dmul_rn(mb, x.x));
+                sy = __dadd_rn(sy, __dmul_rn(mb, x.y));
+            }
+            if constexpr (!PUSH) { sums[ncells + c] = m; sums[2 * ncells + c] = sx; sums[3 * ncells + c] = sy; }
+        }
+        if constexpr (!PUSH) sums[c] = (double)cnt;
+        if constexpr (PUSH) {
+            if (cnt) {
+                for (int r = 0; r < pc.n_ranks; ++r) {
+                    double* in = reinterpret_cast<double*>(pc.peer_base[r] + pc.off_inbox) + (uint64_t)pc.rank * 4 * ncells + c;
+                    in[0] = (double)cnt; in[ncells] = m; in[2 * ncells] = sx; in[3 * ncells] = sy;
+                }
+            }
+        }
     }
-    sums[ncells + c] = m; sums[2 * ncells + c] = sx; sums[3 * ncells + c] = sy;
+    if constexpr (PUSH) {
+        __shared__ bool last;
+        uint32_t* ticket = reinterpret_cast<uint32_t*>(pc.peer_base[pc.rank] + pc.off_err) + 2;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (last) {
+            if (threadIdx.x == 0) *ticket = 0;
+            const uint32_t seq = *(reinterpret_cast<const uint32_t*>(pc.peer_base[pc.rank] + pc.off_err) + 1);
+            __threadfence_system();
+            if ((int)threadIdx.x < pc.n_ranks)
+                st_release_sys(reinterpret_cast<uint32_t*>(pc.peer_base[threadIdx.x] + pc.off_in_flag) + pc.rank, seq);
+        }
+    }
 }
 
 // ---- top levels (F-5 .. 0): run by the LAST block of tree_bottom_kernel to finish (atomic ticket), level by level
@@ -383,9 +415,19 @@ __global__ void __launch_bounds__(kBottomThreads)
 tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, const double2* __restrict__ pos,
                    const double* __restrict__ mass, double G0, double mass_eps, uint32_t exact_leaf_max,
                    unsigned long long* __restrict__ counters, const StepConsts* __restrict__ consts,
-                   const double* __restrict__ sums, uint32_t* __restrict__ done_ticket) {
+                   const double* __restrict__ sums, uint32_t* __restrict__ done_ticket, const __grid_constant__ PeerComm pc) {
     pdl_entry();
     const int F = d.finest;
+    if constexpr (SHARDED) {
+        if (pc.n_ranks > 1) {   // peer-memory exchange: every rank's contributions of this step must have landed in the inbox
+            uint8_t* own = pc.peer_base[pc.rank];
+            if ((int)threadIdx.x < pc.n_ranks)
+                wait_flag(reinterpret_cast<const uint32_t*>(own + pc.off_in_flag) + threadIdx.x,
+                          *(reinterpret_cast<const uint32_t*>(own + pc.off_err) + 1), reinterpret_cast<uint32_t*>(own + pc.off_err),
+                          pc.timeout_ns);
+            __syncthreads();
+        }
+    }
     const double scale = consts->scale;
     const double G = G0 * scale * scale;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -405,11 +447,24 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
         // global sums of all ranks; `first` stays this rank's own run (self_node bookkeeping)
         const uint32_t lcnt = t.count[offF + code];
         if (lcnt) cur.first = t.first[offF + code];
-        cur.cnt = (uint32_t)llrint(sums[code]);
-        const double m = sums[ncells + code];
+        double tc, m, sx, sy;
+        if (pc.n_ranks > 1) {   // add the ranks' contributions in rank order (identical on every rank); zero what was consumed
+            tc = 0.0; m = 0.0; sx = 0.0; sy = 0.0;
+            double* in = reinterpret_cast<double*>(pc.peer_base[pc.rank] + pc.off_inbox) + code;
+            for (int r = 0; r < pc.n_ranks; ++r, in += 4 * ncells) {
+                const double cr = __ldcg(in);
+                if (cr != 0.0) {
+                    tc += cr; m += __ldcg(in + ncells); sx += __ldcg(in + 2 * ncells); sy += __ldcg(in + 3 * ncells);
+                    in[0] = 0.0; in[ncells] = 0.0; in[2 * ncells] = 0.0; in[3 * ncells] = 0.0;
+                }
+            }
+        } else {                // NCCL fallback: `sums` holds the all-reduced values
+            tc = sums[code]; m = sums[ncells + code]; sx = sums[2 * ncells + code]; sy = sums[3 * ncells + code];
+        }
+        cur.cnt = (uint32_t)llrint(tc);
         cur.m = m;
-        cur.cx = m > 0.0 ? __ddiv_rn(sums[2 * ncells + code], m) : 0.0;
-        cur.cy = m > 0.0 ? __ddiv_rn(sums[3 * ncells + code], m) : 0.0;
+        cur.cx = m > 0.0 ? __ddiv_rn(sx, m) : 0.0;
+        cur.cy = m > 0.0 ? __ddiv_rn(sy, m) : 0.0;
         store_cell(t, offF + code, cur, F, F, G, mass_eps, scale, consts->thr2[F], sidx);
     } else if (code < ncells) {
         cur.cnt = t.count[offF + code];
@@ -526,7 +581,7 @@ tree_bottom_kernel(TreeArrays t, Dims d, const uint32_t* __restrict__ sidx, cons
 // Phase 1: finest-cell runs (+ heavy cells, + this rank's partial sums when sharded).
 void launch_tree_runs(const uint32_t* skeys, const uint32_t* sidx, const double2* pos, const double* mass,
                       int64_t n, const bh_params& p, const Dims& d, TreeArrays& t, Scratch& s, double* sums,
-                      cudaStream_t st) {
+                      cudaStream_t st, const PeerComm* pc) {
     const int F = d.finest;
     uint32_t* cnt_f = t.count + d.level_off[F];
     uint32_t* first_f = t.first + d.level_off[F];
@@ -543,8 +598,12 @@ void launch_tree_runs(const uint32_t* skeys, const uint32_t* sidx, const double2
                                                      sidx, pos, mass, sums + nc, sums + 2 * nc, sums + 3 * nc, true,
                                                      s.huge_partial, s.huge_tickets);
         ++g_launches;
-        cell_partial_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(cnt_f, first_f, nc, sidx, pos, mass, exact_max,
-                                                                          sums);
+        PeerComm none{};
+        none.n_ranks = 1;
+        if (pc) cell_partial_kernel<true><<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(cnt_f, first_f, nc, sidx, pos, mass,
+                                                                                       exact_max, sums, *pc);
+        else cell_partial_kernel<false><<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(cnt_f, first_f, nc, sidx, pos, mass,
+                                                                                     exact_max, sums, none);
         ++g_launches;
     } else {
         // (n > 0 here: the previous operation on the stream is cell_runs_kernel)
@@ -559,15 +618,17 @@ void launch_tree_runs(const uint32_t* skeys, const uint32_t* sidx, const double2
 // Phase 2: all levels bottom-up.  `sums` (sharded build) = all-reduced per-cell sums.
 void launch_tree_levels(const uint32_t* sidx, const double2* pos, const double* mass, const bh_params& p,
                         const Dims& d, TreeArrays& t, Scratch& s, const StepConsts* consts, const double* sums,
-                        cudaStream_t st) {
+                        cudaStream_t st, const PeerComm* pc) {
+    PeerComm none{};
+    none.n_ranks = 1;
     const int F = d.finest;
     uint32_t exact_max = (uint32_t)(p.exact_leaf_max < 0 ? 0 : p.exact_leaf_max);
     unsigned blocks = (unsigned)((d.ncells_finest + kBottomThreads - 1) / kBottomThreads);
     // bbox_ticket is free again here (the bounds kernel resets it) — reused as the "blocks done" ticket
     if (sums) tree_bottom_kernel<true><<<blocks, kBottomThreads, 0, st>>>(t, d, sidx, pos, mass, p.G, p.mass_eps, exact_max,
-                                                                        s.counters, consts, sums, s.bbox_ticket);
+                                                                        s.counters, consts, sums, s.bbox_ticket, pc ? *pc : none);
     else launch_chain(tree_bottom_kernel<false>, dim3(blocks), dim3(kBottomThreads), st, true, t, d, sidx, pos, mass, p.G,
-                      p.mass_eps, exact_max, s.counters, consts, (const double*)nullptr, s.bbox_ticket);
+                      p.mass_eps, exact_max, s.counters, consts, (const double*)nullptr, s.bbox_ticket, none);
     ++g_launches;
 }
 

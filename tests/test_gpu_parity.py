@@ -261,6 +261,9 @@ def test_ab_switches_are_bit_identical(env, monkeypatch):
     A/B fall-backs (per-body FP64 bisection, restore by device copies) give the same bits."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
+    # bit identity between differently driven contexts needs the same summation order inside shared cells: keep the
+    # body arrays in the caller's order here (the periodic physical re-sort has its own tests, test_gpu_reorder.py)
+    monkeypatch.setenv("BH_REORDER", "0")
     rng = np.random.default_rng(11)
     n = 70001
     pos = rng.uniform(-1, 1, size=(n, 2))
