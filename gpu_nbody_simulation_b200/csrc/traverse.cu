@@ -48,6 +48,7 @@ constexpr int kTravWarps = kTravThreads / 32;
 constexpr int kStackCap = 3 * kMaxDepthDense + 8;
 
 struct TravArgs {
+    const uint32_t* skeys;      // finest-cell key per sorted position
     const uint32_t* sidx;       // body index per sorted position
     const uint32_t* own_list;   // optional: sorted positions owned by this rank (multi-GPU)
     const uint32_t* self_node;  // per body: its own single-occupant leaf (pyramid index) or 0xffffffff
@@ -109,6 +110,50 @@ __device__ __forceinline__ void finish_body(const TravArgs& a, uint32_t body, do
     }
 }
 
+// ---- FP64 rescue of bodies the FP32 frame cannot resolve ---------------------------------------------------------
+// The double-float displacement resolves separations down to 2^-48 of the frame (the scaled root box, or the warp's
+// box in the list kernel).  The one systematic case below that is a body whose OWN multi-body cap-level cell has its
+// centre of mass (almost) on the body: coincident bodies, whose COM differs from them by an FP64 ulp — and the
+// reference applies that cell to the body itself, so the pair decides the body's whole force.  Such a
+// body is detected in the prologue (one FP64 subtraction against its own cell), taken out of the warp's FP32 walk and
+// evaluated by the reference's own per-body FP64 walk (project.cu:593-675) in the epilogue.  Costs nothing in the hot
+// loops; never triggers on the benchmark workloads.
+constexpr double kTinyRel2 = 5.6e-17;   // (2^-27)^2: below 2^-27 of the frame the double-float form loses > 1e-6 of d
+
+__device__ __forceinline__ bool own_cell_unresolved(const TravArgs& a, uint32_t sorted_pos, double px, double py,
+                                                    double scale, double frame2) {
+    const uint32_t ci = a.finest_off + __ldg(a.skeys + sorted_pos);
+    if (__ldg(a.t_count + ci) < 2u) return false;
+    const double dx = (__ldg(a.t_comx + ci) - px) * scale, dy = (__ldg(a.t_comy + ci) - py) * scale;
+    return dx * dx + dy * dy < kTinyRel2 * frame2;          // false for NaN
+}
+
+__device__ __noinline__ void fp64_body_walk(const TravArgs& a, uint32_t selfn, double px, double py, double& sx, double& sy) {
+    uint32_t stack[3 * kMaxDepthDense + 8];
+    int top = 0;
+    stack[top++] = 0u;
+    double ax = 0.0, ay = 0.0;
+    while (top > 0) {
+        const uint32_t idx = stack[--top];
+        const uint32_t fl = a.flags[idx];
+        if (!(fl & kNodeNonZero)) continue;                                   // project.cu:617
+        const int level = (31 - __clz(3u * idx + 1u)) >> 1;
+        const double dx = a.t_comx[idx] - px, dy = a.t_comy[idx] - py;
+        const double d2 = dx * dx + dy * dy;
+        const double d = sqrt(d2) + a.dist_eps;                               // project.cu:634
+        if ((fl & kNodeLeaf) || (a.consts->size[level] / d < a.theta)) {      // project.cu:643
+            if (selfn != idx) {                                               // project.cu:646
+                const double fm = (a.G * a.t_mass[idx]) / d2;                 // (times m_i in finish_body)
+                ax += fm * (dx / d);
+                ay += fm * (dy / d);
+            }
+        } else {
+            for (uint32_t q = 0; q < 4; ++q) stack[top++] = 4u * idx + 1u + q;
+        }
+    }
+    sx = ax; sy = ay;
+}
+
 // ------------------------------------------------------------------------------------------------
 // FP32 traversal, BPL bodies per lane
 // ------------------------------------------------------------------------------------------------
@@ -166,6 +211,7 @@ traverse_f32_kernel(const __grid_constant__ TravArgs a) {
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&s_stack[warp][0]);
 
     uint32_t body[BPL], selfn[BPL];
+    bool rescue[BPL];            // evaluated by fp64_body_walk in the epilogue instead of the warp's FP32 walk
     float2 nh[BPL], nl[BPL];     // minus the scaled body position, hi and lo floats
     float2 acc2[BPL];            // sum of G M d / (d2 (d + eps)); times m_i at the end
     const float feps = a.consts->feps;
@@ -177,15 +223,20 @@ traverse_f32_kernel(const __grid_constant__ TravArgs a) {
         for (int b = 0; b < BPL; ++b) {
             const int64_t slot = warp_slot0 + b * 32 + lane;
             body[b] = 0xffffffffu; selfn[b] = 0xffffffffu;
+            rescue[b] = false;
             double px = 0.0, py = 0.0;
+            uint32_t sp = 0;
             if (slot < a.n_slots) {
-                uint32_t sp = a.own_list ? a.own_list[slot] : (uint32_t)slot;
+                sp = a.own_list ? a.own_list[slot] : (uint32_t)slot;
                 body[b] = a.sidx[sp];
                 selfn[b] = a.self_node[body[b]];
                 double2 p = a.pos_in[body[b]];
                 px = p.x; py = p.y;
             }
             const double sx = px * scale, sy = py * scale;
+            if constexpr (!EXACT) {
+                if (slot < a.n_slots) rescue[b] = own_cell_unresolved(a, sp, px, py, scale, sx * sx + sy * sy);
+            }
             const float xh = (float)sx, yh = (float)sy;
             nh[b] = make_float2(-xh, -yh);
             nl[b] = make_float2(-(float)(sx - (double)xh), -(float)(sy - (double)yh));
@@ -274,7 +325,7 @@ traverse_f32_kernel(const __grid_constant__ TravArgs a) {
         }
 #pragma unroll
         for (int b = 0; b < BPL; ++b) {
-            const bool live = body[b] != 0xffffffffu;
+            const bool live = body[b] != 0xffffffffu && !rescue[b];
             const float2 mh = live ? nh[b] : make_float2(kFarLane, kFarLane);
             m[b] = root_done ? 0u : eval(A, B, 0u, b, mh, live);
             any |= m[b];
@@ -326,7 +377,9 @@ traverse_f32_kernel(const __grid_constant__ TravArgs a) {
         if (body[b] != 0xffffffffu) {
             const double2 p = a.pos_in[body[b]];
             const double mi = a.mass[body[b]];
-            finish_body<INTEGRATE>(a, body[b], p.x, p.y, mi, mi * (double)acc2[b].x, mi * (double)acc2[b].y);
+            double fx = (double)acc2[b].x, fy = (double)acc2[b].y;
+            if (rescue[b]) fp64_body_walk(a, selfn[b], p.x, p.y, fx, fy);
+            finish_body<INTEGRATE>(a, body[b], p.x, p.y, mi, mi * fx, mi * fy);
         }
     }
     if constexpr (COUNT) {
@@ -607,7 +660,7 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
     }
     const int64_t warp_slot0 = (int64_t)tile * 64;
 
-    uint32_t body[2], selfn[2];
+    uint32_t body[2], selfn[2], spos[2];
     float2 nxh, nyh, nxl, nyl;   // minus the local-frame positions of body 0 (.x) and body 1 (.y), hi / lo floats
     float2 accx = make_float2(0.f, 0.f), accy = make_float2(0.f, 0.f);
     {
@@ -616,10 +669,11 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
             const int64_t slot = warp_slot0 + b * 32 + lane;
-            body[b] = 0xffffffffu; selfn[b] = 0xffffffffu;
+            body[b] = 0xffffffffu; selfn[b] = 0xffffffffu; spos[b] = 0u;
             double px = 0.0, py = 0.0;
             if (slot < a.n_slots) {
                 uint32_t sp = a.own_list ? a.own_list[slot] : (uint32_t)slot;
+                spos[b] = sp;
                 body[b] = a.sidx[sp];
                 selfn[b] = a.self_node[body[b]];
                 double2 p = a.pos_in[body[b]];
@@ -627,7 +681,9 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
             }
             sx[b] = px * scale; sy[b] = py * scale;
         }
-        const bool l0 = body[0] != 0xffffffffu, l1 = body[1] != 0xffffffffu;
+        bool l0 = body[0] != 0xffffffffu, l1 = body[1] != 0xffffffffu;
+        // (first pass over the frame: the box of ALL bodies; bodies whose own cell the local frame cannot resolve are then
+        // taken out of the walk — see fp64_body_walk — which can only shrink the box)
         const uint32_t live0 = __ballot_sync(0xffffffffu, l0), live1 = __ballot_sync(0xffffffffu, l1);
         // bounding box of the warp's bodies (floats rounded outwards by the slack below), frame origin = its centre
         const float inf = __int_as_float(0x7f800000);
@@ -641,9 +697,14 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
         }
         const double ox = 0.5 * ((double)x0 + (double)x1), oy = 0.5 * ((double)y0 + (double)y1);
         float t[2][4];
+        bool resc[2] = {false, false};
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
             const double rx = sx[b] - ox, ry = sy[b] - oy;
+            if (body[b] != 0xffffffffu)
+                // (the node records themselves carry the COM as a double-float of the GLOBAL scaled coordinate: that, not
+                // the local frame, bounds what the near-field arithmetic resolves)
+                resc[b] = own_cell_unresolved(a, spos[b], sx[b] / scale, sy[b] / scale, scale, sx[b] * sx[b] + sy[b] * sy[b]);
             const float xh = (float)rx, yh = (float)ry;
             t[b][0] = -xh; t[b][1] = -yh;
             t[b][2] = -(float)(rx - (double)xh); t[b][3] = -(float)(ry - (double)yh);
@@ -661,9 +722,12 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
             wc.slack = 1.2e-7f * mag;
             const float wx = wc.bx1 - wc.bx0, wy = wc.by1 - wc.by0;
             wc.far2 = 0.015625f * fmaf(wx, wx, wy * wy);
-            wc.live0 = live0; wc.live1 = live1;
             s_wc[warp] = wc;
         }
+        // bodies the frame cannot resolve leave the walk: bit 31 of spos marks them for the epilogue
+        const uint32_t walk0 = __ballot_sync(0xffffffffu, l0 && !resc[0]), walk1 = __ballot_sync(0xffffffffu, l1 && !resc[1]);
+        if (lane == 0) { s_wc[warp].live0 = walk0; s_wc[warp].live1 = walk1; }
+        spos[0] = resc[0] ? 1u : 0u; spos[1] = resc[1] ? 1u : 0u;
         __syncwarp();
     }
     const float2 eps2 = make_float2(feps, feps), neg_eps2 = make_float2(-feps, -feps);
@@ -877,7 +941,9 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
         if (body[b] != 0xffffffffu) {
             const double2 p = a.pos_in[body[b]];
             const double mi = a.mass[body[b]];
-            finish_body<INTEGRATE>(a, body[b], p.x, p.y, mi, mi * (double)ax[b], mi * (double)ay[b]);
+            double fx = (double)ax[b], fy = (double)ay[b];
+            if (spos[b]) fp64_body_walk(a, selfn[b], p.x, p.y, fx, fy);       // rescued body: the reference's FP64 walk
+            finish_body<INTEGRATE>(a, body[b], p.x, p.y, mi, mi * fx, mi * fy);
         }
     }
     __syncwarp();       // the warp's shared arrays are reused by its next tile
@@ -1108,9 +1174,9 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
                      const uint32_t* own_list, const uint32_t* own_count_dev, int64_t own_n,
                      const bh_params& p, const Dims& d, const TreeArrays& t, const StepConsts* consts,
                      unsigned long long* counters, bool integrate, cudaStream_t st) {
-    (void)own_lo; (void)own_hi; (void)own_count_dev; (void)n; (void)skeys;
+    (void)own_lo; (void)own_hi; (void)own_count_dev; (void)n;
     TravArgs a;
-    a.sidx = sidx; a.own_list = own_list; a.self_node = t.self_node;
+    a.skeys = skeys; a.sidx = sidx; a.own_list = own_list; a.self_node = t.self_node;
     a.pos_in = pos_in; a.vel_in = vel_in;
     a.pos = pos; a.vel = vel; a.acc = acc; a.force = force; a.mass = mass;
     a.rec = t.rec; a.flags = t.flags; a.t_mass = t.mass; a.t_comx = t.comx; a.t_comy = t.comy;
