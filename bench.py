@@ -59,9 +59,9 @@ UNIT = "body·steps/s"
 GEN_KIND = {"disk": "uniform_disk", "plummer": "plummer_2d", "square": "uniform_square"}
 # dram__bytes_read.sum + dram__bytes_write.sum and smsp__inst_executed.sum of the production traversal kernel, one
 # `ncu --set full` capture at N = 1M uniform disk; see profiles/ (file named in NCU_SOURCE)
-NCU_SOURCE = "profiles/r01_traverse_v8_pair_ncu_summary.txt"
-TRAVERSE_DRAM_BYTES_NCU = 74_801_152 + 37_312_768
-TRAVERSE_WARP_INSTRUCTIONS_NCU = 298_806_710
+NCU_SOURCE = "profiles/r02_traverse_list_ncu_summary.txt"
+TRAVERSE_DRAM_BYTES_NCU = 61_381_376 + 23_144_192
+TRAVERSE_WARP_INSTRUCTIONS_NCU = 225_959_564
 
 
 def make_workload(n, dist="disk"):
@@ -604,8 +604,8 @@ def run_ours(args):
             direct = {"n_bodies": dn, "ms": dms, "pairs_per_s": pairs / (dms * 1e-3),
                       "tflops_at_20_flop_per_pair": pairs * 20.0 / (dms * 1e-3) / 1e12,
                       "frac_of_fp32_peak": (pairs * 20.0 / (dms * 1e-3) / 1e12 / peak_tf) if peak_tf else None,
-                      "formula": "main_approach_1.cpp:53-75 (G m_i m_j d / (d^2 d), i != j), FP32 arithmetic on a "
-                                 "double-float displacement, shared-memory tiles"}
+                      "formula": "main_approach_1.cpp:53-75 (G m_i m_j d / (d^2 d), i != j), FP32 arithmetic on single-float "
+                                 "coordinates (FP64 re-centring before the conversion), shared-memory tiles"}
             if not args.no_cpu_baseline:
                 import oracle
                 sel = np.linspace(0, dn - 1, 64).astype(np.int64)
