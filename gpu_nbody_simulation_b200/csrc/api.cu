@@ -660,7 +660,7 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     { const char* e = getenv("BH_SNAPSHOT_COPY"); c->snapshot_by_copy = e && e[0] == '1'; }
     // cell keys from the boundary table (same bits as the per-body bisection): 220 -> 159 us for bounds + keys at 16M
     // bodies (the bisection is 415 instructions per body), +2 us at 1M; BH_KEYS_TABLE=0 / 1 forces either
-    { const char* e = getenv("BH_KEYS_TABLE"); c->keys_table = e ? e[0] == '1' : (p->n_bodies / p->n_ranks >= 4000000); }
+    { const char* e = getenv("BH_KEYS_TABLE"); c->keys_table = e ? e[0] == '1' : (p->n_bodies / p->n_ranks >= 1500000); }
     { const char* e = getenv("BH_PDL"); c->pdl = e && e[0] == '1' && p->n_ranks == 1; }
     { const char* e = getenv("BH_HOST_TRACE"); c->host_trace = e && e[0] == '1'; }
     { const char* e = getenv("BH_REORDER"); c->auto_reorder = !(e && e[0] == '0'); }
@@ -719,7 +719,7 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     BH_ALLOC(c->s.heavy_list, c->d.ncells_finest);
     BH_ALLOC(c->s.huge_list, c->s.max_huge);
     BH_ALLOC(c->s.huge_partial, (size_t)c->s.max_huge * kHugeParts * 3);
-    // Cell keys: per-body FP64 bisection below 4M bodies per rank, the boundary-table variant (same bits) above:
+    // Cell keys: per-body FP64 bisection below 1.5M bodies per rank, the boundary-table variant (same bits) above:
     // at 1M bodies the two are equal (latency-bound), at 16M the table saves 60 us.
     if (c->keys_table) BH_ALLOC(c->s.cell_bnd, 2 * (((size_t)1 << c->d.finest) + 1));
     if (p->n_ranks > 1) {

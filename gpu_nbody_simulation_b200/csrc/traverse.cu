@@ -625,7 +625,7 @@ __device__ __forceinline__ void sts_v4_if(bool doit, uint4* p, uint32_t x, uint3
 }
 
 #ifndef BH_LIST_MIN_BLOCKS
-#define BH_LIST_MIN_BLOCKS 7    // per 128 threads: <= 72 registers, 28 warps per SM
+#define BH_LIST_MIN_BLOCKS 8    // per 128 threads: <= 72 registers, 28 warps per SM
 #endif
 template <bool INTEGRATE, bool EXACT_EPS>
 __global__ void __launch_bounds__(kTravThreads, BH_LIST_MIN_BLOCKS)
