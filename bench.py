@@ -393,8 +393,10 @@ def run_ours(args):
     def morton_order(pos, vel, mass, n_):
         # Hand the bodies over in Morton order of the initial distribution (computed once with the
         # library itself, outside any timed region): a rank's contiguous index slice is then a compact
-        # region, so the 64 bodies of a traversal warp stay neighbours.  Body order is arbitrary for a
-        # synthetic workload; a multi-GPU application keeps its bodies in this order permanently.
+        # region, so the 64 bodies of a traversal warp stay neighbours.  The device-resident legs would not
+        # need this any more (bh_snapshot re-partitions a multi-rank context: gather, full build, global
+        # permutation — DESIGN 12), but the e2e leg uploads each rank's slice from the CALLER's arrays every
+        # step, and there the application's order is what a rank gets.
         with bh.Simulation(n_, device=local, max_depth=args.max_depth) as tmp:
             tmp.set_bodies(pos, vel, mass)
             tmp.build_tree()

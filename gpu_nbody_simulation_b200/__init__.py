@@ -67,7 +67,7 @@ class Params(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("interactions", C.c_uint64), ("visits", C.c_uint64), ("opens", C.c_uint64),
                 ("warp_steps", C.c_uint64), ("nodes", C.c_uint64), ("heavy_cells", C.c_uint64),
-                ("zero_mass_bodies", C.c_uint64), ("reserved", C.c_uint64 * 1)]
+                ("zero_mass_bodies", C.c_uint64), ("reorders", C.c_uint64)]
 
 
 class Timers(C.Structure):

@@ -176,8 +176,10 @@ struct bh_ctx {
     // caller's original index; setters and getters go through it, so the C-ABI keeps its ORIGINAL-order contract.
     uint32_t* perm = nullptr;        // [n]; meaningful only while !perm_identity
     bool perm_identity = true;
-    bool auto_reorder = true;        // env BH_REORDER=0 disables; always off in FP64 mode and multi-rank contexts
+    bool auto_reorder = true;        // env BH_REORDER=0 disables; off in FP64 mode unless BH_REORDER=1
+    bool force_reorder = false;      // env BH_REORDER=1: also in FP64 verification mode
     int steps_since_reorder = 0;
+    uint64_t n_reorders = 0;
     double2* ro_tmp2 = nullptr;      // [4][n] double2: gather targets of pos, vel, acc, force
     double* ro_tmp1 = nullptr;       // [n]
     uint32_t* ro_tmpu = nullptr;     // [n]
@@ -231,7 +233,8 @@ int dev_alloc(T** ptr, size_t count) {
 
 #define BH_TRY(expr) do { int rc__ = (expr); if (rc__ != BH_OK) return rc__; } while (0)
 
-constexpr int kReorderEvery = 16;   // steps between two physical re-sorts of the body arrays (resident Morton order)
+constexpr int kReorderEvery = 16;       // steps between two physical re-sorts of the body arrays (resident Morton order)
+constexpr int kRepartitionEvery = 64;   // the same on a multi-rank context (it costs an all-gather of the state + a full build)
 
 struct DeviceGuard {
     int prev = -1;
@@ -408,6 +411,7 @@ void accumulate_profile(bh_ctx* c) {
 }
 
 bool reorder_allowed(const bh_ctx* c);
+int reorder_period(const bh_ctx* c);
 int enqueue_reorder(bh_ctx* c);
 
 int run_steps(bh_ctx* c, int nsteps, bool from_snapshot) {
@@ -434,13 +438,13 @@ int run_steps(bh_ctx* c, int nsteps, bool from_snapshot) {
             cudaGraphDestroy(graph);
         }
         for (int s = 0; s < nsteps; ++s) {
-            if (!from_snapshot && reorder_allowed(c) && ++c->steps_since_reorder > kReorderEvery) BH_TRY(enqueue_reorder(c));
+            if (!from_snapshot && reorder_allowed(c) && ++c->steps_since_reorder > reorder_period(c)) BH_TRY(enqueue_reorder(c));
             BH_CUDA_OK(cudaGraphLaunch(c->graph[gi], c->stream));
             g_launches += c->graph_kernels[gi];
         }
     } else {
         for (int s = 0; s < nsteps; ++s) {
-            if (!from_snapshot && reorder_allowed(c) && !c->profiling && ++c->steps_since_reorder > kReorderEvery)
+            if (!from_snapshot && reorder_allowed(c) && !c->profiling && ++c->steps_since_reorder > reorder_period(c))
                 BH_TRY(enqueue_reorder(c));
             BH_TRY(enqueue_step(c, from_snapshot));
             accumulate_profile(c);
@@ -464,14 +468,36 @@ int reorder_alloc(bh_ctx* c) {
     return BH_OK;
 }
 
+// single rank: on unless BH_REORDER=0 (or FP64 verification mode without BH_REORDER=1).  Multi rank: the same, and it
+// needs the NCCL communicator (the re-partition gathers the slices); collective — every rank takes the same decision.
 bool reorder_allowed(const bh_ctx* c) {
-    return c->auto_reorder && c->p.n_ranks == 1 && !(c->p.flags & BH_FLAG_FP64_TRAVERSAL);
+    if (!c->auto_reorder) return false;
+    if ((c->p.flags & BH_FLAG_FP64_TRAVERSAL) && !c->force_reorder) return false;
+    if (c->p.flags & BH_FLAG_EXACT_LEAVES) return c->p.n_ranks == 1;
+    return c->p.n_ranks == 1 || c->comm != nullptr;
 }
+int reorder_period(const bh_ctx* c) { return c->p.n_ranks > 1 ? kRepartitionEvery : kReorderEvery; }
 
 // Sort the bodies by their current cell keys and move the state arrays into that order (asynchronous on the stream).
+// Multi-rank contexts (RE-PARTITIONING): every rank holds full-size arrays of which only its index slice is
+// current, so the slices are gathered first (NCCL broadcasts), every rank then does the SAME full build and the SAME
+// permutation — after which the fixed index slices [N r / R, N (r + 1) / R) are contiguous Morton ranges again,
+// whatever order the application handed the bodies over in and however far they have drifted since.
 int enqueue_reorder(bh_ctx* c) {
     BH_TRY(reorder_alloc(c));
-    BH_TRY(enqueue_build(c, false, nullptr, nullptr));
+    const bool multi = c->p.n_ranks > 1;
+    if (multi) {
+        if (!c->mass_complete) { BH_TRY(exchange_slices(c, c->mass, sizeof(double))); c->mass_complete = true; }
+        BH_TRY(exchange_slices(c, c->pos, sizeof(double2)));
+        BH_TRY(exchange_slices(c, c->vel, sizeof(double2)));
+        BH_TRY(exchange_slices(c, c->acc, sizeof(double2)));
+        BH_TRY(exchange_slices(c, c->force, sizeof(double2)));
+        if (c->have_snapshot) {
+            BH_TRY(exchange_slices(c, c->snap_pos, sizeof(double2)));
+            BH_TRY(exchange_slices(c, c->snap_vel, sizeof(double2)));
+        }
+    }
+    BH_TRY(enqueue_build(c, multi, nullptr, nullptr));
     const int64_t n = c->d.n;
     reorder_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
         c->idx[c->sorted], n, c->pos, c->vel, c->acc, c->force, c->mass, c->perm_identity ? nullptr : c->perm, c->ro_tmp2,
@@ -494,7 +520,9 @@ int enqueue_reorder(bh_ctx* c) {
     }
     c->perm_identity = false;
     c->steps_since_reorder = 0;
+    c->n_reorders += 1;
     c->tree_valid = false;          // sorted positions / self_node refer to the old internal indices
+    if (multi) c->mass_complete = true;
     return BH_OK;
 }
 
@@ -663,7 +691,7 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     { const char* e = getenv("BH_KEYS_TABLE"); c->keys_table = e ? e[0] == '1' : (p->n_bodies / p->n_ranks >= 1500000); }
     { const char* e = getenv("BH_PDL"); c->pdl = e && e[0] == '1' && p->n_ranks == 1; }
     { const char* e = getenv("BH_HOST_TRACE"); c->host_trace = e && e[0] == '1'; }
-    { const char* e = getenv("BH_REORDER"); c->auto_reorder = !(e && e[0] == '0'); }
+    { const char* e = getenv("BH_REORDER"); c->auto_reorder = !(e && e[0] == '0'); c->force_reorder = e && e[0] == '1'; }
     { const char* e = getenv("BH_HOST_PIPELINE_MULTI"); c->host_pipeline_multi = !(e && e[0] == '0'); }   // default on
     { const char* e = getenv("BH_HOST_CHUNKS"); if (e && atoi(e) >= 1) c->host_chunks = std::min(atoi(e), kMaxHostChunks); }
     if (p->device >= 0) c->device = p->device;
@@ -871,7 +899,7 @@ int bh_set_bodies(bh_ctx* c, const double* pos, const double* vel, const double*
     c->bodies_set = true;
     c->tree_valid = false;
     c->perm_identity = true;                       // caller's order
-    c->steps_since_reorder = kReorderEvery - 1;    // a multi-step run re-sorts the arrays before its second step
+    c->steps_since_reorder = reorder_period(c) - 1;   // a multi-step run re-sorts the arrays before its second step
     return BH_OK;
 }
 
@@ -940,6 +968,7 @@ int bh_step_host(bh_ctx* c, const double* pos, const double* vel, const double* 
         // the plain sequence below (tests/multi_gpu_check.py --host-step, profiles/r02_multi_gpu_check_g2.log);
         // 2 GPUs, 1M bodies each: 1.72 -> 1.56 ms per step.
         DeviceGuard g(c->device);
+        c->perm_identity = true;     // the call overwrites the rank's whole slice in the caller's order
         const int64_t lo = c->own_lo, cnt = c->own_hi - c->own_lo;
         BH_CUDA_OK(cudaEventRecord(c->ev0, c->stream));
         BH_CUDA_OK(cudaEventRecord(c->ev_fork, c->stream));
@@ -1186,6 +1215,7 @@ int bh_get_counters(bh_ctx* c, bh_counters* out) {
     out->interactions = v[0]; out->visits = v[1]; out->opens = v[2]; out->warp_steps = v[3]; out->nodes = v[4];
     out->heavy_cells = (uint64_t)heavy + huge;   // cell_runs_kernel queues the two kinds separately
     out->zero_mass_bodies = c->zero_mass_bodies;
+    out->reorders = c->n_reorders;
     return BH_OK;
 }
 
@@ -1243,7 +1273,7 @@ int bh_generate(bh_ctx* c, int32_t kind, uint64_t seed) {
     c->mass_complete = c->p.n_ranks == 1;
     c->zero_mass_bodies = 0;                 // log-uniform in [0.1, 0.5]
     c->perm_identity = true;
-    c->steps_since_reorder = kReorderEvery - 1;
+    c->steps_since_reorder = reorder_period(c) - 1;
     c->bodies_set = true;
     c->tree_valid = false;
     return BH_OK;

@@ -89,7 +89,7 @@ typedef struct bh_counters {
                                   one as EMPTY and overwrites it (project.cu:393-405), which makes its topology depend
                                   on the insertion order; the engine counts every body (order-independent tree) and
                                   reports the condition here instead of reproducing it */
-    uint64_t reserved[1];
+    uint64_t reorders;     /* physical re-sorts of the body arrays (single rank) / re-partitions (multi rank) since bh_create */
 } bh_counters;
 
 /* Accumulated device time per phase in microseconds (cudaEvent, only while profiling is on). */

@@ -25,7 +25,12 @@ ap.add_argument("--no-p2p", action="store_true", help="NCCL all-reduces instead 
 ap.add_argument("--host-step", action="store_true",
                 help="also check ONE bh_step_host call (own slice up / down) against the single-GPU step; with "
                      "BH_HOST_PIPELINE_MULTI=1 this exercises the pipelined multi-rank host step")
+ap.add_argument("--repartition", action="store_true",
+                help="bodies in random order + BH_REORDER=1: the engine re-partitions (gathers the slices, full build, global "
+                     "permutation) before the second step, so that every rank's index slice is a Morton range again")
 a = ap.parse_args()
+if a.repartition:
+    os.environ["BH_REORDER"] = "1"       # also in FP64 mode
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -50,7 +55,11 @@ if a.host_step:
     host_slice = sim.step_host(pos, vel, mass)[lo_r:hi_r].copy()      # a rank's call fills only its own slice
 sim.set_bodies(pos, vel, mass)
 sim.step(a.steps)
+n_reorders = sim.counters()["reorders"]
 p_multi, v_multi, f_multi = sim.positions(), sim.velocities(), sim.forces()
+if a.repartition:
+    print(f"rank {rank}: {n_reorders} re-partition(s) in {a.steps} steps", flush=True)
+    assert n_reorders >= 1
 sim.close()
 ok = True
 if a.host_step:
@@ -77,6 +86,8 @@ if rank == 0:
     # reference's sequential running average): node COMs differ by ~1e-16 relative, which the
     # self-inclusive near-COM interactions amplify to ~1e-9 of the force
     tol = 1e-8 if a.fp64 else 1e-6
+    if a.repartition and not a.fp64:
+        tol = 1e-4      # two FP32 runs whose in-cell summation orders differ drift apart by ~1e-7 per step
     errs = {"pos": rel(p_multi, p_one), "vel": rel(v_multi, v_one), "force": rel(f_multi, f_one)}
     print(f"world={world} n={a.n} steps={a.steps} fp64={a.fp64} p2p={not a.no_p2p} multi-vs-single rel-RMS {errs} (tol {tol})", flush=True)
     ok = all(e <= tol for e in errs.values())
