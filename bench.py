@@ -435,7 +435,7 @@ def run_ours(args):
         return out
 
     pos, vel, mass = make_workload(n, args.dist)
-    if world > 1:
+    if world > 1 and not args.no_presort:
         pos, vel, mass = morton_order(pos, vel, mass, n)
     sim = make_sim(n, world)
     sim.set_bodies(pos, vel, mass)
@@ -733,6 +733,8 @@ def main():
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-reduces instead of the peer-memory exchange")
     ap.add_argument("--total-bodies", type=int, default=0,
                     help="strong scaling: total body count over all GPUs (default: weak scaling, 1M per GPU)")
+    ap.add_argument("--no-presort", action="store_true",
+                    help="N > 1: hand the bodies over in the generator's (random) order and let the engine re-partition")
     ap.add_argument("--quick", action="store_true",
                     help="headline brackets + phases only (no e2e, accuracy, baselines, strong, direct): scaling scripts")
     ap.add_argument("--reference-lines", action="store_true",
