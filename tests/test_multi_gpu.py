@@ -188,3 +188,74 @@ def test_gloo_world2_sharded_build_gives_the_global_tree(tmp_path, n, max_depth)
     nz = want[:, 5] > 0
     assert np.allclose(got0[nz, 2], want[nz, 6], rtol=1e-12, atol=1e-18)
     assert np.allclose(got0[nz, 3], want[nz, 7], rtol=1e-12, atol=1e-18)
+
+
+# ------------------------------------------------------------------------------------------------
+# Re-partitioning: every rank gathers the slices, computes the SAME keys / stable order / permutation and
+# applies it to its full-size arrays; the fixed index slices are then contiguous Morton ranges and the getters
+# (gather, then un-permute) still return the caller's order.  gloo + numpy model of csrc/api.cu: enqueue_reorder.
+# ------------------------------------------------------------------------------------------------
+def _repartition_worker(rank, world, port, n, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import gpu_nbody_simulation_b200 as bh
+    import oracle
+    from gpu_nbody_simulation_b200 import initial_conditions as ic
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pos, vel, mass = ic.uniform_disk(n, seed=7, round6=False)
+    sizes = [bh.shard_range(n, world, r) for r in range(world)]
+    lo, hi = sizes[rank]
+    # full-size arrays of which only the own slice is current (the others hold garbage, like on the device)
+    rng = np.random.default_rng(100 + rank)
+    p = rng.normal(size=(n, 2)); p[lo:hi] = pos[lo:hi]
+    v = rng.normal(size=(n, 2)); v[lo:hi] = vel[lo:hi]
+
+    def gather(a):                      # exchange_slices: one broadcast per owner
+        for r, (l, h) in enumerate(sizes):
+            t = torch.from_numpy(np.ascontiguousarray(a[l:h]))
+            dist.broadcast(t, src=r)
+            a[l:h] = t.numpy()
+    gather(p); gather(v)
+    keys = oracle.body_keys(p, oracle.root_bounds(p))        # the full build, identical on every rank
+    order = np.argsort(keys, kind="stable")                  # sidx
+    p, v, perm = p[order], v[order], order.copy()            # reorder_gather_kernel (perm: internal -> original)
+    own_keys = keys[order][lo:hi]
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), perm=perm, kmin=own_keys.min(), kmax=own_keys.max(),
+             pos_slice=p[lo:hi], vel_slice=v[lo:hi])
+    # a getter: gather the (internal-order) slices, then un-permute
+    p[:lo] = 0; p[hi:] = 0
+    gather(p)
+    out = np.empty_like(p); out[perm] = p
+    np.save(os.path.join(out_dir, f"get_r{rank}.npy"), out)
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_repartition_protocol(tmp_path):
+    import torch.multiprocessing as mp
+    from gpu_nbody_simulation_b200 import initial_conditions as ic
+    n, world = 5001, 2
+    mp.spawn(_repartition_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    pos, vel, mass = ic.uniform_disk(n, seed=7, round6=False)
+    r = [np.load(os.path.join(tmp_path, f"r{k}.npz")) for k in range(world)]
+    assert np.array_equal(r[0]["perm"], r[1]["perm"])                        # the same permutation on every rank
+    assert np.array_equal(np.sort(r[0]["perm"]), np.arange(n))
+    assert int(r[0]["kmax"]) <= int(r[1]["kmin"])                            # index slices = contiguous Morton ranges
+    for k in range(world):
+        assert np.array_equal(np.load(os.path.join(tmp_path, f"get_r{k}.npy")), pos)   # getters: the caller's order
+
+
+@pytest.mark.gpu
+def test_two_gpus_repartition_free_running_fp64():
+    """20 free-running FP64 steps on 2 ranks with bodies in random order and one re-partition, against the single-GPU
+    context (<= 1e-8) and the CPU oracle (<= 1e-8): tests/multi_gpu_check.py --repartition."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "multi_gpu_check.py"), "--bodies", "100001",
+           "--steps", "20", "--fp64", "--repartition"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert "MULTI_GPU_CHECK PASS" in res.stdout and "re-partition(s)" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
