@@ -555,27 +555,29 @@ def run_ours(args):
     del f_gpu
 
     # ---- end to end through the C-ABI with host buffers --------------------------------------------
-    hp = torch.from_numpy(pos).pin_memory()
-    hv = torch.from_numpy(vel).pin_memory()
-    hm = torch.from_numpy(mass).pin_memory()
-    hout = torch.empty((n, 2), dtype=torch.float64).pin_memory()
-    for _ in range(max(1, min(W, 3))):
-        sim.step_host(hp, hv, hm, hout)
-    e2e_runs = []
-    for _ in range(1 if args.quick else max(3, min(R, 10))):
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            # bh_step_host: H2D of this step's inputs (pinned), one step, D2H of its result; synchronous
+    e2e = None
+    if not args.no_e2e:
+        hp = torch.from_numpy(pos).pin_memory()
+        hv = torch.from_numpy(vel).pin_memory()
+        hm = torch.from_numpy(mass).pin_memory()
+        hout = torch.empty((n, 2), dtype=torch.float64).pin_memory()
+        for _ in range(max(1, min(W, 3))):
             sim.step_host(hp, hv, hm, hout)
-        barrier()
-        e2e_runs.append(max_over_ranks(time.perf_counter() - t0))
-    e2e_s = statistics.median(e2e_runs)
-    per_rank = own_hi - own_lo
-    e2e = {"value": n * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(40 * n), "d2h_bytes_per_step": int(16 * n),
-           "ms_per_step": e2e_s / K * 1e3, "brackets": len(e2e_runs),
-           "note": f"each rank moves its own slice ({per_rank} bodies: {40 * per_rank} B up, {16 * per_rank} B down) over its own PCIe link"}
-    del hp, hv, hm, hout
+        e2e_runs = []
+        for _ in range(1 if args.quick else max(3, min(R, 10))):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                # bh_step_host: H2D of this step's inputs (pinned), one step, D2H of its result; synchronous
+                sim.step_host(hp, hv, hm, hout)
+            barrier()
+            e2e_runs.append(max_over_ranks(time.perf_counter() - t0))
+        e2e_s = statistics.median(e2e_runs)
+        per_rank = own_hi - own_lo
+        e2e = {"value": n * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(40 * n), "d2h_bytes_per_step": int(16 * n),
+               "ms_per_step": e2e_s / K * 1e3, "brackets": len(e2e_runs),
+               "note": f"each rank moves its own slice ({per_rank} bodies: {40 * per_rank} B up, {16 * per_rank} B down) over its own PCIe link"}
+        del hp, hv, hm, hout
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not strong_only:
@@ -733,6 +735,7 @@ def main():
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-reduces instead of the peer-memory exchange")
     ap.add_argument("--total-bodies", type=int, default=0,
                     help="strong scaling: total body count over all GPUs (default: weak scaling, 1M per GPU)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (very large N: pinned host memory)")
     ap.add_argument("--no-presort", action="store_true",
                     help="N > 1: hand the bodies over in the generator's (random) order and let the engine re-partition")
     ap.add_argument("--quick", action="store_true",

@@ -314,7 +314,7 @@ int enqueue_build(bh_ctx* c, bool full, const double2* src, cudaEvent_t mass_rea
     const bool sharded = c->p.n_ranks > 1 && !full;
     if (!sharded) {
         launch_bounds(src, c->d.n, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream);
-        launch_keys(src, c->d.n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream, 0,
+        launch_keys(src, c->d.n, c->d, c->sp, c->consts, c->keys[0], c->tree.count + c->d.level_off[c->d.finest], c->s.digit_hist, c->stream, 0,
                     c->s.cell_bnd);
         prof_mark(c, 1);
         launch_sort(c->keys, c->idx, c->d.n, c->sp, c->s, &c->sorted, c->stream, 0u);
@@ -331,7 +331,7 @@ int enqueue_build(bh_ctx* c, bool full, const double2* src, cudaEvent_t mass_rea
             BH_TRY(allreduce_f64(c, c->bbox_raw, 4, ncclMin));
             launch_bounds_finalize(c->bbox_raw, c->p, c->d, c->s, c->consts, c->stream);
         }
-        launch_keys(src + lo, n_own, c->d, c->sp_own, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream,
+        launch_keys(src + lo, n_own, c->d, c->sp_own, c->consts, c->keys[0], c->tree.count + c->d.level_off[c->d.finest], c->s.digit_hist, c->stream,
                     (uint32_t)lo, c->s.cell_bnd);
         prof_mark(c, 1);
         launch_sort(c->keys, c->idx, n_own, c->sp_own, c->s, &c->sorted, c->stream, (uint32_t)lo);
@@ -610,7 +610,7 @@ int enqueue_host_step(bh_ctx* c, const double* pos, const double* vel, const dou
     zero_scratch(c);
     BH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_up[0], 0));
     launch_bounds(c->pos, n, c->p, c->d, c->s, c->consts, c->bounds_grid, c->stream);
-    launch_keys(c->pos, n, c->d, c->sp, c->consts, c->keys[0], c->idx[0], c->s.digit_hist, c->stream, 0, c->s.cell_bnd);
+    launch_keys(c->pos, n, c->d, c->sp, c->consts, c->keys[0], c->tree.count + c->d.level_off[c->d.finest], c->s.digit_hist, c->stream, 0, c->s.cell_bnd);
     launch_sort(c->keys, c->idx, n, c->sp, c->s, &c->sorted, c->stream, 0u);
     if (nch > 1) launch_chunk_lists(c->idx[c->sorted], n, cb, c->chunk_counts, c->chunk_lists, c->stream);
     trace_mark(c, "gpu: sort+lists done", c->stream);
@@ -721,8 +721,9 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     // Everything from the finest level's counts to the end is zeroed by ONE memset per step (zero_scratch).
     const int nbins = 1 << c->sp.nbins_log2;
     const size_t np_pad = ((size_t)np + 3) & ~(size_t)3;   // keeps the 64-bit counters 8-byte aligned
+    const size_t scan_tiles = (size_t)((c->d.ncells_finest + 4095) / 4096);
     size_t words = (size_t)kMaxSortPasses * kMaxBins + 16 /*tickets, heavy, bbox ticket*/ + 16 /*8 x u64 counters*/ +
-                   (size_t)c->sp.passes * c->sp.ntiles * nbins;
+                   (size_t)c->sp.passes * c->sp.ntiles * nbins + scan_tiles;
     words = (words + 3) & ~(size_t)3;
     c->s.max_huge = n / kHugeCellMin + 1;
     const size_t huge_words = (size_t)c->s.max_huge + 1;    // [max_huge] = huge_count
@@ -737,6 +738,8 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     c->s.bbox_ticket = c->s.tickets + 9;
     c->s.counters = (unsigned long long*)(c->s.tickets + 16);
     c->s.tile_state = c->s.tickets + 32;
+    c->s.scan_ticket = c->s.tickets + 10;
+    c->s.scan_state = c->s.tile_state + (size_t)c->sp.passes * c->sp.ntiles * nbins;
     c->s.huge_tickets = zb + words;
     c->s.huge_count = c->s.huge_tickets + c->s.max_huge;
     cudaDeviceProp prop;
@@ -1213,7 +1216,7 @@ int bh_get_counters(bh_ctx* c, bh_counters* out) {
     BH_CUDA_OK(cudaStreamSynchronize(c->stream));
     memset(out, 0, sizeof *out);
     out->interactions = v[0]; out->visits = v[1]; out->opens = v[2]; out->warp_steps = v[3]; out->nodes = v[4];
-    out->heavy_cells = (uint64_t)heavy + huge;   // cell_runs_kernel queues the two kinds separately
+    out->heavy_cells = (uint64_t)heavy + huge;   // cell_scan_kernel queues the two kinds separately
     out->zero_mass_bodies = c->zero_mass_bodies;
     out->reorders = c->n_reorders;
     return BH_OK;

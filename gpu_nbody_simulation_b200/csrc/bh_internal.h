@@ -74,6 +74,8 @@ struct Scratch {
     uint32_t* heavy_count;    // 1
     unsigned long long* counters;  // [8] interactions, visits, opens, warp_steps, nodes, heavy
     uint32_t* bbox_ticket;    // 1
+    uint32_t* scan_ticket;    // 1   cell_scan_kernel: tile order
+    uint32_t* scan_state;     // [ceil(finest cells / 4096)] decoupled look-back states of the cell scan
     uint32_t* finest_count;   // alias of tree.count at the finest level (inside the zeroed block)
     // not zeroed:
     double* bbox_partial;     // [grid][4]
@@ -125,8 +127,8 @@ void peer_comm_layout(PeerComm& pc, int rank, int n_ranks, uint64_t ncells, size
 void launch_bounds_finalize(const double* raw, const bh_params& p, const Dims& d, Scratch& s, StepConsts* consts,
                             cudaStream_t st);
 void launch_keys(const double2* pos, int64_t n, const Dims& d, const SortPlan& sp, const StepConsts* consts,
-                 uint32_t* keys, uint32_t* idx, uint32_t* digit_hist, cudaStream_t st, uint32_t idx_base,
-                 const double* cell_bnd);   // cell_bnd: Scratch::cell_bnd (table lookup) or nullptr (bisection)
+                 uint32_t* keys, uint32_t* cell_count, uint32_t* digit_hist, cudaStream_t st, uint32_t idx_base,
+                 const double* cell_bnd);   // cell_count: finest level of TreeArrays::count (zeroed); cell_bnd: table or nullptr
 // pc != nullptr (sharded build with the peer-memory exchange): the partial sums of this rank's non-empty cells go
 // straight into every rank's inbox (launch_tree_runs), and the level pass adds the ranks' contributions itself
 void launch_tree_runs(const uint32_t* skeys, const uint32_t* sidx, const double2* pos, const double* mass,

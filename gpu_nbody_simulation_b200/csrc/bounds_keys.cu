@@ -203,7 +203,7 @@ __device__ __forceinline__ uint32_t locate_cell(double x, double x0, double inv_
 template <bool TABLE>
 __global__ void __launch_bounds__(256)
 keys_kernel(const double2* __restrict__ pos, int64_t n, int finest, const StepConsts* __restrict__ consts,
-            uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ digit_hist,
+            uint32_t* __restrict__ keys, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ digit_hist,
             int passes, int bits_per_pass, uint32_t idx_base, const double* __restrict__ cell_bnd) {
     __shared__ uint32_t hist[kMaxSortPasses * kMaxBins];
     pdl_entry();
@@ -238,6 +238,13 @@ keys_kernel(const double2* __restrict__ pos, int64_t n, int finest, const StepCo
             }
         }
         keys[i] = key;               // (the first sort pass generates the body indices idx_base + i itself)
+        {   // bodies per finest cell (zeroed every step): the cell runs of the sorted order follow from these counts by
+            // a scan (tree_build.cu: cell_scan_kernel), without a pass over the sorted keys.  One atomic per distinct
+            // key of the warp (bodies in resident order share cells with their neighbours).
+            const uint32_t act = __activemask();
+            const uint32_t peers = __match_any_sync(act, key);
+            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(cell_count + key, (uint32_t)__popc(peers));
+        }
         for (int ps = 0; ps < passes; ++ps)
             atomicAdd(&hist[ps * kMaxBins + ((key >> (ps * bits_per_pass)) & dmask)], 1u);
     }
@@ -268,16 +275,16 @@ void launch_bounds_finalize(const double* raw, const bh_params& p, const Dims& d
 }
 
 void launch_keys(const double2* pos, int64_t n, const Dims& d, const SortPlan& sp, const StepConsts* consts,
-                 uint32_t* keys, uint32_t* idx, uint32_t* digit_hist, cudaStream_t st, uint32_t idx_base,
+                 uint32_t* keys, uint32_t* cell_count, uint32_t* digit_hist, cudaStream_t st, uint32_t idx_base,
                  const double* cell_bnd) {
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     if (cell_bnd)
-        launch_chain(keys_kernel<true>, dim3((unsigned)blocks), dim3(256), st, true, pos, n, d.finest, consts, keys, idx,
+        launch_chain(keys_kernel<true>, dim3((unsigned)blocks), dim3(256), st, true, pos, n, d.finest, consts, keys, cell_count,
                      digit_hist, sp.passes, sp.bits_per_pass, idx_base, cell_bnd);
     else
-        launch_chain(keys_kernel<false>, dim3((unsigned)blocks), dim3(256), st, true, pos, n, d.finest, consts, keys, idx,
+        launch_chain(keys_kernel<false>, dim3((unsigned)blocks), dim3(256), st, true, pos, n, d.finest, consts, keys, cell_count,
                      digit_hist, sp.passes, sp.bits_per_pass, idx_base, (const double*)nullptr);
     ++g_launches;
 }

@@ -112,55 +112,95 @@ __device__ __forceinline__ void store_cell(const TreeArrays& t, uint64_t at, con
     if (level == 0 && c.cnt == 1u && c.first != kNoFirst) t.self_node[sidx[c.first]] = 0u;   // a lone body: the root is its leaf
 }
 
-// ---- finest-cell runs from the sorted keys ------------------------------------------------------
-// The thread at the LAST body of a run finds the run's start by binary search and records
-// (first, count); runs longer than exact_leaf_max are queued for the parallel summation kernel.
+// ---- finest-cell runs: exclusive scan of the per-cell body counts ------------------------------------------------
+// The key kernel counts the bodies of every finest cell (bounds_keys.cu); a cell's run in the sorted order starts at
+// the number of bodies in all cells with a smaller key.  One pass with decoupled look-back over 4096-cell tiles
+// (atomic ticket = tile order, so every tile a block waits on is resident).  Round 1 found the runs from the sorted
+// keys (one thread per BODY, binary searches, 20 us at 1M bodies and 157 us at 16M); this is one thread per 16 CELLS,
+// 262 144 cells at the default cap whatever N.  Over-full cells are queued here too (one atomic per warp and queue).
+#define kScanAgg (1u << 30)
+#define kScanIncl (2u << 30)
+#define kScanVal ((1u << 30) - 1u)
+constexpr int kScanItems = 16;
+
 __global__ void __launch_bounds__(256)
-cell_runs_kernel(const uint32_t* __restrict__ skeys, int64_t n, uint32_t* __restrict__ cnt_f,
-                 uint32_t* __restrict__ first_f, uint32_t exact_leaf_max, uint32_t* __restrict__ heavy_list,
-                 uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ huge_list, uint32_t* __restrict__ huge_count) {
+cell_scan_kernel(const uint32_t* __restrict__ cnt_f, uint32_t* __restrict__ first_f, uint64_t ncells,
+                 uint32_t exact_leaf_max, uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_count,
+                 uint32_t* __restrict__ huge_list, uint32_t* __restrict__ huge_count, uint32_t* state, uint32_t* ticket) {
+    __shared__ uint32_t s_tile, s_prev;
+    __shared__ uint32_t s_warp[8];
     pdl_entry();
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const bool in = j < n;
-    const uint32_t k = in ? skeys[j] : 0u;
-    const bool head = in && (j == 0 || skeys[j - 1] != k);
-    const bool tail = in && (j + 1 >= n || skeys[j + 1] != k);
-    // run start: the nearest head at or below this lane inside the warp, else binary search
-    const uint32_t heads = __ballot_sync(0xffffffffu, head) & (0xffffffffu >> (31 - lane));
-    uint32_t c = 0;
-    if (tail) {
-        int64_t lo;
-        if (heads) {
-            lo = j - lane + (31 - __clz(heads));
-        } else {
-            lo = 0;
-            int64_t hi = j - lane;   // the run began before this warp's first key
-            while (lo < hi) {        // first position with key >= k
-                int64_t mid = (lo + hi) >> 1;
-                if (skeys[mid] < k) lo = mid + 1; else hi = mid;
-            }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t c0 = (uint64_t)tile * (256 * kScanItems) + (uint64_t)tid * kScanItems;
+    uint32_t cnt[kScanItems];
+    uint32_t local = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {        // (the finest level starts at an odd offset of the pyramid: scalar loads)
+        cnt[k] = (c0 + k < ncells) ? __ldg(cnt_f + c0 + k) : 0u;
+        local += cnt[k];
+    }
+    uint32_t inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { woff += (w < warp) ? s_warp[w] : 0u; total += s_warp[w]; }
+    if (warp == 0) {
+        // publish this tile's count, then add up the tiles before it (window of 32 states, nearest first)
+        volatile uint32_t* st = state;
+        if (lane == 0) st[tile] = (tile == 0 ? kScanIncl : kScanAgg) | total;
+        uint32_t prev = 0;
+        int64_t t = (int64_t)tile - 1;
+        while (t >= 0) {
+            const int64_t i = t - lane;
+            const uint32_t v = i >= 0 ? st[i] : kScanIncl;            // before tile 0: an inclusive prefix of 0
+            const uint32_t not_ready = __ballot_sync(0xffffffffu, v == 0u);
+            const uint32_t incl = __ballot_sync(0xffffffffu, (v >> 30) == 2u);
+            const int first_incl = incl ? __ffs(incl) - 1 : 32;
+            if (not_ready & ((first_incl >= 31) ? 0xffffffffu : ((2u << first_incl) - 1u))) continue;   // not published yet: look again
+            uint32_t x = (lane <= first_incl) ? (v & kScanVal) : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            prev += x;
+            if (incl) break;
+            t -= 32;
         }
-        c = (uint32_t)(j + 1 - lo);
-        cnt_f[k] = c;
-        first_f[k] = (uint32_t)lo;
+        if (lane == 0) {
+            if (tile > 0) { __threadfence(); st[tile] = kScanIncl | (prev + total); }
+            s_prev = prev;
+        }
     }
-    // queue over-full cells: ONE atomic per warp and queue (at 16M bodies nearly every cell is over-full; one atomic per
-    // cell on a single counter serialised 143 000 of them)
-    const bool over = c > exact_leaf_max, huge = over && c > kHugeCellMin, heavy = over && !huge;
-    const uint32_t mh = __ballot_sync(0xffffffffu, heavy), mg = __ballot_sync(0xffffffffu, huge);
-    const uint32_t lt = (1u << lane) - 1u;
-    if (mh) {
-        uint32_t base = 0;
-        if (lane == __ffs(mh) - 1) base = atomicAdd(heavy_count, (uint32_t)__popc(mh));
-        base = __shfl_sync(0xffffffffu, base, __ffs(mh) - 1);
-        if (heavy) heavy_list[base + __popc(mh & lt)] = k;                   // one block-independent warp each
-    }
-    if (mg) {
-        uint32_t base = 0;
-        if (lane == __ffs(mg) - 1) base = atomicAdd(huge_count, (uint32_t)__popc(mg));
-        base = __shfl_sync(0xffffffffu, base, __ffs(mg) - 1);
-        if (huge) huge_list[base + __popc(mg & lt)] = k;                     // summed by kHugeParts blocks each
+    __syncthreads();
+    uint32_t run = s_prev + woff + inc - local;       // sorted position of the first body of this thread's first cell
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const uint64_t c = c0 + k;
+        const uint32_t n_c = cnt[k];
+        if (c < ncells) first_f[c] = run;
+        run += n_c;
+        const bool over = n_c > exact_leaf_max, huge = over && n_c > kHugeCellMin, heavy = over && !huge;
+        const uint32_t mh = __ballot_sync(0xffffffffu, heavy), mg = __ballot_sync(0xffffffffu, huge);
+        const uint32_t lt = (1u << lane) - 1u;
+        if (mh) {
+            uint32_t base = 0;
+            if (lane == __ffs(mh) - 1) base = atomicAdd(heavy_count, (uint32_t)__popc(mh));
+            base = __shfl_sync(0xffffffffu, base, __ffs(mh) - 1);
+            if (heavy) heavy_list[base + __popc(mh & lt)] = (uint32_t)c;      // one warp each
+        }
+        if (mg) {
+            uint32_t base = 0;
+            if (lane == __ffs(mg) - 1) base = atomicAdd(huge_count, (uint32_t)__popc(mg));
+            base = __shfl_sync(0xffffffffu, base, __ffs(mg) - 1);
+            if (huge) huge_list[base + __popc(mg & lt)] = (uint32_t)c;        // summed by kHugeParts blocks each
+        }
     }
 }
 
@@ -276,7 +316,7 @@ __device__ __forceinline__ void huge_cells(uint32_t p, uint32_t slot, double (*s
     }
 }
 
-// One launch for both kinds of over-full finest cells (cell_runs_kernel queues them separately).
+// One launch for both kinds of over-full finest cells (cell_scan_kernel queues them separately).
 __global__ void __launch_bounds__(256)
 heavy_huge_kernel(const uint32_t* __restrict__ heavy_list, const uint32_t* __restrict__ heavy_count,
                   const uint32_t* __restrict__ huge_list, const uint32_t* __restrict__ huge_count,
@@ -587,11 +627,11 @@ void launch_tree_runs(const uint32_t* skeys, const uint32_t* sidx, const double2
     uint32_t* first_f = t.first + d.level_off[F];
     const uint64_t nc = d.ncells_finest;
     uint32_t exact_max = (uint32_t)(p.exact_leaf_max < 0 ? 0 : p.exact_leaf_max);
-    if (n > 0) {
-        launch_chain(cell_runs_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), st, true, skeys, n, cnt_f, first_f,
-                     exact_max, s.heavy_list, s.heavy_count, s.huge_list, s.huge_count);
-        ++g_launches;
-    }
+    (void)skeys;
+    launch_chain(cell_scan_kernel, dim3((unsigned)((nc + 256 * kScanItems - 1) / (256 * kScanItems))), dim3(256), st, true,
+                 (const uint32_t*)cnt_f, first_f, nc, exact_max, s.heavy_list, s.heavy_count, s.huge_list, s.huge_count,
+                 s.scan_state, s.scan_ticket);
+    ++g_launches;
     const unsigned hh_blocks = kHeavyBlocks + kHugeParts * kHugeSlots;
     if (sums) {
         heavy_huge_kernel<<<hh_blocks, 256, 0, st>>>(s.heavy_list, s.heavy_count, s.huge_list, s.huge_count, cnt_f, first_f,
@@ -606,8 +646,7 @@ void launch_tree_runs(const uint32_t* skeys, const uint32_t* sidx, const double2
                                                                                      exact_max, sums, none);
         ++g_launches;
     } else {
-        // (n > 0 here: the previous operation on the stream is cell_runs_kernel)
-        launch_chain(heavy_huge_kernel, dim3(hh_blocks), dim3(256), st, n > 0, (const uint32_t*)s.heavy_list,
+        launch_chain(heavy_huge_kernel, dim3(hh_blocks), dim3(256), st, true, (const uint32_t*)s.heavy_list,
                      (const uint32_t*)s.heavy_count, (const uint32_t*)s.huge_list, (const uint32_t*)s.huge_count,
                      (const uint32_t*)cnt_f, (const uint32_t*)first_f, sidx, pos, mass, t.mass + d.level_off[F],
                      t.comx + d.level_off[F], t.comy + d.level_off[F], false, s.huge_partial, s.huge_tickets);

@@ -11,12 +11,12 @@ if [ "$G" -eq 1 ]; then L="python"; else
     L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port $((29600 + G))"; fi
 for N in 4000000 16000000 64000000; do
     steps=$(( N >= 64000000 ? 10 : 30 ))
-    timeout 400 $L bench.py --gpus "$G" --steps $steps --warmup 3 --total-bodies $N --no-cpu-baseline --no-gpu-baseline \
+    timeout 400 $L bench.py --gpus "$G" --steps $steps --warmup 3 --total-bodies $N --quick --no-e2e \
         > "gpurun_out/r2_strong_${N}_g${G}.json" 2> "gpurun_out/r2_strong_${N}_g${G}.err"
 done
 for D in 10 12; do
     timeout 400 $L bench.py --gpus "$G" --steps 20 --warmup 3 --total-bodies 16000000 --dist plummer --max-depth $D \
-        --no-cpu-baseline --no-gpu-baseline > "gpurun_out/r2_plummer16M_cap${D}_g${G}.json" 2> "gpurun_out/r2_plummer16M_cap${D}_g${G}.err"
+        --quick --no-e2e > "gpurun_out/r2_plummer16M_cap${D}_g${G}.json" 2> "gpurun_out/r2_plummer16M_cap${D}_g${G}.err"
 done
 python - <<'PY'
 import glob, json
@@ -25,5 +25,5 @@ for f in sorted(glob.glob("gpurun_out/r2_strong_*_g*.json") + glob.glob("gpurun_
         if ln.startswith("{"):
             d = json.loads(ln)
             print(f.split("/")[-1], d["n_gpus"], "GPUs", round(d["value"] / 1e9, 3), "G body-steps/s", round(d["ms_per_step"], 4), "ms/step",
-                  "e2e", round(d["e2e"]["value"] / 1e9, 3), d["clocks"])
+                  d["phases_us"], d["clocks"])
 PY
