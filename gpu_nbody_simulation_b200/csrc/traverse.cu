@@ -33,7 +33,6 @@
 //
 // FP64 mode (BH_FLAG_FP64_TRAVERSAL): the reference's expressions verbatim on the FP64 tree arrays.
 #include <algorithm>
-#include <type_traits>
 
 #include "bh_internal.h"
 
@@ -774,19 +773,13 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
         accy = __ffma2_rn(f, dy, accy);
     };
     // class M: the per-body test of the pair kernel; returns the ballots of the bodies that open the node
-    // far_tag = std::true_type: the node is far from the warp's box (dmin^2 >= diag^2 / 64, nearly every class-M node:
-    // they sit around 2 x their size away) — single-float displacement as for far class-A nodes
-    auto eval_mixed = [&](auto far_tag, const float4 A, const float gm, const float thr, const uint32_t idx, const uint32_t pm0,
+    auto eval_mixed = [&](const float4 A, const float gm, const float thr, const uint32_t idx, const uint32_t pm0,
                           const uint32_t pm1, uint32_t& m0, uint32_t& m1) {
-        constexpr bool FAR = decltype(far_tag)::value;
         const bool a0 = pm0 & lanebit, a1 = pm1 & lanebit;
         const float2 mxh = make_float2(a0 ? nxh.x : kFarLane, a1 ? nxh.y : kFarLane);
         const float2 myh = make_float2(a0 ? nyh.x : kFarLane, a1 ? nyh.y : kFarLane);
-        float2 dx = __fadd2_rn(make_float2(A.x, A.x), mxh), dy = __fadd2_rn(make_float2(A.y, A.y), myh);
-        if constexpr (!FAR) {
-            dx = __fadd2_rn(dx, __fadd2_rn(make_float2(A.z, A.z), nxl));
-            dy = __fadd2_rn(dy, __fadd2_rn(make_float2(A.w, A.w), nyl));
-        }
+        const float2 dx = __fadd2_rn(__fadd2_rn(make_float2(A.x, A.x), mxh), __fadd2_rn(make_float2(A.z, A.z), nxl));
+        const float2 dy = __fadd2_rn(__fadd2_rn(make_float2(A.y, A.y), myh), __fadd2_rn(make_float2(A.w, A.w), nyl));
         const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
         const float2 g = gfactor(d2, gm);
         float2 f;
@@ -830,7 +823,7 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
         const float2 B = __ldg(reinterpret_cast<const float2*>(a.rec) + 2);
         const ListWarpConsts& wc = s_wc[warp];
         uint32_t m0, m1;
-        eval_mixed(std::false_type{}, to_local(R, wc), B.x, B.y, 0u, wc.live0, wc.live1, m0, m1);
+        eval_mixed(to_local(R, wc), B.x, B.y, 0u, wc.live0, wc.live1, m0, m1);
         if ((m0 | m1) != 0u) {
             if (lane == 0) stack[0] = make_uint4(0u, m0, m1, 0u);
             top = 1;
@@ -857,7 +850,7 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
         }
         const float gm = __uint_as_float(Bq.x), thr = __uint_as_float(Bq.y);
         uint32_t pm0 = ent.y, pm1 = ent.z;
-        // ---- classify: 0 dropped, 1 far A full mask, 2 far A partial mask, 3 near A, 4 O, 5 near M, 6 far M ----
+        // ---- classify: 0 dropped, 1 far A full mask, 2 far A partial mask, 3 near A, 4 O, 5 M ----
         int cls = 0;
         float4 L = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid && gm != 0.f) {
@@ -881,25 +874,24 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
                 cls = (dmin2 > thr * (1.f + kListDelta)) ? 1 : (dmax2 <= thr * (1.f - kListDelta)) ? 4 : 5;
             }
             if (cls == 1) cls = !(dmin2 >= wc.far2) ? 3 : (pm0 != wc.live0 || pm1 != wc.live1) ? 2 : 1;
-            else if (cls == 5 && dmin2 >= wc.far2) cls = 6;
             if ((pm0 | pm1) == 0u) cls = 0;                   // (a lone body's own leaf)
         }
         const uint32_t b1 = __ballot_sync(0xffffffffu, cls == 1), b2 = __ballot_sync(0xffffffffu, cls == 2);
         const uint32_t b3 = __ballot_sync(0xffffffffu, cls == 3), b4 = __ballot_sync(0xffffffffu, cls == 4);
-        const uint32_t b5 = __ballot_sync(0xffffffffu, cls == 5), b6 = __ballot_sync(0xffffffffu, cls == 6);
-        const int n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3), n5 = __popc(b5), n6 = __popc(b6);
+        const uint32_t b5 = __ballot_sync(0xffffffffu, cls == 5);
+        const int n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3), n5 = __popc(b5);
         sts_v4_if(cls == 4, stack + top + __popc(b4 & lanemask_lt), child, pm0, pm1, 0u);
         top += __popc(b4);
-        {   // one staging array for the five applied classes, in class order: far full | far masked | near | near M | far M
-            const uint32_t mine = cls == 1 ? b1 : cls == 2 ? b2 : cls == 3 ? b3 : cls == 5 ? b5 : b6;
-            const int base = cls == 1 ? 0 : cls == 2 ? n1 : cls == 3 ? n1 + n2 : cls == 5 ? n1 + n2 + n3 : n1 + n2 + n3 + n5;
+        {   // one staging array for the four applied classes, in class order: far full | far masked | near | M
+            const uint32_t mine = cls == 1 ? b1 : cls == 2 ? b2 : cls == 3 ? b3 : b5;
+            const int base = cls == 1 ? 0 : cls == 2 ? n1 : cls == 3 ? n1 + n2 : n1 + n2 + n3;
             const int at = base + __popc(mine & lanemask_lt);
             const bool far = cls == 1 || cls == 2, staged = cls != 0 && cls != 4;
             // far entries: (cx, cy, gm, -) so that one 128-bit load feeds the force loop; near / M: the double-float pair
             sts_v4_if(staged, reinterpret_cast<uint4*>(nodeA + at), __float_as_uint(L.x), __float_as_uint(L.y),
                       far ? Bq.x : __float_as_uint(L.z), __float_as_uint(L.w));
             sts_v4_if(staged, nodeB + at, Bq.x, Bq.y, pm0, pm1);
-            if (cls >= 5) cellv[at] = child;
+            if (cls == 5) cellv[at] = child;
         }
         __syncwarp();
         // ---- apply the staged nodes to the warp's 64 bodies ----
@@ -916,26 +908,15 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
             const uint4 SB = nodeB[i];
             apply_near(nodeA[i], __uint_as_float(SB.x), SB.z, SB.w);
         }
-        // class M: the per-body test, the only class that pushes here.  Near ones (rare) one at a time, far ones two per
-        // iteration (independent chains).
-        const int endMn = n1 + n2 + n3 + n5, endM = endMn + n6;
-        for (; i < endMn; ++i) {
-            const float4 SA = nodeA[i];
-            const uint4 SB = nodeB[i];
-            const uint32_t c = cellv[i];
-            uint32_t m0, m1;
-            eval_mixed(std::false_type{}, SA, __uint_as_float(SB.x), __uint_as_float(SB.y), c, SB.z, SB.w, m0, m1);
-            const bool push = (m0 | m1) != 0u;
-            sts_v4_if(push && lane == 0, stack + top, c, m0, m1, 0u);
-            top += push;
-        }
+        // class M: the per-body test, the only class that pushes here; two nodes per iteration (independent chains)
+        const int endM = n1 + n2 + n3 + n5;
         for (; i + 1 < endM; i += 2) {
             const float4 SA0 = nodeA[i], SA1 = nodeA[i + 1];
             const uint4 SB0 = nodeB[i], SB1 = nodeB[i + 1];
             const uint32_t c0 = cellv[i], c1 = cellv[i + 1];
             uint32_t p0, p1, q0, q1;
-            eval_mixed(std::true_type{}, SA0, __uint_as_float(SB0.x), __uint_as_float(SB0.y), c0, SB0.z, SB0.w, p0, p1);
-            eval_mixed(std::true_type{}, SA1, __uint_as_float(SB1.x), __uint_as_float(SB1.y), c1, SB1.z, SB1.w, q0, q1);
+            eval_mixed(SA0, __uint_as_float(SB0.x), __uint_as_float(SB0.y), c0, SB0.z, SB0.w, p0, p1);
+            eval_mixed(SA1, __uint_as_float(SB1.x), __uint_as_float(SB1.y), c1, SB1.z, SB1.w, q0, q1);
             const bool pushp = (p0 | p1) != 0u, pushq = (q0 | q1) != 0u;
             sts_v4_if(pushp && lane == 0, stack + top, c0, p0, p1, 0u);
             top += pushp;
@@ -947,7 +928,7 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
             const uint4 SB = nodeB[i];
             const uint32_t c = cellv[i];
             uint32_t m0, m1;
-            eval_mixed(std::true_type{}, SA, __uint_as_float(SB.x), __uint_as_float(SB.y), c, SB.z, SB.w, m0, m1);
+            eval_mixed(SA, __uint_as_float(SB.x), __uint_as_float(SB.y), c, SB.z, SB.w, m0, m1);
             const bool push = (m0 | m1) != 0u;
             sts_v4_if(push && lane == 0, stack + top, c, m0, m1, 0u);
             top += push;
