@@ -259,3 +259,55 @@ def test_two_gpus_repartition_free_running_fp64():
            "--steps", "20", "--fp64", "--repartition"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert "MULTI_GPU_CHECK PASS" in res.stdout and "re-partition(s)" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+# ------------------------------------------------------------------------------------------------
+# The round-2 cell-sum exchange: every rank stores the sums of its NON-EMPTY finest cells into its slot of
+# every rank's inbox; the consumer adds the slots in rank order and zeroes what it consumed.  gloo all_gather stands in
+# for the peer stores; the result must equal the dense rank-ordered sum on every rank, bit for bit, step after step
+# (the inbox is clean again without a memset).
+# ------------------------------------------------------------------------------------------------
+def _inbox_worker(rank, world, port, ncells, steps, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    inbox = np.zeros((world, 4, ncells))                      # [source rank][count, m, mx, my][cell]
+    results = []
+    for s in range(steps):
+        rng = np.random.default_rng(1000 * s + rank)
+        cells = rng.choice(ncells, size=ncells // (world + 1), replace=False)     # this rank's occupied cells
+        local = np.zeros((4, ncells))
+        local[0, cells] = rng.integers(1, 50, size=len(cells))
+        local[1:, cells] = rng.normal(size=(3, len(cells)))
+        # push: only the non-empty cells travel (index + 4 values); every rank receives every rank's list
+        idx = np.flatnonzero(local[0])
+        payload = [None] * world
+        dist.all_gather_object(payload, (idx, local[:, idx]))
+        for src, (i, v) in enumerate(payload):
+            inbox[src][:, i] = v
+        # consume: rank order, skip empty slots, zero what was read
+        total = np.zeros((4, ncells))
+        for src in range(world):
+            hit = inbox[src, 0] != 0.0
+            total[:, hit] = total[:, hit] + inbox[src][:, hit]
+            inbox[src][:, hit] = 0.0
+        assert not inbox.any()                                 # clean for the next step
+        dense = [None] * world
+        dist.all_gather_object(dense, local)
+        want = np.zeros((4, ncells))
+        for src in range(world):
+            want = want + dense[src]
+        assert np.array_equal(total, want)
+        results.append(total)
+    np.save(os.path.join(out_dir, f"inbox_r{rank}.npy"), np.stack(results))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_sparse_inbox_exchange(tmp_path):
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_inbox_worker, args=(world, _free_port(), 4096, 3, str(tmp_path)), nprocs=world, join=True)
+    a, b = (np.load(os.path.join(tmp_path, f"inbox_r{k}.npy")) for k in range(world))
+    assert np.array_equal(a, b)                                # identical reduced sums on every rank
