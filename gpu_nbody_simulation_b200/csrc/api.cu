@@ -215,7 +215,9 @@ int compute_dims(const bh_params& p, Dims& d, SortPlan& sp) {
     sp.passes = (bits + 8) / 9;
     sp.bits_per_pass = (bits + sp.passes - 1) / sp.passes;
     sp.nbins_log2 = sp.bits_per_pass <= 8 ? 8 : 9;
-    sp.ntiles = (int)((p.n_bodies + kSortTile - 1) / kSortTile);
+    sp.items = p.n_bodies < kSortSmallN ? kSortItemsSmall : kSortItems;
+    const int64_t tile = (int64_t)kSortThreads * sp.items;
+    sp.ntiles = (int)((p.n_bodies + tile - 1) / tile);
     if (sp.ntiles < 1) sp.ntiles = 1;
     return BH_OK;
 }
@@ -759,7 +761,12 @@ int bh_create(const bh_params* p, bh_ctx** out) {
 #undef BH_ALLOC
     bh_shard_range(n, p->n_ranks, p->rank, &c->own_lo, &c->own_hi);
     c->sp_own = c->sp;
-    c->sp_own.ntiles = (int)std::max<int64_t>(1, (c->own_hi - c->own_lo + kSortTile - 1) / kSortTile);
+    {   // a rank sorts only its slice: keep the allocation of the full plan (it has at least as many tile states)
+        const int64_t n_own = c->own_hi - c->own_lo;
+        c->sp_own.items = c->sp.items;
+        const int64_t tile = (int64_t)kSortThreads * c->sp_own.items;
+        c->sp_own.ntiles = (int)std::max<int64_t>(1, (n_own + tile - 1) / tile);
+    }
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     for (auto& ev : c->ev_up) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);

@@ -28,7 +28,7 @@ constexpr uint32_t kValMask = (1u << 30) - 1u;
 #ifndef BH_SORT_MIN_BLOCKS
 #define BH_SORT_MIN_BLOCKS 3     // <= 80 registers: 24 warps per SM instead of 16 (the pass is latency-bound)
 #endif
-template <int NBINS_LOG2, bool FIRST>
+template <int NBINS_LOG2, bool FIRST, int ITEMS>
 __global__ void __launch_bounds__(kSortThreads, BH_SORT_MIN_BLOCKS)
 onesweep_pass(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
@@ -49,7 +49,8 @@ onesweep_pass(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t dmask = (1u << bits) - 1u;
-    const int64_t base = (int64_t)tile * kSortTile + (int64_t)warp * (32 * kSortItems) + lane;
+    constexpr int kSortItems = ITEMS;     // (shadows the namespace constant: this instantiation's tile shape)
+    const int64_t base = (int64_t)tile * (kSortThreads * ITEMS) + (int64_t)warp * (32 * ITEMS) + lane;
 
     uint32_t key[kSortItems];
     uint32_t rank[kSortItems];
@@ -199,12 +200,14 @@ void launch_sort(uint32_t* keys[2], uint32_t* vals[2], int64_t n, const SortPlan
         uint32_t* state = s.tile_state + (size_t)pass * sp.ntiles * nbins;
         const uint32_t* hist = s.digit_hist + (size_t)pass * kMaxBins;
         int shift = pass * sp.bits_per_pass;
-#define BH_PASS(NB, F)                                                                                                   \
-        launch_chain(onesweep_pass<NB, F>, dim3(sp.ntiles), dim3(kSortThreads), st, true, (const uint32_t*)keys[cur],   \
+#define BH_PASS(NB, F, IT)                                                                                               \
+        launch_chain(onesweep_pass<NB, F, IT>, dim3(sp.ntiles), dim3(kSortThreads), st, true, (const uint32_t*)keys[cur], \
                      (const uint32_t*)vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, sp.bits_per_pass, hist, state,  \
                      s.tickets + pass, val_base)
-        if (sp.nbins_log2 == 9) { if (pass == 0) BH_PASS(9, true); else BH_PASS(9, false); }
-        else { if (pass == 0) BH_PASS(8, true); else BH_PASS(8, false); }
+#define BH_PASS_IT(NB, F) do { if (sp.items == kSortItemsSmall) BH_PASS(NB, F, kSortItemsSmall); else BH_PASS(NB, F, kSortItems); } while (0)
+        if (sp.nbins_log2 == 9) { if (pass == 0) BH_PASS_IT(9, true); else BH_PASS_IT(9, false); }
+        else { if (pass == 0) BH_PASS_IT(8, true); else BH_PASS_IT(8, false); }
+#undef BH_PASS_IT
 #undef BH_PASS
         ++g_launches;
         cur ^= 1;
