@@ -12,9 +12,9 @@ namespace bh {
 constexpr int kMaxLevels = 16;       // levels 0..max_depth-1 (max_depth <= 13 in the dense pyramid)
 constexpr int kMaxDepthDense = 13;   // 4^12 finest cells * 32 B = 512 MiB of records
 constexpr int kSortThreads = 256;
-constexpr int kSortItems = 16;       // keys per thread and tile for large inputs; 8 below kSortSmallN (more, shorter tiles:
-constexpr int kSortItemsSmall = 8;   // the pass is latency-bound there and 245 tiles of 4096 keys are 1.65 per SM)
-constexpr int64_t kSortSmallN = 3000000;
+constexpr int kSortItems = 16;       // keys per thread and tile
+constexpr int kSortItemsSmall = 8;   // A/B (round 2): 489 tiles of 2048 keys at 1M bodies instead of 245 of 4096 — measured
+constexpr int64_t kSortSmallN = 0;   // SLOWER (47.1 vs 39.6 us for the two passes: twice the look-back), so never selected
 constexpr int kMaxSortPasses = 4;
 constexpr int kMaxBins = 512;
 constexpr uint32_t kHugeCellMin = 8192;    // finest cells above this many bodies are summed by kHugeParts blocks
