@@ -28,6 +28,7 @@ def test_many_steps_with_and_without_reordering_agree():
             with Simulation(n, **GENTLE) as sim:
                 sim.set_bodies(pos, vel, mass)
                 sim.step(40)                      # re-sorted before step 2, then every 16 steps
+                assert sim.counters()["reorders"] == (3 if flag == "1" else 0)
                 out[flag] = (sim.positions(), sim.velocities(), sim.forces(), sim.accelerations())
         finally:
             del os.environ["BH_REORDER"]
