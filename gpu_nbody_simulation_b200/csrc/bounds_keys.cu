@@ -239,14 +239,18 @@ keys_kernel(const double2* __restrict__ pos, int64_t n, int finest, const StepCo
         }
         keys[i] = key;               // (the first sort pass generates the body indices idx_base + i itself)
         {   // bodies per finest cell (zeroed every step): the cell runs of the sorted order follow from these counts by
-            // a scan (tree_build.cu: cell_scan_kernel), without a pass over the sorted keys.  One atomic per distinct
-            // key of the warp (bodies in resident order share cells with their neighbours).
+            // a scan (tree_build.cu: cell_scan_kernel), without a pass over the sorted keys.  One atomic per DISTINCT key
+            // of the warp — for the cell count and for the digit histograms alike: bodies in resident order share their
+            // cell with their neighbours, so a warp has ~5 distinct keys (and 32-way conflicts on the high digit otherwise).
             const uint32_t act = __activemask();
             const uint32_t peers = __match_any_sync(act, key);
-            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(cell_count + key, (uint32_t)__popc(peers));
+            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+                const uint32_t cnt = (uint32_t)__popc(peers);
+                atomicAdd(cell_count + key, cnt);
+                for (int ps = 0; ps < passes; ++ps)
+                    atomicAdd(&hist[ps * kMaxBins + ((key >> (ps * bits_per_pass)) & dmask)], cnt);
+            }
         }
-        for (int ps = 0; ps < passes; ++ps)
-            atomicAdd(&hist[ps * kMaxBins + ((key >> (ps * bits_per_pass)) & dmask)], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < passes * kMaxBins; i += blockDim.x) {
