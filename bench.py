@@ -405,7 +405,7 @@ def run_ours(args):
 
     def make_sim(n_, n_ranks, counters=False, p2p=True):
         s = bh.Simulation(n_, device=local, rank=rank if n_ranks > 1 else 0, n_ranks=n_ranks, graph=not args.no_graph,
-                          max_depth=args.max_depth, counters=counters, exact_leaves=args.exact_leaves and n_ranks == 1)
+                          max_depth=args.max_depth, counters=counters, exact_leaves=args.exact_leaves)
         if n_ranks > 1:
             idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
             if rank == 0:
@@ -549,7 +549,7 @@ def run_ours(args):
         try:
             import oracle
             accuracy = sampled_accuracy(bh, oracle, f_gpu, pos, mass, args.max_depth, own_lo, own_hi,
-                                        exact_leaves=args.exact_leaves and world == 1)
+                                        exact_leaves=args.exact_leaves)
         except Exception as e:   # never worth losing the line for
             accuracy = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     del f_gpu
@@ -730,7 +730,8 @@ def main():
                     help="synthetic distribution (BASELINE config 2: disk; config 3: plummer)")
     ap.add_argument("--max-depth", type=int, default=10,
                     help="QUADTREE_MAX_DEPTH (reference: 10); BASELINE config 3 (clustered Plummer) raises it, up to 13")
-    ap.add_argument("--exact-leaves", action="store_true", help="BH_FLAG_EXACT_LEAVES (extension; single GPU)")
+    ap.add_argument("--exact-leaves", action="store_true",
+                    help="BH_FLAG_EXACT_LEAVES (extension); N > 1: every step all-gathers the positions, every rank builds the full tree")
     ap.add_argument("--no-graph", action="store_true", help="direct kernel launches instead of CUDA-graph replay")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-reduces instead of the peer-memory exchange")
     ap.add_argument("--total-bodies", type=int, default=0,

@@ -174,6 +174,11 @@ struct bh_ctx {
     // from time to time, so that "body index" ~ "sorted position": the per-body gathers / scatters of the build
     // and of the traversal prologue / epilogue become (nearly) coalesced.  `perm` maps the internal index to the
     // caller's original index; setters and getters go through it, so the C-ABI keeps its ORIGINAL-order contract.
+    // Exact leaves on a multi-rank context: a leaf's bodies may live on other ranks, so the sharded build does not
+    // do.  Every step the ranks all-gather the positions (NCCL broadcasts of the slices, 16 B/body), every rank
+    // builds the FULL tree redundantly (north_star's original scheme) and walks only its own bodies (the sorted
+    // positions whose body lies in its index slice: chunk_lists).  No CUDA graph (NCCL calls inside the step).
+    bool exact_multi = false;
     uint32_t* perm = nullptr;        // [n]; meaningful only while !perm_identity
     bool perm_identity = true;
     bool auto_reorder = true;        // env BH_REORDER=0 disables; off in FP64 mode unless BH_REORDER=1
@@ -311,6 +316,12 @@ int enqueue_build(bh_ctx* c, bool full = false, const double2* src = nullptr, cu
 int enqueue_build(bh_ctx* c, bool full, const double2* src, cudaEvent_t mass_ready) {
     if (!src) src = c->pos;
     g_pdl = c->pdl;
+    const bool own_list_needed = c->exact_multi && !full;
+    if (own_list_needed) {      // exact leaves, several ranks: everybody needs everybody's bodies (see bh_ctx::exact_multi)
+        if (!c->mass_complete) { BH_TRY(exchange_slices(c, c->mass, sizeof(double))); c->mass_complete = true; }
+        BH_TRY(exchange_slices(c, (void*)src, sizeof(double2)));
+        full = true;
+    }
     zero_scratch(c);
     prof_mark(c, 0);
     const bool sharded = c->p.n_ranks > 1 && !full;
@@ -324,6 +335,16 @@ int enqueue_build(bh_ctx* c, bool full, const double2* src, cudaEvent_t mass_rea
         launch_tree(c->keys[c->sorted], c->idx[c->sorted], src, c->mass, c->d.n, c->p, c->d, c->tree, c->s, c->consts,
                     c->stream);
         c->tree_full = true;
+        if (own_list_needed) {   // sorted positions of this rank's bodies, in sorted order: [0, lo) | [lo, hi) | [hi, n)
+            if (!c->chunk_lists) {
+                BH_TRY(dev_alloc(&c->chunk_lists, (size_t)c->d.n));
+                BH_TRY(dev_alloc(&c->chunk_counts, (size_t)kMaxHostChunks * ((c->d.n + 255) / 256)));
+            }
+            ChunkBounds cb{};
+            cb.n_chunks = 3;
+            cb.lo[0] = 0; cb.lo[1] = (uint32_t)c->own_lo; cb.lo[2] = (uint32_t)c->own_hi; cb.lo[3] = (uint32_t)c->d.n;
+            launch_chunk_lists(c->idx[c->sorted], c->d.n, cb, c->chunk_counts, c->chunk_lists, c->stream);
+        }
     } else {
         const int64_t lo = c->own_lo, n_own = c->own_hi - c->own_lo;
         if (c->p2p_ready) {   // box exchange fused into the bounds kernel (peer stores + flags)
@@ -358,6 +379,7 @@ int enqueue_build(bh_ctx* c, bool full, const double2* src, cudaEvent_t mass_rea
 // the kernel variant is still chosen from the TOTAL body count so that the bits equal a whole-set launch.
 int enqueue_forces(bh_ctx* c, bool integrate, const double2* src_pos = nullptr, const double2* src_vel = nullptr,
                    const uint32_t* list = nullptr, int64_t list_n = 0) {
+    if (c->exact_multi && !list) { list = c->chunk_lists + c->own_lo; list_n = c->own_hi - c->own_lo; }
     // after a sharded build the sorted list holds exactly this rank's bodies
     const int64_t n_all = (c->p.n_ranks > 1 && !c->tree_full) ? (c->own_hi - c->own_lo) : c->d.n;
     g_pdl = c->pdl;
@@ -422,7 +444,8 @@ int run_steps(bh_ctx* c, int nsteps, bool from_snapshot) {
     if (nsteps < 0) { set_error("nsteps < 0"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     // NCCL calls are not captured; the peer-memory exchange is plain kernels, so multi-rank steps replay too
-    const bool use_graph = !(c->p.flags & BH_FLAG_NO_GRAPH) && !c->profiling && (c->p.n_ranks == 1 || c->p2p_ready);
+    const bool use_graph = !(c->p.flags & BH_FLAG_NO_GRAPH) && !c->profiling && (c->p.n_ranks == 1 || c->p2p_ready) &&
+                           !c->exact_multi;
     const int gi = from_snapshot ? 1 : 0;
     BH_CUDA_OK(cudaEventRecord(c->ev0, c->stream));
     if (use_graph && nsteps > 0) {
@@ -674,10 +697,6 @@ int bh_create(const bh_params* p, bh_ctx** out) {
         return BH_ERR_INVALID;
     }
     if (p->n_ranks < 1 || p->rank < 0 || p->rank >= p->n_ranks) { set_error("bad rank / n_ranks"); return BH_ERR_INVALID; }
-    if ((p->flags & BH_FLAG_EXACT_LEAVES) && p->n_ranks > 1) {
-        set_error("BH_FLAG_EXACT_LEAVES needs the leaf's bodies on the device: single-rank contexts only");
-        return BH_ERR_INVALID;
-    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -701,6 +720,7 @@ int bh_create(const bh_params* p, bh_ctx** out) {
     if (c->device >= ndev) { set_error("device %d of %d", c->device, ndev); delete c; return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
     compute_dims(c->p, c->d, c->sp);
+    c->exact_multi = (p->flags & BH_FLAG_EXACT_LEAVES) && p->n_ranks > 1;
     const int64_t n = p->n_bodies;
     int rc = BH_OK;
     auto fail = [&](int code) { bh_destroy(c); return code; };
@@ -972,7 +992,7 @@ int bh_step_from_snapshot(bh_ctx* c, int32_t nsteps) {
 // their uploads overlap the build and the traversal.  out_pos_host receives the new positions.
 int bh_step_host(bh_ctx* c, const double* pos, const double* vel, const double* mass, double* out_pos) {
     if (!c || !pos || !vel || !mass || !out_pos) { set_error("null argument"); return BH_ERR_INVALID; }
-    if (c->p.n_ranks > 1 && c->host_pipeline_multi && c->p2p_ready && !c->profiling) {
+    if (c->p.n_ranks > 1 && c->host_pipeline_multi && c->p2p_ready && !c->profiling && !c->exact_multi) {
         // the single-rank pipeline for one rank's slice — positions up, then bounds / keys / sort while masses
         // and velocities are still in flight; integrator + download on the high-priority stream.  Bit-identical to
         // the plain sequence below (tests/multi_gpu_check.py --host-step, profiles/r02_multi_gpu_check_g2.log);
@@ -1084,7 +1104,7 @@ int bh_build_tree(bh_ctx* c) {
 int bh_compute_forces(bh_ctx* c) {
     if (!c || !c->tree_valid) { set_error("bh_compute_forces: no tree for the current positions (call bh_build_tree; a step moves the bodies)"); return BH_ERR_INVALID; }
     DeviceGuard g(c->device);
-    if (c->p.n_ranks > 1 && c->tree_full) BH_TRY(enqueue_build(c));   // diagnostic getters left a full tree behind
+    if (c->p.n_ranks > 1 && c->tree_full && !c->exact_multi) BH_TRY(enqueue_build(c));   // diagnostic getters left a full tree behind
     cudaMemsetAsync(c->s.counters, 0, 4 * sizeof(unsigned long long), c->stream);
     return enqueue_forces(c, false);
 }

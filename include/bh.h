@@ -45,8 +45,10 @@ enum {
     BH_FLAG_EXACT_LEAVES = 1u << 4    /* EXTENSION, not reference behaviour: a multi-body leaf at
                                          the depth cap acts through its bodies one by one (self excluded) instead
                                          of through one monopole that contains the body itself (project.cu:360-382,
-                                         :646).  Single GPU only.  Specified by the oracle's
-                                         bho_compute_forces_exact_leaves; default off = reference semantics. */
+                                         :646).  Specified by the oracle's bho_compute_forces_exact_leaves; default
+                                         off = reference semantics.  On a multi-rank context every step all-gathers
+                                         the positions over NCCL and every rank builds the full tree (a leaf's bodies
+                                         may live on other ranks); bh_attach_nccl is required. */
 };
 
 /* Runtime copy of the reference's compile-time macros and source-level constants.

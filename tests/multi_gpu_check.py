@@ -25,6 +25,7 @@ ap.add_argument("--no-p2p", action="store_true", help="NCCL all-reduces instead 
 ap.add_argument("--host-step", action="store_true",
                 help="also check ONE bh_step_host call (own slice up / down) against the single-GPU step; with "
                      "BH_HOST_PIPELINE_MULTI=1 this exercises the pipelined multi-rank host step")
+ap.add_argument("--exact-leaves", action="store_true", help="BH_FLAG_EXACT_LEAVES on every context (all-gather + full build per step)")
 ap.add_argument("--repartition", action="store_true",
                 help="bodies in random order + BH_REORDER=1: the engine re-partitions (gathers the slices, full build, global "
                      "permutation) before the second step, so that every rank's index slice is a Morton range again")
@@ -38,6 +39,8 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 pos, vel, mass = ic.uniform_disk(a.n, seed=4242, round6=False)
 # gentle dynamics so that several steps stay comparable (the reference constants explode after one step)
 kw = dict(G=6.67e-11 * 1e-6, fp64=a.fp64)
+if a.exact_leaves:
+    kw["exact_leaves"] = True
 
 idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
 if rank == 0:
@@ -96,8 +99,12 @@ if rank == 0:
         p, v = pos.copy(), vel.copy()
         par = oracle.default_params(G=kw["G"])
         for _ in range(a.steps):
-            r = oracle.step(p, v, mass, par, nthreads=oracle.max_threads())
-            p, v = r["pos"], r["vel"]
+            if a.exact_leaves:      # the oracle's exact-leaves extension + the reference's update
+                f_o, _ = oracle.Tree(p, mass, par).forces_exact_leaves(nthreads=oracle.max_threads())
+                _, v, p = oracle.update(f_o, mass, v, p, par.dt)
+            else:
+                r = oracle.step(p, v, mass, par, nthreads=oracle.max_threads())
+                p, v = r["pos"], r["vel"]
         e = rel(p_multi, p)
         print(f"multi-GPU vs CPU oracle after {a.steps} steps: position rel-RMS {e:.3e}", flush=True)
         ok = ok and e <= (1e-8 if a.fp64 else 1e-5)

@@ -75,9 +75,16 @@ def test_root_is_the_multi_body_leaf_and_whole_step():
             assert rel_rms(sim.positions(), p) <= tol and rel_rms(sim.velocities(), v) <= tol
 
 
-def test_flag_is_single_rank_only():
-    with pytest.raises(BhError):
-        Simulation(1000, exact_leaves=True, rank=0, n_ranks=2)
+def test_multi_rank_exact_leaves_needs_the_communicator():
+    """On a multi-rank context the flag makes every step all-gather the positions (a leaf's bodies may live on other
+    ranks): without an attached NCCL communicator the step fails loudly (the 2-GPU run is tests/multi_gpu_check.py
+    --exact-leaves)."""
+    rng = np.random.default_rng(3)
+    n = 1000
+    with Simulation(n, exact_leaves=True, rank=0, n_ranks=2) as sim:
+        sim.set_bodies(rng.uniform(-1, 1, (n, 2)), np.zeros((n, 2)), rng.uniform(0.1, 0.5, n))
+        with pytest.raises(BhError):
+            sim.step(1)
 
 
 @pytest.mark.parametrize("bodies_per_lane", [0, 2])
