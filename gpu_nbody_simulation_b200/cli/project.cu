@@ -20,7 +20,8 @@
 //   * -DBH_POSITIONS_TXT=1 [-DBH_POSITIONS_STRIDE=k] also writes the trajectory file positions.txt that plot_2d.py
 //     reads (format of savePositions, project.cu:855-863), which the reference's GPU path never writes: one open
 //     file, every k-th state, copied and formatted asynchronously (bh_trajectory_*);
-//   * cap-level single leaves print the occupant's real position (reference: out-of-bounds read).
+//   * cap-level single leaves print the occupant's real position (reference: out-of-bounds read);
+//   * -DBH_EXACT_LEAVES=1 / -DBH_FP64=1 select the exact-leaves extension / the FP64 verification traversal.
 #ifndef N_BODIES
 #define N_BODIES (1000 * 40)
 #endif
@@ -50,6 +51,9 @@
 #endif
 #ifndef BH_FP64
 #define BH_FP64 0
+#endif
+#ifndef BH_EXACT_LEAVES
+#define BH_EXACT_LEAVES 0         // 1: multi-body leaves at the depth cap act through their bodies (extension)
 #endif
 
 #include "../csrc/api.cu"
@@ -95,6 +99,7 @@ int main() {
     bh_default_params(&p);
     p.n_bodies = n; p.G = G_CONST; p.dt = DELTA_T; p.theta = THETA; p.max_depth = QUADTREE_MAX_DEPTH;
     if (BH_FP64) p.flags |= BH_FLAG_FP64_TRAVERSAL;
+    if (BH_EXACT_LEAVES) p.flags |= BH_FLAG_EXACT_LEAVES;
     bh_ctx* ctx = nullptr;
     if (bh_create(&p, &ctx) != BH_OK) die("bh_create");
     { FILE* f = fopen("quadtree_init_gpu.txt", "w"); if (f) fclose(f); }          // project.cu:928-929 opens both
