@@ -3,6 +3,11 @@
 // Replaces computeForcesGpu (project.cu:679-793; CPU twin computeForces :593-675) and
 // updateAccVelPos (project.cu:819-836).
 //
+// Kernels in this file: traverse_f32_list_kernel (production from 500k bodies on: group-classified walk, see its own
+// header further down), traverse_f32_kernel (generic, 1 or 2 bodies per lane: small inputs, counters, exact leaves),
+// traverse_f32_pair_kernel (round 1's production kernel: A/B variant and packed exact leaves), traverse_f64_kernel
+// (verification mode).  What they share — written for the generic / pair kernels first:
+//
 // One warp owns 32*BPL consecutive bodies of the Morton-sorted order (each lane BPL of them) and
 // walks the dense pyramid depth first with ONE warp-shared stack in shared memory.  A stack entry
 // is (cell p, mask of the bodies that opened it).  Popping p evaluates its four children

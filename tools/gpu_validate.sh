@@ -8,14 +8,12 @@ nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader > gpurun_out/smi
 ( timeout 600 python -m pytest tests -m gpu -q -rfs 2>&1 | tail -60; echo "rc=${PIPESTATUS[0]}" ) > gpurun_out/pytest.log
 ( timeout 120 python __graft_entry__.py smoke 2>&1 | tail -5; echo "smoke rc=${PIPESTATUS[0]}" ) > gpurun_out/smoke.log
 timeout 400 python bench.py > gpurun_out/bench_default.log 2> gpurun_out/bench_default.err
-BH_PDL=1 timeout 200 python bench.py --steps 100 --no-cpu-baseline --no-gpu-baseline \
-    > gpurun_out/bench_pdl1.log 2>&1
-BH_PDL=0 BH_HOST_CHUNKS=1 timeout 200 python bench.py --steps 100 --no-cpu-baseline --no-gpu-baseline \
-    > gpurun_out/bench_pdl0_chunks1.log 2>&1
+BH_PDL=1 timeout 200 python bench.py --steps 100 --quick > gpurun_out/bench_pdl1.log 2>&1
+BH_REORDER=0 timeout 200 python bench.py --steps 100 --quick > gpurun_out/bench_reorder0.log 2>&1
 timeout 200 python tools/e2e_sweep.py > gpurun_out/e2e_sweep.log 2>&1
 if [ "${1:-}" = "ncu" ]; then
     timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
-        --log-file gpurun_out/launches_bench.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-baseline \
+        --log-file gpurun_out/launches_bench.csv python bench.py --steps 3 --warmup 3 --brackets 1 --quick \
         > gpurun_out/ncu_bench.log 2>&1
 fi
 tail -25 gpurun_out/pytest.log; cat gpurun_out/smoke.log; cat gpurun_out/e2e_sweep.log; rm -f gpurun_out/bench_oldpaths.log gpurun_out/bench_snapcopy.log gpurun_out/bench_bisect.log
