@@ -632,6 +632,20 @@ __device__ __forceinline__ void sts_v4_if(bool doit, uint4* p, uint32_t x, uint3
 #ifndef BH_LIST_MIN_BLOCKS
 #define BH_LIST_MIN_BLOCKS 8    // per 128 threads: <= 72 registers, 28 warps per SM
 #endif
+// Far class-A nodes without the distance offset: G M / (d^2 (d + eps)) differs from G M / d^3 by eps / d relative,
+// and a node only counts as FAR when d >= 2^25 eps (folded into the warp's far2 threshold), i.e. below half an FP32
+// ulp — one packed multiply less per far entry (3 instead of FMUL2 + FFMA2 + 2 FMUL2).  0 = round 2's expression.
+#ifndef BH_FARM_UNROLL
+#define BH_FARM_UNROLL 4
+#endif
+#ifndef BH_NEAR_UNROLL
+#define BH_NEAR_UNROLL 2
+#endif
+constexpr int kNearUnroll = BH_NEAR_UNROLL;
+constexpr int kFarMaskedUnroll = BH_FARM_UNROLL;   // entries per iteration of the far, partial-mask loop
+#ifndef BH_FAR_NO_EPS
+#define BH_FAR_NO_EPS 1
+#endif
 template <bool INTEGRATE, bool EXACT_EPS>
 __global__ void __launch_bounds__(kTravThreads, BH_LIST_MIN_BLOCKS)
 traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
@@ -727,6 +741,9 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
             wc.slack = 1.2e-7f * mag;
             const float wx = wc.bx1 - wc.bx0, wy = wc.by1 - wc.by0;
             wc.far2 = 0.015625f * fmaf(wx, wx, wy * wy);
+#if BH_FAR_NO_EPS
+            if constexpr (!EXACT_EPS) { const float dfar = 33554432.f * feps; wc.far2 = fmaxf(wc.far2, dfar * dfar); }
+#endif
             s_wc[warp] = wc;
         }
         // bodies the frame cannot resolve leave the walk: bit 31 of spos marks them for the epilogue
@@ -751,18 +768,28 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
             return __fmul2_rn(make_float2(gm, gm), __fmul2_rn(t, u));
         }
     };
+    // far nodes (d >= 2^25 eps by the far2 threshold): G M / d^3, the offset is below the FP32 rounding
+    auto gfactor_far = [&](const float2 d2, const float gm) -> float2 {
+#if BH_FAR_NO_EPS
+        if constexpr (!EXACT_EPS) {
+            const float2 inv = make_float2(approx_rsqrt(d2.x), approx_rsqrt(d2.y));
+            return __fmul2_rn(__fmul2_rn(make_float2(gm, gm), inv), __fmul2_rn(inv, inv));
+        } else
+#endif
+            return gfactor(d2, gm);
+    };
     // far class A: single-float displacement in the local frame
     auto apply_far = [&](const float4 F) {
         const float2 dx = __fadd2_rn(make_float2(F.x, F.x), nxh), dy = __fadd2_rn(make_float2(F.y, F.y), nyh);
         const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
-        const float2 g = gfactor(d2, F.z);
+        const float2 g = gfactor_far(d2, F.z);
         accx = __ffma2_rn(g, dx, accx);
         accy = __ffma2_rn(g, dy, accy);
     };
     auto apply_far_masked = [&](const float4 F, const uint2 m) {
         const float2 dx = __fadd2_rn(make_float2(F.x, F.x), nxh), dy = __fadd2_rn(make_float2(F.y, F.y), nyh);
         const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
-        const float2 g = gfactor(d2, F.z);
+        const float2 g = gfactor_far(d2, F.z);
         const float2 f = make_float2((m.x & lanebit) ? g.x : 0.f, (m.y & lanebit) ? g.y : 0.f);
         accx = __ffma2_rn(f, dx, accx);
         accy = __ffma2_rn(f, dy, accy);
@@ -903,12 +930,12 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
         int i = 0;
 #pragma unroll 4
         for (; i < n1; ++i) apply_far(nodeA[i]);
-#pragma unroll 2
+#pragma unroll kFarMaskedUnroll
         for (; i < n1 + n2; ++i) {
             const uint4 SB = nodeB[i];
             apply_far_masked(nodeA[i], make_uint2(SB.z, SB.w));
         }
-#pragma unroll 2
+#pragma unroll kNearUnroll
         for (; i < n1 + n2 + n3; ++i) {
             const uint4 SB = nodeB[i];
             apply_near(nodeA[i], __uint_as_float(SB.x), SB.z, SB.w);
