@@ -171,7 +171,18 @@ def shard_range(n_bodies: int, n_ranks: int, rank: int):
     return lo.value, hi.value
 
 
+def _nccl_first_use():
+    """libbh.so dlopens libnccl on first use and prefers a copy the process has already loaded.  A python host that
+    also uses torch must have torch's bundled libnccl loaded FIRST: two libraries with the SONAME libnccl.so.2
+    cannot coexist, and the system copy loaded first would break a later ``import torch``."""
+    import importlib.util
+    import sys
+    if "torch" not in sys.modules and importlib.util.find_spec("torch") is not None:
+        import torch  # noqa: F401
+
+
 def nccl_unique_id() -> bytes:
+    _nccl_first_use()
     buf = C.create_string_buffer(128)
     _check(lib().bh_nccl_unique_id(buf))
     return buf.raw
@@ -283,6 +294,7 @@ class Simulation:
 
     # ---- state ----
     def attach_nccl(self, unique_id: bytes):
+        _nccl_first_use()
         buf = C.create_string_buffer(unique_id, 128)
         _check(lib().bh_attach_nccl(self._h, buf))
 

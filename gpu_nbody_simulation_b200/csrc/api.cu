@@ -53,10 +53,13 @@ static NcclApi* nccl_api() {
 }
 static void nccl_load() {
     NcclApi& api = g_nccl;
+    // Order: a libnccl the process has ALREADY loaded (a python host's torch brings its own copy; a second copy of the
+    // same SONAME cannot coexist), then BH_NCCL_LIB (explicit path for C++ hosts), then the system library.
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     void* h = nullptr;
-    for (const char* nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_NOLOAD); if (h) break; }   // torch's copy if loaded
-    if (!h) for (const char* nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    for (const char* nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_NOLOAD); if (h) break; }
+    if (!h) { const char* env = getenv("BH_NCCL_LIB"); if (env && *env) h = dlopen(env, RTLD_NOW | RTLD_LOCAL); }
+    if (!h) for (const char* nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_LOCAL); if (h) break; }
     if (!h) return;
 #define BH_SYM(field, name)                                                        \
     api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name));            \
@@ -271,8 +274,11 @@ int peer_error(bh_ctx* c) {
 // All-gather of one owned slice per rank (ragged sizes allowed): grouped broadcasts.
 int exchange_slices(bh_ctx* c, void* base, size_t elem_bytes) {
     if (c->p.n_ranks <= 1) return BH_OK;
+    // (the communicator is checked BEFORE libnccl is touched: loading the system's libnccl into a process that imports
+    // torch — with its own bundled libnccl of the same SONAME — afterwards breaks that import)
+    if (!c->comm) { set_error("multi-rank context without an attached NCCL communicator"); return BH_ERR_NCCL; }
     NcclApi* api = nccl_api();
-    if (!api || !c->comm) { set_error("multi-rank context without an attached NCCL communicator"); return BH_ERR_NCCL; }
+    if (!api) return BH_ERR_NCCL;
     BH_NCCL_OK(api, api->GroupStart());
     for (int r = 0; r < c->p.n_ranks; ++r) {
         int64_t lo, hi;
@@ -294,8 +300,9 @@ void zero_scratch(bh_ctx* c) {
 void prof_mark(bh_ctx* c, int i) { if (c->profiling) cudaEventRecord(c->pev[i], c->stream); }
 
 int allreduce_f64(bh_ctx* c, double* buf, size_t count, ncclRedOp_t op) {
+    if (!c->comm) { set_error("multi-rank context without an attached NCCL communicator"); return BH_ERR_NCCL; }
     NcclApi* api = nccl_api();
-    if (!api || !c->comm) { set_error("multi-rank context without an attached NCCL communicator"); return BH_ERR_NCCL; }
+    if (!api) return BH_ERR_NCCL;
     BH_NCCL_OK(api, api->AllReduce(buf, buf, count, ncclDouble, op, c->comm, c->stream));
     return BH_OK;
 }

@@ -85,6 +85,11 @@ def test_multi_rank_exact_leaves_needs_the_communicator():
         sim.set_bodies(rng.uniform(-1, 1, (n, 2)), np.zeros((n, 2)), rng.uniform(0.1, 0.5, n))
         with pytest.raises(BhError):
             sim.step(1)
+    # the refusal must not have loaded the system's libnccl: a later `import torch` (its own bundled libnccl, same SONAME)
+    # would fail — which is how this was found (the GPU suite imports torch in later tests)
+    import torch  # noqa: F401
+    loaded = [ln.split()[-1] for ln in open("/proc/self/maps") if "libnccl" in ln]
+    assert all("nvidia" in p or "torch" in p for p in loaded), loaded
 
 
 @pytest.mark.parametrize("bodies_per_lane", [0, 2])
