@@ -60,8 +60,8 @@ GEN_KIND = {"disk": "uniform_disk", "plummer": "plummer_2d", "square": "uniform_
 # dram__bytes_read.sum + dram__bytes_write.sum and smsp__inst_executed.sum of the production traversal kernel, one
 # `ncu --set full` capture at N = 1M uniform disk; see profiles/ (file named in NCU_SOURCE)
 NCU_SOURCE = "profiles/r02_traverse_list_ncu_summary.txt"
-TRAVERSE_DRAM_BYTES_NCU = 62_307_328 + 26_153_728
-TRAVERSE_WARP_INSTRUCTIONS_NCU = 226_762_869
+TRAVERSE_DRAM_BYTES_NCU = 61_915_136 + 25_891_840
+TRAVERSE_WARP_INSTRUCTIONS_NCU = 218_505_556
 
 
 def make_workload(n, dist="disk"):
