@@ -646,9 +646,15 @@ constexpr int kFarMaskedUnroll = BH_FARM_UNROLL;   // entries per iteration of t
 #ifndef BH_FAR_NO_EPS
 #define BH_FAR_NO_EPS 1
 #endif
-template <bool INTEGRATE, bool EXACT_EPS>
+// LEAVES (BH_FLAG_EXACT_LEAVES with reserved[0] = 9; a separate instantiation, the production kernel's code is
+// unchanged): a multi-body leaf at the depth cap is a seventh class.  It is not staged as one monopole but queued with
+// its mask; after the round's lists have been applied, its bodies are converted into the warp-local frame by one lane
+// each (32 members per pass), staged like near class-A nodes and applied to the bodies of the mask, self excluded by
+// body index — the same pair expression as the pair kernel's member loop, ~26 instead of ~45 instructions per member.
+template <bool INTEGRATE, bool EXACT_EPS, bool LEAVES = false>
 __global__ void __launch_bounds__(kTravThreads, BH_LIST_MIN_BLOCKS)
 traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
+    __shared__ __align__(16) uint4 s_leaf[LEAVES ? kTravWarps : 1][LEAVES ? 32 : 1];   // (first, count, mask0, mask1)
     __shared__ __align__(16) uint4 s_stack[kTravWarps][kListStackCap];   // (cell, mask0, mask1, -)
     __shared__ __align__(16) float4 s_nodeA[kTravWarps][32];             // staged nodes, local frame: far class A: cx cy gm - ;
                                                                          //   near class A / class M: chx chy clx cly
@@ -720,7 +726,7 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
             const double rx = sx[b] - ox, ry = sy[b] - oy;
-            if (body[b] != 0xffffffffu)
+            if (!LEAVES && body[b] != 0xffffffffu)   // (LEAVES: a body's own multi-body cell is never applied to it as a monopole)
                 // (the node records themselves carry the COM as a double-float of the GLOBAL scaled coordinate: that, not
                 // the local frame, bounds what the near-field arithmetic resolves)
                 resc[b] = own_cell_unresolved(a, spos[b], sx[b] / scale, sy[b] / scale, scale, sx[b] * sx[b] + sy[b] * sy[b]);
@@ -849,13 +855,58 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
         return out;
     };
 
+    // LEAVES: the bodies first .. first + cnt of the sorted order (one cap-level cell) act one by one on the bodies of
+    // the mask, self excluded (oracle/bh_oracle.c: bho_compute_forces_exact_leaves).  Uses the staging arrays: call it
+    // only when nobody reads them any more.
+    [[maybe_unused]] auto apply_leaf_members = [&](const uint32_t first, const uint32_t cnt, const uint32_t pm0, const uint32_t pm1) {
+        const double scale_d = a.consts->scale, Gs = a.G * scale_d * scale_d;
+        const double ox = (double)s_wc[warp].oxh + (double)s_wc[warp].oxl, oy = (double)s_wc[warp].oyh + (double)s_wc[warp].oyl;
+        const bool a0 = pm0 & lanebit, a1 = pm1 & lanebit;
+        for (uint32_t j0 = 0; j0 < cnt; j0 += 32u) {
+            __syncwarp();                                   // the previous pass / the round's loops are done with the arrays
+            const uint32_t j = j0 + (uint32_t)lane;
+            if (j < cnt) {
+                const uint32_t bj = __ldg(a.sidx + first + j);
+                const double2 pj = a.pos_in[bj];
+                const double rx = pj.x * scale_d - ox, ry = pj.y * scale_d - oy;
+                const float xh = (float)rx, yh = (float)ry;
+                nodeA[lane] = make_float4(xh, yh, (float)(rx - (double)xh), (float)(ry - (double)yh));
+                nodeB[lane] = make_uint4(__float_as_uint((float)(Gs * a.mass[bj])), bj, 0u, 0u);
+            }
+            __syncwarp();
+            const int m = (int)(cnt - j0 < 32u ? cnt - j0 : 32u);
+#pragma unroll 2
+            for (int i = 0; i < m; ++i) {
+                const float4 A = nodeA[i];
+                const uint4 MB = nodeB[i];
+                const float2 dx = __fadd2_rn(__fadd2_rn(make_float2(A.x, A.x), nxh), __fadd2_rn(make_float2(A.z, A.z), nxl));
+                const float2 dy = __fadd2_rn(__fadd2_rn(make_float2(A.y, A.y), nyh), __fadd2_rn(make_float2(A.w, A.w), nyl));
+                const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+                const float2 g = gfactor(d2, __uint_as_float(MB.x));
+                // the select comes last: a body's own entry has d2 == 0 (g is NaN there) and must contribute exactly 0
+                const float2 f = make_float2((a0 && body[0] != MB.y) ? g.x : 0.f, (a1 && body[1] != MB.y) ? g.y : 0.f);
+                accx = __ffma2_rn(f, dx, accx);
+                accy = __ffma2_rn(f, dy, accy);
+            }
+        }
+        __syncwarp();
+    };
+
     int top = 0;
     {   // the root (project.cu:711-715 pushes node 0): per-body test
         const float4 R = __ldg(reinterpret_cast<const float4*>(a.rec));
         const float2 B = __ldg(reinterpret_cast<const float2*>(a.rec) + 2);
         const ListWarpConsts& wc = s_wc[warp];
-        uint32_t m0, m1;
-        eval_mixed(to_local(R, wc), B.x, B.y, 0u, wc.live0, wc.live1, m0, m1);
+        uint32_t m0 = 0u, m1 = 0u;
+        bool root_done = false;
+        if constexpr (LEAVES) {
+            const uint2 CF = __ldg(reinterpret_cast<const uint2*>(a.rec) + 3);   // count first
+            if (B.y < 0.f && B.x != 0.f && CF.x >= 2u) {       // the root itself is the multi-body leaf (depth cap 1)
+                apply_leaf_members(CF.y, CF.x, wc.live0, wc.live1);
+                root_done = true;
+            }
+        }
+        if (!root_done) eval_mixed(to_local(R, wc), B.x, B.y, 0u, wc.live0, wc.live1, m0, m1);
         if ((m0 | m1) != 0u) {
             if (lane == 0) stack[0] = make_uint4(0u, m0, m1, 0u);
             top = 1;
@@ -899,6 +950,8 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
                         const int64_t slot = (int64_t)Bq.w - warp_slot0;
                         if (slot >= 0 && slot < 64) { if (slot < 32) pm0 &= ~(1u << slot); else pm1 &= ~(1u << (slot - 32)); }
                     }
+                } else if constexpr (LEAVES) {
+                    cls = 6;                                  // several bodies (only possible at the depth cap): members
                 }
             } else {
                 const float fx = fmaxf(L.x - wc.bx0, wc.bx1 - L.x) + ex, fy = fmaxf(L.y - wc.by0, wc.by1 - L.y) + ey;
@@ -914,11 +967,17 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
         const int n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3), n5 = __popc(b5);
         sts_v4_if(cls == 4, stack + top + __popc(b4 & lanemask_lt), child, pm0, pm1, 0u);
         top += __popc(b4);
+        [[maybe_unused]] int n6 = 0;
+        if constexpr (LEAVES) {
+            const uint32_t b6 = __ballot_sync(0xffffffffu, cls == 6);
+            n6 = __popc(b6);
+            sts_v4_if(cls == 6, s_leaf[warp] + __popc(b6 & lanemask_lt), Bq.w, Bq.z, pm0, pm1);
+        }
         {   // one staging array for the four applied classes, in class order: far full | far masked | near | M
             const uint32_t mine = cls == 1 ? b1 : cls == 2 ? b2 : cls == 3 ? b3 : b5;
             const int base = cls == 1 ? 0 : cls == 2 ? n1 : cls == 3 ? n1 + n2 : n1 + n2 + n3;
             const int at = base + __popc(mine & lanemask_lt);
-            const bool far = cls == 1 || cls == 2, staged = cls != 0 && cls != 4;
+            const bool far = cls == 1 || cls == 2, staged = cls != 0 && cls != 4 && (!LEAVES || cls != 6);
             // far entries: (cx, cy, gm, -) so that one 128-bit load feeds the force loop; near / M: the double-float pair
             sts_v4_if(staged, reinterpret_cast<uint4*>(nodeA + at), __float_as_uint(L.x), __float_as_uint(L.y),
                       far ? Bq.x : __float_as_uint(L.z), __float_as_uint(L.w));
@@ -966,6 +1025,12 @@ traverse_f32_list_kernel(const __grid_constant__ TravArgs a) {
             top += push;
         }
         __syncwarp();
+        if constexpr (LEAVES) {
+            for (int e6 = 0; e6 < n6; ++e6) {
+                const uint4 Lf = s_leaf[warp][e6];
+                apply_leaf_members(Lf.x, Lf.y, Lf.z, Lf.w);
+            }
+        }
     }
     const float ax[2] = {accx.x, accx.y}, ay[2] = {accy.x, accy.y};
 #pragma unroll
@@ -1223,6 +1288,10 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
     // bodies to keep every SM's warp slots full (ncu: profiles/r01_traverse_v4_*)
     const bool exact_leaves = p.flags & BH_FLAG_EXACT_LEAVES;   // extension: generic 1-body-per-lane / FP64 kernels only
     const bool leaves_pair = exact_leaves && p.reserved[0] == 2 && !(p.flags & (BH_FLAG_COUNTERS | BH_FLAG_FP64_TRAVERSAL));
+    // exact leaves in the list kernel: on request (9) and by default from kTwoBodiesPerLaneMin bodies on (launches over an
+    // own-list — multi-rank exact leaves, host step — arrive here with reserved[0] = 1 / 2 and keep the generic / pair kernel)
+    const bool leaves_list = exact_leaves && !(p.flags & (BH_FLAG_COUNTERS | BH_FLAG_FP64_TRAVERSAL)) &&
+                             (p.reserved[0] == 9 || (p.reserved[0] == 0 && own_n >= kTwoBodiesPerLaneMin));
     const int bpl = leaves_pair ? 2 : exact_leaves ? 1 : (p.reserved[0] == 1) ? 1 : (p.reserved[0] == 2 || p.reserved[0] == 3 || p.reserved[0] == 8) ? 2 : (own_n >= kTwoBodiesPerLaneMin ? 2 : 1);
     // previous operation on the stream = tree_top_kernel (or a peer-exchange kernel; g_pdl is off there)
 #define BH_GO(K) launch_chain(K, dim3(blocks), dim3(kTravThreads), st, true, a)
@@ -1238,7 +1307,21 @@ void launch_traverse(const uint32_t* skeys, const uint32_t* sidx, const double2*
         const int64_t per_block = (int64_t)kTravThreads * bpl;
         unsigned blocks = (unsigned)((own_n + per_block - 1) / per_block);
 #define BH_TRAV(B, I, C) BH_GO((traverse_f32_kernel<B, I, C>))
-        if (leaves_pair) {
+        if (leaves_list) {      // exact leaves in the list kernel (persistent warps over 64-body tiles)
+            const bool exact = p.flags & BH_FLAG_EXACT_EPS;
+            static int resident_l = 0;
+            if (!resident_l) {
+                int dev = 0, sms = 148, per_sm = BH_LIST_MIN_BLOCKS;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, traverse_f32_list_kernel<true, false, true>, kTravThreads, 0);
+                resident_l = sms * (per_sm > 0 ? per_sm : BH_LIST_MIN_BLOCKS);
+            }
+            const unsigned tiles = (unsigned)((own_n + 63) / 64);
+            blocks = std::min<unsigned>((tiles + kTravWarps - 1) / kTravWarps, (unsigned)resident_l);
+            if (integrate) { if (exact) BH_GO((traverse_f32_list_kernel<true, true, true>)); else BH_GO((traverse_f32_list_kernel<true, false, true>)); }
+            else { if (exact) BH_GO((traverse_f32_list_kernel<false, true, true>)); else BH_GO((traverse_f32_list_kernel<false, false, true>)); }
+        } else if (leaves_pair) {
             const bool exact = p.flags & BH_FLAG_EXACT_EPS;
             if (integrate) { if (exact) BH_GO((traverse_f32_pair_kernel<true, true, true>)); else BH_GO((traverse_f32_pair_kernel<true, false, true>)); }
             else { if (exact) BH_GO((traverse_f32_pair_kernel<false, true, true>)); else BH_GO((traverse_f32_pair_kernel<false, false, true>)); }

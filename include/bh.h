@@ -74,7 +74,8 @@ typedef struct bh_params {
     int32_t rank;         /* 0 .. n_ranks-1 */
     int32_t n_ranks;      /* 1 = single GPU */
     int32_t reserved[4];  /* reserved[0]: traversal tuning knob: 0 = default, 1 / 2 = bodies per lane (2 = packed pair
-                             kernel), 3 = generic kernel with 2 bodies per lane */
+                             kernel), 3 = generic kernel with 2 bodies per lane, 9 = with BH_FLAG_EXACT_LEAVES: the
+                             list kernel's member loop */
 } bh_params;
 
 typedef struct bh_ctx bh_ctx; /* opaque; owns device memory, stream, CUDA graph, NCCL comm */

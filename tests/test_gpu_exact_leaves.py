@@ -39,14 +39,19 @@ def test_forces_match_the_oracle_extension(name):
         assert rel_rms(f[ok], want[ok]) <= 1e-5        # FP32 traversal, same bar as the reference-semantics mode
         per = np.linalg.norm(f[ok] - want[ok], axis=1) / np.maximum(np.linalg.norm(want[ok], axis=1), 1e-300)
         assert np.median(per) <= 1e-5
-    for exact_eps in (False, True):             # the pair kernel's exact-leaves path (two bodies per lane, packed)
-        with Simulation(len(mass), exact_leaves=True, bodies_per_lane=2, exact_eps=exact_eps) as sim:
-            sim.set_bodies(pos, vel, mass)
-            sim.build_tree()
-            sim.compute_forces()
-            f = sim.forces()
-            ok = np.isfinite(want).all(axis=1)
-            assert rel_rms(f[ok], want[ok]) <= 1e-5, exact_eps
+    # the pair kernel's exact-leaves path (2: two bodies per lane, packed) and the list kernel's (9: members staged in
+    # the warp-local frame)
+    for bpl in (2, 9):
+        for exact_eps in (False, True):
+            with Simulation(len(mass), exact_leaves=True, bodies_per_lane=bpl, exact_eps=exact_eps) as sim:
+                sim.set_bodies(pos, vel, mass)
+                sim.build_tree()
+                sim.compute_forces()
+                f = sim.forces()
+                ok = np.isfinite(want).all(axis=1)
+                assert rel_rms(f[ok], want[ok]) <= 1e-5, (bpl, exact_eps)
+                per = np.linalg.norm(f[ok] - want[ok], axis=1) / np.maximum(np.linalg.norm(want[ok], axis=1), 1e-300)
+                assert np.median(per) <= 1e-5, (bpl, exact_eps)
 
 
 def test_against_the_direct_sum(shipped40k):
@@ -66,8 +71,8 @@ def test_root_is_the_multi_body_leaf_and_whole_step():
     pos = rng.uniform(-1, 1, size=(n, 2)); vel = rng.uniform(-1e-4, 1e-4, size=(n, 2)); mass = rng.uniform(0.1, 0.5, size=n)
     par = oracle.default_params(max_depth=1)
     want, _ = oracle.Tree(pos, mass, par).forces_exact_leaves()
-    for fp64, tol in ((True, 1e-12), (False, 1e-5)):
-        with Simulation(n, fp64=fp64, exact_leaves=True, max_depth=1, exact_leaf_max=1 << 20) as sim:
+    for fp64, tol, bpl in ((True, 1e-12, 0), (False, 1e-5, 0), (False, 1e-5, 9)):
+        with Simulation(n, fp64=fp64, exact_leaves=True, max_depth=1, exact_leaf_max=1 << 20, bodies_per_lane=bpl) as sim:
             sim.set_bodies(pos, vel, mass)
             sim.step(1)                                # fused integrator epilogue of the exact-leaves kernels
             assert rel_rms(sim.forces(), want) <= tol
@@ -92,7 +97,7 @@ def test_multi_rank_exact_leaves_needs_the_communicator():
     assert all("nvidia" in p or "torch" in p for p in loaded), loaded
 
 
-@pytest.mark.parametrize("bodies_per_lane", [0, 2])
+@pytest.mark.parametrize("bodies_per_lane", [0, 2, 9])
 def test_whole_step_many_blocks_reads_pre_step_positions(bodies_per_lane):
     """The member loop reads OTHER bodies' positions; an in-place fused integrator in a block that finished earlier
     would hand it post-step positions (a race that a few co-resident blocks never show).  bh_step therefore runs the
