@@ -391,7 +391,9 @@ int enqueue_forces(bh_ctx* c, bool integrate, const double2* src_pos = nullptr, 
     const int64_t n_all = (c->p.n_ranks > 1 && !c->tree_full) ? (c->own_hi - c->own_lo) : c->d.n;
     g_pdl = c->pdl;
     bh_params p = c->p;
-    if (list && p.reserved[0] == 0) p.reserved[0] = n_all >= kTwoBodiesPerLaneMin ? 2 : 1;
+    // (9 = exact leaves in the list kernel: validated for whole-set launches only, so an own-list launch falls back to
+    // the pair / generic kernel like the default does)
+    if (list && (p.reserved[0] == 0 || p.reserved[0] == 9)) p.reserved[0] = n_all >= kTwoBodiesPerLaneMin ? 2 : 1;
     // Exact leaves read OTHER bodies' positions (the members of a shared cap leaf) during the walk; a fused in-place
     // integrator in a warp that finished earlier would already have moved them.  Forces first, then one integrator
     // launch over the same bodies — unless the step is out of place (reads the snapshot, writes pos / vel).
