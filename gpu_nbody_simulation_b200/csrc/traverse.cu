@@ -632,9 +632,8 @@ __device__ __forceinline__ void sts_v4_if(bool doit, uint4* p, uint32_t x, uint3
 #ifndef BH_LIST_MIN_BLOCKS
 #define BH_LIST_MIN_BLOCKS 8    // per 128 threads: <= 72 registers, 28 warps per SM
 #endif
-// Far class-A nodes without the distance offset: G M / (d^2 (d + eps)) differs from G M / d^3 by eps / d relative,
-// and a node only counts as FAR when d >= 2^25 eps (folded into the warp's far2 threshold), i.e. below half an FP32
-// ulp — one packed multiply less per far entry (3 instead of FMUL2 + FFMA2 + 2 FMUL2).  0 = round 2's expression.
+// Entries per iteration of the far partial-mask loop (its list holds ~10 entries per round: x4 measured 305 -> 302 us at
+// 1M, 824 -> 806 us at 4M) and of the near loop (~2.4 entries per round: x4 would mostly run in the remainder code).
 #ifndef BH_FARM_UNROLL
 #define BH_FARM_UNROLL 4
 #endif
@@ -642,12 +641,16 @@ __device__ __forceinline__ void sts_v4_if(bool doit, uint4* p, uint32_t x, uint3
 #define BH_NEAR_UNROLL 2
 #endif
 constexpr int kNearUnroll = BH_NEAR_UNROLL;
-constexpr int kFarMaskedUnroll = BH_FARM_UNROLL;   // entries per iteration of the far, partial-mask loop
+constexpr int kFarMaskedUnroll = BH_FARM_UNROLL;
+// Far class-A nodes without the distance offset: G M / (d^2 (d + eps)) differs from G M / d^3 by eps / d relative,
+// and a node only counts as FAR when d >= 2^25 eps (folded into the warp's far2 threshold), i.e. below half an FP32
+// ulp — one packed operation less per far entry (3 FMUL2 instead of FMUL2 + FFMA2 + 2 FMUL2): 317 -> 305 us at 1M
+// (profiles/r02_far_no_eps_ab.txt).  0 = the expression with the offset, as in the near / mixed loops.
 #ifndef BH_FAR_NO_EPS
 #define BH_FAR_NO_EPS 1
 #endif
-// LEAVES (BH_FLAG_EXACT_LEAVES with reserved[0] = 9; a separate instantiation, the production kernel's code is
-// unchanged): a multi-body leaf at the depth cap is a seventh class.  It is not staged as one monopole but queued with
+// LEAVES (BH_FLAG_EXACT_LEAVES on whole-set launches over >= kTwoBodiesPerLaneMin bodies, or reserved[0] = 9; a separate
+// instantiation, the production kernel's code is unchanged): a multi-body leaf at the depth cap is a seventh class.  It is not staged as one monopole but queued with
 // its mask; after the round's lists have been applied, its bodies are converted into the warp-local frame by one lane
 // each (32 members per pass), staged like near class-A nodes and applied to the bodies of the mask, self excluded by
 // body index — the same pair expression as the pair kernel's member loop, ~26 instead of ~45 instructions per member.
