@@ -82,3 +82,40 @@ def test_shell_scripts_parse():
     assert len(scripts) >= 6
     for s in scripts:
         assert subprocess.run(["bash", "-n", s]).returncode == 0, s
+
+
+def _bench_line(name):
+    with open(os.path.join(ROOT, "profiles", name)) as f:
+        return json.loads(next(ln for ln in f if ln.startswith("{")))
+
+
+def test_committed_bench_lines_obey_the_contract():
+    """The bench lines committed under profiles/ (printed by bench.py on B200s) carry every key of the measurement
+    contract and their numbers are consistent with each other — a guard against the docs and the evidence drifting
+    apart, and against a bench.py edit that drops a key."""
+    d = _bench_line("r02_bench_default.json")
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "accuracy"):
+        assert k in d, k
+    assert d["metric"] == bench.METRIC and d["n_gpus"] == 1 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    n = d["config"]["n_bodies"]
+    assert n == bench.BODIES_PER_GPU and "workload" in d["config"] and "model" not in d["config"]
+    assert abs(d["value"] - n / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]               # body-steps/s = N / step time
+    r = d["roofline"]
+    assert r["bound"] == "fp32" and abs(r["frac"] - r["achieved"] / r["peak"]) <= 1e-9
+    assert abs(r["achieved"] - r["interactions_per_step"] * r["flop_per_interaction"] / (r["kernel_us"] * 1e-6) / 1e12) <= 1e-6 * r["achieved"]
+    assert r["kernel_us"] * 1e-3 <= d["ms_per_step"] * 1.1
+    # (the line was printed with the ncu capture of the previous build of the same kernel: 88.5 MB; the final one: 87.8 MB)
+    assert 0.95 < r["traffic"] / bench.TRAVERSE_DRAM_BYTES_NCU < 1.05 and r["traffic"] >= 72 * n
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 40 * n and e["d2h_bytes_per_step"] == 16 * n and 0 < e["value"] < d["value"]
+    c = d["cpu_baseline"]
+    assert c["kind"] == "reference" and c["cores"] == 1 and 0 < c["value"] < 1e-3 * d["value"]
+    assert d["accuracy"]["force_rel_rms_vs_reference_tree"] <= d["accuracy"]["bar"] == 1e-5
+    assert d["gpu_launches"] > 0 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    for name, gpus in (("r02_bench_g2.json", 2), ("r02_bench_g8.json", 8)):
+        m = _bench_line(name)
+        assert m["n_gpus"] == gpus and m["scaling"] == "weak" and m["config"]["n_bodies"] == gpus * bench.BODIES_PER_GPU
+        assert m["accuracy"]["force_rel_rms_vs_reference_tree"] <= 1e-5 and m["roofline"]["frac"] > 0
+        s = m["strong"]
+        assert s and s["speedup_vs_1gpu"] > 1 and s["accuracy"]["force_rel_rms_vs_reference_tree"] <= 1e-5
